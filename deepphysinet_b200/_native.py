@@ -1,0 +1,118 @@
+"""ctypes binding of libdpn_b200.so (include/dpn_b200.h).  The library is built in-tree by
+`__graft_entry__.build()`; there is NO fallback: if it is missing or a call fails, we raise."""
+import ctypes as C
+import os
+
+import torch
+
+from .config import PhysicsConsts
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libdpn_b200.so")
+
+MODE_FP32, MODE_BF16 = 0, 1
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+WEIGHT_FIELDS = ("W1", "b1", "W2", "b2", "e", "Wd", "bd", "Wa", "ba", "Wb", "bb", "wo", "bo")
+
+
+class DpnShape(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("mode", C.c_int32),
+                ("n_norm", C.c_int64), ("seed_scale", C.c_float), ("chunk", C.c_int32)]
+
+
+class DpnConsts(C.Structure):
+    _fields_ = [("dx", C.c_double), ("dy", C.c_double), ("lat_size", C.c_int32), ("lon_size", C.c_int32),
+                ("t_span", C.c_double), ("with_clip", C.c_int32), ("pad_", C.c_int32),
+                ("mean", C.c_double * 6), ("std", C.c_double * 6), ("lo", C.c_double * 6), ("hi", C.c_double * 6),
+                ("factor", C.c_double * 6),
+                ("c_p", C.c_double), ("L", C.c_double), ("R_v", C.c_double), ("R_d", C.c_double)]
+
+
+class DpnPoints(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "y", "t", "f", "coord_pe", "coord_data", "ref")]
+
+
+class DpnWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+class DpnGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in WEIGHT_FIELDS]
+
+
+class DpnPdeOut(C.Structure):
+    _fields_ = [("loss_terms", C.c_void_p), ("vals", C.c_void_p), ("jac", C.c_void_p)]
+
+
+_lib = None
+
+EXPORTS = ("dpn_abi_version", "dpn_last_error", "dpn_workspace_bytes", "dpn_pde_fwd_bwd",
+           "dpn_decoder_fwd", "dpn_decoder_bwd", "dpn_last_launch_count")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s not built - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU/PyTorch fallback for this path)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.dpn_abi_version.restype = C.c_int
+        L.dpn_last_error.restype = C.c_size_t
+        L.dpn_last_error.argtypes = [C.c_char_p, C.c_size_t]
+        L.dpn_workspace_bytes.argtypes = [C.POINTER(DpnShape), C.POINTER(C.c_size_t)]
+        L.dpn_pde_fwd_bwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
+                                      C.POINTER(DpnWeights), C.POINTER(DpnPdeOut), C.POINTER(DpnGrads),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dpn_decoder_fwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
+                                      C.POINTER(DpnWeights), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dpn_decoder_bwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
+                                      C.POINTER(DpnWeights), C.c_void_p, C.POINTER(DpnGrads),
+                                      C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dpn_last_launch_count.restype = C.c_int
+        if L.dpn_abi_version() != 1:
+            raise RuntimeError("libdpn_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        buf = C.create_string_buffer(1024)
+        lib().dpn_last_error(buf, 1024)
+        raise RuntimeError("%s failed (code %d): %s" % (what, rc, buf.value.decode(errors="replace")))
+
+
+def make_consts(pc: PhysicsConsts) -> DpnConsts:
+    c = DpnConsts()
+    c.dx, c.dy, c.lat_size, c.lon_size = pc.dx, pc.dy, pc.lat_size, pc.lon_size
+    c.t_span, c.with_clip = float(pc.t_span if hasattr(pc, "t_span") else pc.pred_t_span), int(bool(pc.with_clip))
+    for name in ("mean", "std", "lo", "hi", "factor"):
+        arr = getattr(c, name)
+        for i, v in enumerate(getattr(pc, name)):
+            arr[i] = float(v)
+    c.c_p, c.L, c.R_v, c.R_d = pc.c_p, pc.L, pc.R_v, pc.R_d
+    return c
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws = {}
+
+
+def workspace(shape: DpnShape, device):
+    """Caller-owned scratch, cached per device and grown on demand (torch caching allocator memory)."""
+    need = C.c_size_t(0)
+    check(lib().dpn_workspace_bytes(C.byref(shape), C.byref(need)), "dpn_workspace_bytes")
+    key = (device.type, device.index)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < need.value:
+        buf = torch.empty(max(need.value, 256), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf, need.value

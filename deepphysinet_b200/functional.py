@@ -1,0 +1,208 @@
+"""torch.autograd.Function wrappers over the C ABI (include/dpn_b200.h).
+
+`PDEResidualFn` is the operator SURVEY.md 8(b) specifies: it replaces everything
+`InterfacePhysics.place_one_batch` (interface_physics.py:271-320) does per query point, and the
+double-backward graph `train_loss.backward()` (:506) would walk, with one library call that returns
+the six loss terms AND the gradients w.r.t. the 13 decoder weight tensors.  Differentiable inputs:
+the DecoderWeights tensors.  Not differentiable (as in the reference, where their .grad is never
+read): x, y, t, f, coord_data.
+"""
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import _native as N
+from .config import PhysicsConsts
+
+
+class DecoderWeights(NamedTuple):
+    """Generated tensors are [B,K,...] (per sample), static ones [K,...]; see include/dpn_b200.h."""
+    W1: torch.Tensor
+    b1: torch.Tensor
+    W2: torch.Tensor
+    b2: torch.Tensor
+    e: torch.Tensor
+    Wd: torch.Tensor
+    bd: torch.Tensor
+    Wa: torch.Tensor
+    ba: torch.Tensor
+    Wb: torch.Tensor
+    bb: torch.Tensor
+    wo: torch.Tensor
+    bo: torch.Tensor
+
+
+def _prep(t, shape=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("deepphysinet_b200 runs on CUDA (sm_100a) only - got a %s tensor; there is no CPU path" % t.device)
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    if shape is not None:
+        t = t.reshape(shape)
+    return t.contiguous()
+
+
+def _check_weights(W: DecoderWeights):
+    B, K = W.W1.shape[0], W.W1.shape[1]
+    exp = dict(W1=(B, K, 256, 192), b1=(B, K, 256), W2=(B, K, 256, 256), b2=(B, K, 256), e=(B, K, 256),
+               Wd=(K, 256, 192), bd=(K, 256), Wa=(K, 256, 256), ba=(K, 256), Wb=(K, 256, 256), bb=(K, 256),
+               wo=(K, 256), bo=(K,))
+    for name, shp in exp.items():
+        if tuple(getattr(W, name).shape) != shp:
+            raise ValueError("DecoderWeights.%s has shape %s, expected %s" % (name, tuple(getattr(W, name).shape), shp))
+    return B, K
+
+
+def _weights_struct(ws):
+    s = N.DpnWeights()
+    for name, t in zip(N.WEIGHT_FIELDS, ws):
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+def _grads_struct(gs):
+    s = N.DpnGrads()
+    for name, t in zip(N.WEIGHT_FIELDS, gs):
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+def _shape(B, Np, K, mode, n_norm=0, seed_scale=1.0, chunk=0):
+    return N.DpnShape(B=B, N=Np, K=K, mode=N.MODES[mode] if isinstance(mode, str) else int(mode),
+                      n_norm=int(n_norm), seed_scale=float(seed_scale), chunk=int(chunk))
+
+
+class PDEResidualFn(torch.autograd.Function):
+    """(total, terms[B,6]) = PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode, n_norm, want_fields, *weights)
+
+    x, y, t, f: [B,N] (or [N], [N,1] for B=1); coord_data [B,N,6].
+    total = mean over samples of the sum of the six terms (DDP sample-mean semantics);
+    terms (float64, per sample, non-differentiable) are what place_one_batch logs (:303-318).
+    Forward already runs the fused backward kernels and caches d(total)/d(weights); backward only
+    scales them by grad_output - valid because `total` is the only differentiable output.
+    """
+
+    @staticmethod
+    def forward(ctx, x, y, t, f, coord_data, consts: PhysicsConsts, mode, n_norm, want_fields, *weights):
+        W = DecoderWeights(*weights)
+        B, K = _check_weights(W)
+        if K != 6:
+            raise ValueError("the PDE residual needs all six nets (u,v,p,T,q,rho)")
+        dev = W.W1.device
+        cd = _prep(coord_data, (B, -1, 6))
+        Np = cd.shape[1]
+        xs = [_prep(a, (B, Np)) for a in (x, y, t, f)]
+        ws = [_prep(w) for w in W]
+        need_grad = any(w.requires_grad for w in weights)
+        grads = [torch.empty_like(w) for w in ws] if need_grad else None
+        terms = torch.empty(B, 6, dtype=torch.float64, device=dev)
+        vals = torch.empty(B, Np, 6, device=dev) if want_fields else None
+        jac = torch.empty(B, Np, 6, 3, device=dev) if want_fields else None
+        shape = _shape(B, Np, 6, mode, n_norm=n_norm, seed_scale=1.0 / B)
+        cst = N.make_consts(consts)
+        pts = N.DpnPoints(x=xs[0].data_ptr(), y=xs[1].data_ptr(), t=xs[2].data_ptr(), f=xs[3].data_ptr(),
+                          coord_pe=None, coord_data=cd.data_ptr(), ref=None)
+        out = N.DpnPdeOut(loss_terms=terms.data_ptr(), vals=None if vals is None else vals.data_ptr(),
+                          jac=None if jac is None else jac.data_ptr())
+        wstruct = _weights_struct(ws)
+        gstruct = _grads_struct(grads) if need_grad else None
+        wsbuf, nbytes = N.workspace(shape, dev)
+        N.check(N.lib().dpn_pde_fwd_bwd(C.byref(shape), C.byref(cst), C.byref(pts), C.byref(wstruct), C.byref(out),
+                                        C.byref(gstruct) if need_grad else None,
+                                        N.ptr(wsbuf), nbytes, N.stream_ptr()), "dpn_pde_fwd_bwd")
+        ctx.grads = grads
+        ctx.dtypes = [w.dtype for w in weights]
+        total = terms.sum(dim=1).mean().to(torch.float32)
+        ctx.mark_non_differentiable(terms)
+        if want_fields:
+            ctx.mark_non_differentiable(vals, jac)
+            return total, terms, vals, jac
+        return total, terms
+
+    @staticmethod
+    def backward(ctx, g_total, *unused):
+        if ctx.grads is None:
+            return (None,) * 22
+        gs = [(g * g_total).to(dt) for g, dt in zip(ctx.grads, ctx.dtypes)]
+        return (None,) * 9 + tuple(gs)
+
+
+class DecoderValuesFn(torch.autograd.Function):
+    """o[B,N,K] = DecoderValuesFn.apply(coord_pe, x, y, t, coord_data, ref, consts, mode, *weights)
+    Values of the K coordinate nets (variable_net.py:67-87).  Either coord_pe [B,N,192] or (x,y,t) is given."""
+
+    @staticmethod
+    def forward(ctx, coord_pe, x, y, t, coord_data, ref, consts: PhysicsConsts, mode, *weights):
+        W = DecoderWeights(*weights)
+        B, K = _check_weights(W)
+        dev = W.W1.device
+        cd = _prep(coord_data, (B, -1, 6))
+        Np = cd.shape[1]
+        pe = _prep(coord_pe, (B, Np, 192))
+        xs = [_prep(a, (B, Np)) for a in (x, y, t)]
+        rf = _prep(ref, (B, Np, K))
+        ws = [_prep(w) for w in W]
+        o = torch.empty(B, Np, K, device=dev)
+        shape = _shape(B, Np, K, mode)
+        cst = N.make_consts(consts)
+        pts = N.DpnPoints(x=N.ptr(xs[0]), y=N.ptr(xs[1]), t=N.ptr(xs[2]), f=None, coord_pe=N.ptr(pe),
+                          coord_data=cd.data_ptr(), ref=N.ptr(rf))
+        wstruct = _weights_struct(ws)
+        wsbuf, nbytes = N.workspace(shape, dev)
+        N.check(N.lib().dpn_decoder_fwd(C.byref(shape), C.byref(cst), C.byref(pts), C.byref(wstruct), N.ptr(o),
+                                        N.ptr(wsbuf), nbytes, N.stream_ptr()), "dpn_decoder_fwd")
+        ctx.saved = (pe, xs, cd, rf, ws, consts, mode, B, Np, K)
+        ctx.dtypes = [w.dtype for w in weights]
+        ctx.need = any(w.requires_grad for w in weights)
+        return o
+
+    @staticmethod
+    def backward(ctx, g_o):
+        if not ctx.need:
+            return (None,) * 21
+        pe, xs, cd, rf, ws, consts, mode, B, Np, K = ctx.saved
+        dev = g_o.device
+        grads = [torch.empty_like(w) for w in ws]
+        shape = _shape(B, Np, K, mode)
+        cst = N.make_consts(consts)
+        pts = N.DpnPoints(x=N.ptr(xs[0]), y=N.ptr(xs[1]), t=N.ptr(xs[2]), f=None, coord_pe=N.ptr(pe),
+                          coord_data=cd.data_ptr(), ref=N.ptr(rf))
+        wstruct, gstruct = _weights_struct(ws), _grads_struct(grads)
+        go = _prep(g_o, (B, Np, K))
+        wsbuf, nbytes = N.workspace(shape, dev)
+        N.check(N.lib().dpn_decoder_bwd(C.byref(shape), C.byref(cst), C.byref(pts), C.byref(wstruct), N.ptr(go),
+                                        C.byref(gstruct), N.ptr(wsbuf), nbytes, N.stream_ptr()), "dpn_decoder_bwd")
+        return (None,) * 8 + tuple(g.to(dt) for g, dt in zip(grads, ctx.dtypes))
+
+
+_DEFAULT_MODE = "bf16"
+
+
+def set_default_mode(mode: str):
+    """'bf16' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core FMA; the 1e-4 parity mode)."""
+    global _DEFAULT_MODE
+    if mode not in N.MODES:
+        raise ValueError("mode must be one of %s" % (tuple(N.MODES),))
+    _DEFAULT_MODE = mode
+
+
+def default_mode():
+    return _DEFAULT_MODE
+
+
+def pde_residual(x, y, t, f, coord_data, W: DecoderWeights, consts: Optional[PhysicsConsts] = None, mode=None,
+                 n_norm=0, want_fields=False):
+    consts = consts or PhysicsConsts()
+    return PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode or _DEFAULT_MODE, n_norm, want_fields, *W)
+
+
+def decoder_values(coord_pe, coord_data, W: DecoderWeights, ref=None, xyz=None, consts=None, mode=None):
+    """Values o [N,K] (B=1) or [B,N,K] from encoded coordinates (or raw xyz=(x,y,t))."""
+    consts = consts or PhysicsConsts()
+    x, y, t = xyz if xyz is not None else (None, None, None)
+    o = DecoderValuesFn.apply(coord_pe, x, y, t, coord_data, ref, consts, mode or _DEFAULT_MODE, *W)
+    return o[0] if coord_data.dim() == 2 else o

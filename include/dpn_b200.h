@@ -1,0 +1,147 @@
+/*
+ * dpn_b200.h - C ABI of libdpn_b200.so: the decoder-query + PDE-residual hot path of
+ * flyakon/DeepPhysiNet, hand-written for NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI / plugin layer: the boundary it offers is two Python call signatures,
+ *     PhysicsNet.forward(field_x, coord_x, coord_data, forecast_h)        DeepPhysiNet/model/physics_net.py:41-55
+ *     InterfacePhysics.place_one_batch(x, y, t, f, field_data, ...)       DeepPhysiNet/interface/interface_physics.py:271-320
+ * This library is what a ctypes binding underneath those two methods calls (INTEGRATION.md shows the
+ * stub).  Every entry point takes plain pointers and sizes; all pointers are DEVICE pointers unless
+ * the name says host; the caller owns every buffer including the workspace; nothing is allocated or
+ * synchronised inside a call; work is enqueued on the given CUDA stream.
+ *
+ * Layout conventions (all row-major, fp32 unless stated):
+ *   B  = samples (independent encoder outputs / weight sets),  N = query points per sample,
+ *   K  = coordinate nets (6 for the PDE path: u, v, p, T, q, rho = coord_data column order,
+ *        physics_net.py:49-54),  H = 256 hidden, C = 192 encoded-coordinate width.
+ *   Generated (hyper-network) tensors are per sample:  W1 [B,K,H,C]  b1 [B,K,H]  W2 [B,K,H,H]  b2 [B,K,H]
+ *   (variable_net.py:57-65) and e [B,K,H] = fore_h_fc(PE(fore_h)) (variable_net.py:75-78).
+ *   Static tensors are shared by all samples:  Wd [K,H,C] bd [K,H] (data_input_fc), Wa [K,H,H] ba [K,H]
+ *   (cat_fc1.fc.0), Wb [K,H,H] bb [K,H] (cat_fc1.fc.2), wo [K,H] bo [K] (out_fc).
+ *
+ * Return value: 0 on success, otherwise a cudaError_t-style / DPN_E_* code; dpn_last_error() gives text.
+ */
+#ifndef DPN_B200_H_
+#define DPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPN_ABI_VERSION 1
+
+#define DPN_H 256
+#define DPN_C 192
+#define DPN_MAX_NETS 6
+
+/* Arithmetic of the dense contractions. */
+enum {
+  DPN_MODE_FP32 = 0,  /* CUDA-core fp32 FMA everywhere: the 1e-4 parity mode                              */
+  DPN_MODE_BF16 = 1   /* tcgen05 kind::f16 (bf16 operands, fp32 TMEM accumulators); tolerance in DESIGN.md */
+};
+
+enum {
+  DPN_OK = 0,
+  DPN_E_INVALID = 10001,    /* bad argument (null pointer, unsupported size, misaligned buffer) */
+  DPN_E_WORKSPACE = 10002,  /* workspace too small: call dpn_workspace_bytes                    */
+  DPN_E_UNSUPPORTED = 10003 /* device is not sm_100 / mode not built                           */
+};
+
+/* Problem shape.  n_norm is the divisor of the per-sample mean (MSELoss, losses/builder.py:10): the
+ * total number of points of the sample, which exceeds N when one sample's points are sharded across
+ * GPUs (SURVEY 8(e) level 2).  seed_scale multiplies dL/d(theta) (1/B for the DDP sample mean). */
+typedef struct DpnShape {
+  int32_t B;
+  int32_t N;
+  int32_t K;
+  int32_t mode;
+  int64_t n_norm;     /* 0 -> N */
+  float seed_scale;   /* 0 -> 1 */
+  int32_t chunk;      /* points per sample processed per internal pass; 0 -> library default */
+} DpnShape;
+
+/* Geometry, normalisation and physics constants.  Defaults: configs/DeepPhysiNet_NCEP_cfg.py:64-83,
+ * :93-95,:139-148 and interface_physics.py:126,146,177,322-332.  Order of the 6-arrays: u,v,p,T,q,rho;
+ * order of factor[]: motion_u, motion_v, continuous, energy, vapor, gas. */
+typedef struct DpnConsts {
+  double dx, dy;          /* grid spacing [m]                                                     */
+  int32_t lat_size, lon_size;
+  double t_span;          /* pred_t_span [s]                                                      */
+  int32_t with_clip;      /* InterfacePhysics.with_clip (interface_physics.py:258-261)            */
+  int32_t pad_;
+  double mean[6], std[6], lo[6], hi[6];
+  double factor[6];
+  double c_p, L, R_v, R_d;
+} DpnConsts;
+
+/* Per-point inputs.  Either (x,y,t) or coord_pe is given:
+ *   x,y,t  [B*N]       physical coordinates (metres, seconds) - required for anything involving d/dx,dy,dt
+ *   coord_pe [B*N,C]   already encoded coordinates (PhysicsNet.forward surface) - values only
+ *   f      [B*N]       Coriolis parameter (dataset/physics_dataset.py:521-526); PDE path only
+ *   coord_data [B*N,6] interpolated coarse field (dataset/physics_dataset.py:477-486)
+ *   ref    [B*N,K]     residual skip; NULL -> coord_data[:, k] (physics_net.py:49-54)                */
+typedef struct DpnPoints {
+  const float *x, *y, *t, *f;
+  const float *coord_pe;
+  const float *coord_data;
+  const float *ref;
+} DpnPoints;
+
+typedef struct DpnWeights {
+  const float *W1, *b1, *W2, *b2, *e;            /* generated, per sample */
+  const float *Wd, *bd, *Wa, *ba, *Wb, *bb, *wo, *bo; /* static              */
+} DpnWeights;
+
+/* Gradients, same shapes as DpnWeights; the library OVERWRITES them (zero-fills first). */
+typedef struct DpnGrads {
+  float *W1, *b1, *W2, *b2, *e;
+  float *Wd, *bd, *Wa, *ba, *Wb, *bb, *wo, *bo;
+} DpnGrads;
+
+/* Outputs of the PDE path.
+ *   loss_terms [B,6] double: factor_e * sum_p r_e^2 / n_norm   (interface_physics.py:285-299)
+ *   vals [B*N,6]   physical values after inverse_norm (+clip)    - optional (NULL to skip)
+ *   jac  [B*N,6,3] d(vals)/d(x,y,t) as InterfacePhysics.gradient - optional (NULL to skip)            */
+typedef struct DpnPdeOut {
+  double *loss_terms;
+  float *vals;
+  float *jac;
+} DpnPdeOut;
+
+int dpn_abi_version(void);
+
+/* Copies the last error text of the calling thread into buf (NUL-terminated); returns its length. */
+size_t dpn_last_error(char *buf, size_t cap);
+
+/* Bytes of device workspace the calls below need for this shape (256-byte aligned base required). */
+int dpn_workspace_bytes(const DpnShape *shape, size_t *bytes);
+
+/* Replaces InterfacePhysics.place_one_batch (interface_physics.py:271-320) followed by
+ * train_loss.backward() (:506/:1056) for the decoder part: per sample, six residual loss terms and
+ * d(sum of terms)/d(every DpnWeights tensor) * seed_scale.  grads may be NULL (forward/loss only). */
+int dpn_pde_fwd_bwd(const DpnShape *shape, const DpnConsts *consts, const DpnPoints *pts,
+                    const DpnWeights *w, const DpnPdeOut *out, const DpnGrads *grads,
+                    void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Replaces the six VariableNet.forward calls of PhysicsNet.forward (physics_net.py:49-54,
+ * variable_net.py:67-87): normalised outputs o [B*N,K].  Values only (dense-grid inference,
+ * interface_physics.py:538-563, and the supervised margin loss :467-474). */
+int dpn_decoder_fwd(const DpnShape *shape, const DpnConsts *consts, const DpnPoints *pts,
+                    const DpnWeights *w, float *o, void *workspace, size_t workspace_bytes,
+                    void *cuda_stream);
+
+/* Backward of dpn_decoder_fwd: given d_o [B*N,K] = dL/do, writes dL/d(every DpnWeights tensor) * seed_scale. */
+int dpn_decoder_bwd(const DpnShape *shape, const DpnConsts *consts, const DpnPoints *pts,
+                    const DpnWeights *w, const float *d_o, const DpnGrads *grads,
+                    void *workspace, size_t workspace_bytes, void *cuda_stream);
+
+/* Introspection for tests and bench: number of kernels the last call on this thread launched. */
+int dpn_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPN_B200_H_ */
