@@ -25,7 +25,8 @@ class DpnConsts(C.Structure):
                 ("t_span", C.c_double), ("with_clip", C.c_int32), ("pad_", C.c_int32),
                 ("mean", C.c_double * 6), ("std", C.c_double * 6), ("lo", C.c_double * 6), ("hi", C.c_double * 6),
                 ("factor", C.c_double * 6),
-                ("c_p", C.c_double), ("L", C.c_double), ("R_v", C.c_double), ("R_d", C.c_double)]
+                ("c_p", C.c_double), ("L", C.c_double), ("R_v", C.c_double), ("R_d", C.c_double),
+                ("band_coord", C.c_float * 32), ("band_data", C.c_float * 16)]
 
 
 class DpnPoints(C.Structure):
@@ -86,13 +87,28 @@ def check(rc, what):
 def make_consts(pc: PhysicsConsts) -> DpnConsts:
     c = DpnConsts()
     c.dx, c.dy, c.lat_size, c.lon_size = pc.dx, pc.dy, pc.lat_size, pc.lon_size
-    c.t_span, c.with_clip = float(pc.t_span if hasattr(pc, "t_span") else pc.pred_t_span), int(bool(pc.with_clip))
+    c.t_span, c.with_clip = float(pc.pred_t_span), int(bool(pc.with_clip))
     for name in ("mean", "std", "lo", "hi", "factor"):
         arr = getattr(c, name)
         for i, v in enumerate(getattr(pc, name)):
             arr[i] = float(v)
     c.c_p, c.L, c.R_v, c.R_d = pc.c_p, pc.L, pc.R_v, pc.R_d
+    for i, v in enumerate(_bands(32)):
+        c.band_coord[i] = v
+    for i, v in enumerate(_bands(16)):
+        c.band_data[i] = v
     return c
+
+
+_band_cache = {}
+
+
+def _bands(n):
+    # the same torch expression the reference evaluates at module init (position_encoding.py:27) -> bit-identical
+    if n not in _band_cache:
+        from .pe import freq_bands
+        _band_cache[n] = [float(v) for v in freq_bands(n).to(torch.float32)]
+    return _band_cache[n]
 
 
 def ptr(t):

@@ -1,0 +1,166 @@
+// extern "C" surface of libdpn_b200.so (include/dpn_b200.h): argument validation, mode dispatch.
+#include <stdarg.h>
+
+#include "dpn_fp32.cuh"
+#include "dpn_tc.cuh"
+
+namespace dpn {
+
+static thread_local char g_err[1024] = "";
+thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int chunk_of(const DpnShape& s) {
+  int c = s.chunk > 0 ? s.chunk : (s.mode == DPN_MODE_FP32 ? f32::DEFAULT_CHUNK : tc::DEFAULT_CHUNK);
+  if (s.mode != DPN_MODE_FP32) c = (c + 127) / 128 * 128;
+  int n = s.mode == DPN_MODE_FP32 ? s.N : (s.N + 127) / 128 * 128;
+  return c < n ? c : (n > 0 ? n : 1);
+}
+
+static int check_shape(const DpnShape* s) {
+  if (!s) { set_error("shape is NULL"); return DPN_E_INVALID; }
+  if (s->B <= 0 || s->N <= 0 || s->K <= 0 || s->K > DPN_MAX_NETS) {
+    set_error("bad shape B=%d N=%d K=%d (need B>0, N>0, 1<=K<=6)", s->B, s->N, s->K);
+    return DPN_E_INVALID;
+  }
+  if (s->mode != DPN_MODE_FP32 && s->mode != DPN_MODE_BF16) {
+    set_error("unknown mode %d", s->mode);
+    return DPN_E_INVALID;
+  }
+  return 0;
+}
+
+static int check_device() {
+  int dev = 0;
+  cudaDeviceProp prop;
+  DPN_CUDA_OK(cudaGetDevice(&dev));
+  DPN_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("libdpn_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+    return DPN_E_UNSUPPORTED;
+  }
+  return 0;
+}
+
+static size_t ws_bytes(const DpnShape& s) {
+  const int ch = chunk_of(s);
+  return s.mode == DPN_MODE_FP32 ? f32::workspace_bytes(ch, s.K, s.B) : tc::workspace_bytes(ch, s.K, s.B);
+}
+
+static int dispatch(Job& job, void* stream) {
+  g_launches = 0;
+  int rc = check_device();
+  if (rc) return rc;
+  job.chunk = chunk_of(job.shape);
+  const size_t need = ws_bytes(job.shape);
+  if (!job.workspace || job.workspace_bytes < need) {
+    set_error("workspace too small: have %zu bytes, need %zu", job.workspace_bytes, need);
+    return DPN_E_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(job.workspace) & 255) != 0) {
+    set_error("workspace must be 256-byte aligned");
+    return DPN_E_INVALID;
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  return job.shape.mode == DPN_MODE_FP32 ? f32::run(job, st) : tc::run(job, st);
+}
+
+static int check_common(const DpnShape* s, const DpnConsts* c, const DpnPoints* p, const DpnWeights* w) {
+  int rc = check_shape(s);
+  if (rc) return rc;
+  if (!c || !p || !w) { set_error("consts / points / weights is NULL"); return DPN_E_INVALID; }
+  const void* ws[] = {w->W1, w->b1, w->W2, w->b2, w->e, w->Wd, w->bd, w->Wa, w->ba, w->Wb, w->bb, w->wo, w->bo};
+  for (const void* q : ws)
+    if (!q || (reinterpret_cast<uintptr_t>(q) & 15)) { set_error("a weight pointer is NULL or not 16-byte aligned"); return DPN_E_INVALID; }
+  if (!p->coord_data) { set_error("coord_data is NULL"); return DPN_E_INVALID; }
+  if (!p->coord_pe && !(p->x && p->y && p->t)) { set_error("need either coord_pe or x,y,t"); return DPN_E_INVALID; }
+  return 0;
+}
+
+static int check_grads(const DpnGrads* g) {
+  const void* gs[] = {g->W1, g->b1, g->W2, g->b2, g->e, g->Wd, g->bd, g->Wa, g->ba, g->Wb, g->bb, g->wo, g->bo};
+  for (const void* q : gs)
+    if (!q || (reinterpret_cast<uintptr_t>(q) & 15)) { set_error("a gradient pointer is NULL or not 16-byte aligned"); return DPN_E_INVALID; }
+  return 0;
+}
+
+}  // namespace dpn
+
+using namespace dpn;
+
+extern "C" {
+
+int dpn_abi_version(void) { return DPN_ABI_VERSION; }
+
+size_t dpn_last_error(char* buf, size_t cap) {
+  if (!buf || cap == 0) return strlen(g_err);
+  strncpy(buf, g_err, cap - 1);
+  buf[cap - 1] = 0;
+  return strlen(buf);
+}
+
+int dpn_last_launch_count(void) { return g_launches; }
+
+int dpn_workspace_bytes(const DpnShape* shape, size_t* bytes) {
+  int rc = check_shape(shape);
+  if (rc) return rc;
+  if (!bytes) { set_error("bytes is NULL"); return DPN_E_INVALID; }
+  *bytes = ws_bytes(*shape);
+  return 0;
+}
+
+int dpn_pde_fwd_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
+                    const DpnPdeOut* out, const DpnGrads* grads, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream) {
+  int rc = check_common(shape, consts, pts, w);
+  if (rc) return rc;
+  if (shape->K != 6) { set_error("the PDE residual needs K = 6 nets (u,v,p,T,q,rho), got %d", shape->K); return DPN_E_INVALID; }
+  if (!(pts->x && pts->y && pts->t && pts->f)) { set_error("the PDE path needs x, y, t and f"); return DPN_E_INVALID; }
+  if (pts->coord_pe || pts->ref) { set_error("the PDE path derives the encoding from x,y,t and the skip from coord_data"); return DPN_E_INVALID; }
+  if (!out || !out->loss_terms) { set_error("out->loss_terms is NULL"); return DPN_E_INVALID; }
+  if (grads && (rc = check_grads(grads))) return rc;
+  Job job;
+  memset(&job, 0, sizeof(job));
+  job.kind = JOB_PDE; job.shape = *shape; job.dc = make_dev_consts(*consts);
+  job.pts = pts; job.w = w; job.out = out; job.grads = grads;
+  job.workspace = workspace; job.workspace_bytes = workspace_bytes;
+  return dispatch(job, cuda_stream);
+}
+
+int dpn_decoder_fwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
+                    float* o, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  int rc = check_common(shape, consts, pts, w);
+  if (rc) return rc;
+  if (!o) { set_error("o is NULL"); return DPN_E_INVALID; }
+  if (!pts->ref && shape->K != 6) { set_error("ref may only be NULL for K = 6"); return DPN_E_INVALID; }
+  Job job;
+  memset(&job, 0, sizeof(job));
+  job.kind = JOB_DEC_FWD; job.shape = *shape; job.dc = make_dev_consts(*consts);
+  job.pts = pts; job.w = w; job.o = o;
+  job.workspace = workspace; job.workspace_bytes = workspace_bytes;
+  return dispatch(job, cuda_stream);
+}
+
+int dpn_decoder_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
+                    const float* d_o, const DpnGrads* grads, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream) {
+  int rc = check_common(shape, consts, pts, w);
+  if (rc) return rc;
+  if (!d_o || !grads) { set_error("d_o / grads is NULL"); return DPN_E_INVALID; }
+  if (!pts->ref && shape->K != 6) { set_error("ref may only be NULL for K = 6"); return DPN_E_INVALID; }
+  if ((rc = check_grads(grads))) return rc;
+  Job job;
+  memset(&job, 0, sizeof(job));
+  job.kind = JOB_DEC_BWD; job.shape = *shape; job.dc = make_dev_consts(*consts);
+  job.pts = pts; job.w = w; job.d_o = d_o; job.grads = grads;
+  job.workspace = workspace; job.workspace_bytes = workspace_bytes;
+  return dispatch(job, cuda_stream);
+}
+
+}  // extern "C"

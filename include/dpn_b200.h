@@ -75,6 +75,11 @@ typedef struct DpnConsts {
   double mean[6], std[6], lo[6], hi[6];
   double factor[6];
   double c_p, L, R_v, R_d;
+  /* fp32 frequency buffers of SineCosPE (utils/position_encoding.py:27,33): the coordinate instance
+   * (interface_physics.py:44, 32 bands) and the data instance (variable_net.py:45, 16 bands).
+   * band_coord[0] == 0 -> the library fills in 2**linspace(0,4,n) itself. */
+  float band_coord[32];
+  float band_data[16];
 } DpnConsts;
 
 /* Per-point inputs.  Either (x,y,t) or coord_pe is given:
