@@ -16,11 +16,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int chunk_of(const DpnShape& s) {
-  int c = s.chunk > 0 ? s.chunk : (s.mode == DPN_MODE_FP32 ? f32::DEFAULT_CHUNK : tc::DEFAULT_CHUNK);
-  if (s.mode != DPN_MODE_FP32) c = (c + 127) / 128 * 128;
-  int n = s.mode == DPN_MODE_FP32 ? s.N : (s.N + 127) / 128 * 128;
-  return c < n ? c : (n > 0 ? n : 1);
+static int f32_chunk(const DpnShape& s) {
+  int c = s.chunk > 0 ? s.chunk : f32::DEFAULT_CHUNK;
+  return c < s.N ? c : s.N;
+}
+
+static int tc_chunk(const DpnShape& s) {
+  int c = s.chunk > 0 ? (s.chunk + 127) / 128 * 128 : tc::default_chunk(s.B);
+  const int n = (s.N + 127) / 128 * 128;
+  return c < n ? c : n;
 }
 
 static int check_shape(const DpnShape* s) {
@@ -49,15 +53,17 @@ static int check_device() {
 }
 
 static size_t ws_bytes(const DpnShape& s) {
-  const int ch = chunk_of(s);
-  return s.mode == DPN_MODE_FP32 ? f32::workspace_bytes(ch, s.K, s.B) : tc::workspace_bytes(ch, s.K, s.B);
+  // the CUDA-core kernels also serve the pre-encoded (coord_pe) surface in bf16 mode, so that mode needs the larger of the two
+  const size_t a = f32::workspace_bytes(f32_chunk(s), s.K, s.B);
+  if (s.mode == DPN_MODE_FP32) return a;
+  const size_t b = tc::workspace_bytes(tc_chunk(s), s.K, s.B);
+  return a > b ? a : b;
 }
 
 static int dispatch(Job& job, void* stream) {
   g_launches = 0;
   int rc = check_device();
   if (rc) return rc;
-  job.chunk = chunk_of(job.shape);
   const size_t need = ws_bytes(job.shape);
   if (!job.workspace || job.workspace_bytes < need) {
     set_error("workspace too small: have %zu bytes, need %zu", job.workspace_bytes, need);
@@ -68,7 +74,9 @@ static int dispatch(Job& job, void* stream) {
     return DPN_E_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  return job.shape.mode == DPN_MODE_FP32 ? f32::run(job, st) : tc::run(job, st);
+  const bool tensor = job.shape.mode == DPN_MODE_BF16 && !job.pts->coord_pe && !job.pts->ref && job.shape.K == 6;
+  job.chunk = tensor ? tc_chunk(job.shape) : f32_chunk(job.shape);
+  return tensor ? tc::run(job, st) : f32::run(job, st);
 }
 
 static int check_common(const DpnShape* s, const DpnConsts* c, const DpnPoints* p, const DpnWeights* w) {

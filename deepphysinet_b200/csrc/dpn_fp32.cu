@@ -598,5 +598,26 @@ int run(const Job& J, cudaStream_t st) {
   return 0;
 }
 
+// ---- launch wrappers shared with the tensor-core mode (dpn_tc.cu) ----------------------------------
+int launch_prep(int B, int Kn, const DpnWeights& Wt, float* uvec, float* wo2, float* cst, float* bsum, cudaStream_t st) {
+  prep_kernel<<<Kn, 256, 0, st>>>(B, Kn, Wt.Wb, Wt.bb, Wt.wo, Wt.bo, Wt.b2, Wt.bd, Wt.e, uvec, wo2, cst, bsum);
+  DPN_LAUNCH_OK();
+  return 0;
+}
+
+int launch_residual(const DevConsts& DC, int P, const float* o, const float* od, const float* f, double inv_n,
+                    double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st) {
+  residual_kernel<<<(P + 255) / 256, 256, 0, st>>>(DC, P, o, od, f, inv_n, seed_scale, loss6, dov, dod, vals, jac);
+  DPN_LAUNCH_OK();
+  return 0;
+}
+
+int launch_finalize(int Kn, const DpnWeights& Wt, const float* vc, const float* vg, const float* sdo, const DpnGrads& G,
+                    cudaStream_t st) {
+  finalize_kernel<<<Kn, 256, 0, st>>>(Wt.Wb, Wt.bb, Wt.wo, vc, vg, sdo, G.Wb, G.bb, G.wo, G.bo);
+  DPN_LAUNCH_OK();
+  return 0;
+}
+
 }  // namespace f32
 }  // namespace dpn

@@ -53,5 +53,12 @@ size_t workspace_bytes(int P, int Kn, int B);
 int launch_gemm(const Gemm& g, int layout, int batches, cudaStream_t st);
 int run(const Job& job, cudaStream_t st);
 
+// pieces reused by the tensor-core mode
+int launch_prep(int B, int Kn, const DpnWeights& Wt, float* uvec, float* wo2, float* cst, float* bsum, cudaStream_t st);
+int launch_residual(const DevConsts& DC, int P, const float* o, const float* od, const float* f, double inv_n,
+                    double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st);
+int launch_finalize(int Kn, const DpnWeights& Wt, const float* vc, const float* vg, const float* sdo, const DpnGrads& G,
+                    cudaStream_t st);
+
 }  // namespace f32
 }  // namespace dpn

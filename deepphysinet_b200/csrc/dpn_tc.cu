@@ -1,5 +1,917 @@
+// DPN_MODE_BF16: the hot path on the 5th-generation tensor cores (tcgen05.mma kind::f16, bf16 operands,
+// fp32 accumulators in TMEM), weights streamed through shared memory with cp.async.bulk (UBLKCP) on mbarriers.
+//
+// Executed algorithm, per tile of 128 query points and per coordinate net:
+//   pass 1  G1 a1 = PE W1^T            -> h1 = relu(a1+b1), mask m1
+//           G2 c  = h1 W2^T + PE6 Wd^T -> c + (b2+bd+e);  o += 2wo.c
+//           G3 a3 = c Wa^T             -> g = relu(a3+ba), o += u.g (u = Wb^T wo: out_fc folded through cat_fc1.fc.2)
+//           G4 y  = (u*m3) Wa + 2wo    reverse sweep of the scalar output: do/dc
+//           G5 q  = y W2, qm = q*m1    do/da1
+//           G6 jin = qm W1             do/dPE  -> do/dz_c = jin . dPE_c   (the 3 Jacobian columns)
+//   residual kernel (fp64, shared with the fp32 mode) -> loss terms + seeds dL/do, dL/d(do/dz_c)
+//   pass 2  ONE combined tangent row: xt = sum_c seed_c dPE_c;  G7 ht = (xt W1^T)*m1;  G8 ct = ht W2^T;  G9 gt = (ct Wa^T)*m3
+//           Z-side rows  zp = dov PE + xt, zh = dov h1 + ht, zc = dov c + ct, gz = dov g + gt, zd = dov PE6
+//   wgrad   dW1 = qm^T zp, dW2 = y^T zh, dWa = (u*m3)^T zc, dWd = y^T zd  : K = points contractions, MN-major operands
+//   colsum  bias gradients and the two vectors the folded output layer needs (vc, vg)
+//
+// Every [128 x Kd] bf16 operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh, in shared memory and in
+// the workspace alike, so a tile written once by an epilogue is (a) the K-major A operand of the next GEMM and
+// (b) an MN-major operand of the weight-gradient contraction, and moves with plain 1-D bulk copies.
 #include "dpn_tc.cuh"
-namespace dpn { namespace tc {
-size_t workspace_bytes(int P, int Kn, int B) { return f32::workspace_bytes(P < 16384 ? P : 16384, Kn, B); }
-int run(const Job& job, cudaStream_t st) { set_error("bf16 mode not built yet"); return DPN_E_UNSUPPORTED; }
-}}
+#include "dpn_umma.cuh"
+
+namespace dpn {
+namespace tc {
+
+using namespace umma;
+
+constexpr int TP = 128;                       // points per tile = TMEM lanes
+constexpr int BLOB_H = TP * H * 2;            // 65536  [128 x 256] bf16
+constexpr int BLOB_C = TP * C * 2;            // 49152  [128 x 192] bf16
+constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of a 128-row blob
+constexpr int STAGE_BYTES = 16384;            // one K=32 chunk of a [256 x K] weight image
+constexpr int NSTAGE = 3;
+constexpr int IMG_HC = H * C * 2;             // 98304
+constexpr int IMG_HH = H * H * 2;             // 131072
+constexpr int GEN_IMG = 2 * IMG_HC + 2 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T
+constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
+constexpr int NBLOB_H = 9, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC GZ | ZP ZD
+constexpr size_t NET_TILE_BYTES = (size_t)NBLOB_H * BLOB_H + (size_t)NBLOB_C * BLOB_C;
+enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC, B_GZ };
+
+struct Work {
+  // geometry of this pass
+  int B, Kn, T;            // samples, nets, tiles per sample
+  int P;                   // valid points per sample in this pass
+  int N;                   // points per sample of the whole call (stride of the per-point inputs)
+  int p0;                  // first point of this pass
+  // weight images
+  const uint8_t* img_gen;  // [B][Kn][GEN_IMG]
+  const uint8_t* img_sta;  // [Kn][STA_IMG]
+  // epilogue vectors (fp32)
+  const float *b1, *bsum;  // [B][Kn][H]
+  const float *ba, *uvec, *wo2, *cst;   // [Kn][H], cst [Kn]
+  // per-point
+  const float* coord_data; // [B*N][6]
+  uint8_t* pe_blob;        // [B*T][BLOB_C]
+  uint8_t* pe6_blob;       // [B*T][BLOB_C]
+  float* pet;              // [B*T][C][TP] fp32 transposed coordinate features
+  uint8_t* blobs;          // [B][Kn][T][NET_TILE_BYTES]
+  float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
+  float band[NF];
+};
+
+__device__ __forceinline__ uint8_t* net_tile(const Work& w, int b, int k, int tl) {
+  return w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * NET_TILE_BYTES;
+}
+__device__ __forceinline__ uint8_t* blob_h(uint8_t* nt, int which) { return nt + (size_t)which * BLOB_H; }
+__device__ __forceinline__ uint8_t* blob_zp(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H; }
+__device__ __forceinline__ uint8_t* blob_zd(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H + BLOB_C; }
+
+// ------------------------------------------------------------------------------------------------
+// Small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+// element (r, 8*kc .. 8*kc+7) of a 128-row blob
+__device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)kc * CORE_STRIDE + (uint32_t)r * 16; }
+
+struct Pipe {            // shared-memory barriers of the fused kernels
+  uint64_t full[NSTAGE], empty[NSTAGE];
+  uint64_t a_bulk, a_epi, acc_ready, act_free;
+  uint32_t tmem_base;
+};
+
+// Producer side of the weight ring: one elected thread.
+struct Producer {
+  Pipe* pp; uint8_t* ring; uint32_t n = 0;
+  __device__ __forceinline__ void put(const uint8_t* src, uint32_t bytes) {
+    const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+    mbar_wait(&pp->empty[s], ph ^ 1);
+    mbar_arrive_expect_tx(&pp->full[s], bytes);
+    bulk_g2s(ring + s * STAGE_BYTES, src, bytes, &pp->full[s]);
+    ++n;
+  }
+  __device__ __forceinline__ void stream(const uint8_t* img, int first, int last, uint32_t bytes) {
+    for (int i = first; i < last; ++i) put(img + (size_t)i * bytes, bytes);
+  }
+};
+
+// MMA side: one elected thread.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major, Nn rows).
+struct Issuer {
+  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t n = 0;
+  __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate) {
+    const uint32_t idesc = idesc_bf16(Nn, 0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+      mbar_wait(&pp->full[s], ph);
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint64_t ad = smem_desc(act_addr + (uint32_t)(c * 4 + 2 * i) * CORE_STRIDE, CORE_STRIDE, 128);
+        const uint64_t bd = smem_desc(ring_addr + s * STAGE_BYTES + (uint32_t)(2 * i) * Nn * 16, Nn * 16, 128);
+        mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0 || i > 0) ? 1u : 0u);
+      }
+      mma_commit(&pp->empty[s]);
+      ++n;
+    }
+  }
+};
+
+__device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], 1); }
+    mbar_init(&pp->a_bulk, 1);
+    mbar_init(&pp->a_epi, TP);
+    mbar_init(&pp->acc_ready, 1);
+    mbar_init(&pp->act_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&pp->tmem_base, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+}
+
+__device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my smem writes / TMEM reads are finished
+  tc_fence_before();
+  fence_proxy_async();
+  mbar_arrive(&pp->a_epi);
+}
+
+// sign / partner of d(PE_j)/dz: PE[6f+c] = sin, PE[6f+3+c] = cos  ->  dPE[6f+c] = +band cos, dPE[6f+3+c] = -band sin
+#define DPE_PARTNER(J) (((J) % 6) < 3 ? (J) + 3 : (J)-3)
+#define DPE_SIGN(J) (((J) % 6) < 3 ? 1.0f : -1.0f)
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1: values + reverse sweep.  One CTA per tile of 128 points, loops over the nets; 2 CTAs per SM.
+// warps 0-3: epilogue (thread = point = TMEM lane), warp 4: bulk-copy producer, warp 5: MMA issuer.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int sweep) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ Pipe pipe;
+  uint8_t* act = smem;
+  uint8_t* ring = smem + BLOB_H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
+  const size_t g = blockIdx.x;                       // global tile index
+  pipe_init(&pipe, warp, tid);
+  const uint32_t tmem = pipe.tmem_base;
+
+  if (warp == 4 && lane == 0) {
+    // ---------------- producer ----------------
+    Producer pr{&pipe, ring};
+    uint32_t af = 0;
+    const uint8_t* pe_src = w.pe_blob + g * BLOB_C;
+    const uint8_t* pe6_src = w.pe6_blob + g * BLOB_C;
+    for (int k = 0; k < w.Kn; ++k) {
+      const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * GEN_IMG;
+      const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
+      const uint8_t *iW1 = gen, *iW1T = gen + IMG_HC, *iW2 = gen + 2 * IMG_HC, *iW2T = gen + 2 * IMG_HC + IMG_HH;
+      const uint8_t *iWd = sta, *iWa = sta + IMG_HC, *iWaT = sta + IMG_HC + IMG_HH;
+      pr.stream(iW1, 0, 2, STAGE_BYTES);
+      if (k > 0) { mbar_wait(&pipe.act_free, af & 1); ++af; }
+      mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
+      bulk_g2s(act, pe_src, BLOB_C, &pipe.a_bulk);
+      pr.stream(iW1, 2, 6, STAGE_BYTES);
+      pr.stream(iW2, 0, 8, STAGE_BYTES);
+      pr.stream(iWd, 0, 2, STAGE_BYTES);
+      mbar_wait(&pipe.act_free, af & 1); ++af;        // G2a has consumed h1
+      mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
+      bulk_g2s(act, pe6_src, BLOB_C, &pipe.a_bulk);
+      pr.stream(iWd, 2, 6, STAGE_BYTES);
+      pr.stream(iWa, 0, 8, STAGE_BYTES);
+      if (sweep) {
+        pr.stream(iWaT, 0, 8, STAGE_BYTES);
+        pr.stream(iW2T, 0, 8, STAGE_BYTES);
+        if (sweep > 1) pr.stream(iW1T, 0, 8, 12288);
+      }
+    }
+  } else if (warp == 5 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+    uint32_t ab = 0, ae = 0;
+    for (int k = 0; k < w.Kn; ++k) {
+      if (k > 0) { mbar_wait(&pipe.a_epi, ae & 1); ++ae; }          // last epilogue of the previous net has drained TMEM
+      mbar_wait(&pipe.a_bulk, ab & 1); ++ab; tc_fence_after();
+      is.gemm(6, H, false); mma_commit(&pipe.acc_ready);            // G1
+      mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+      is.gemm(8, H, false); mma_commit(&pipe.act_free);             // G2a
+      mbar_wait(&pipe.a_bulk, ab & 1); ++ab; tc_fence_after();
+      is.gemm(6, H, true); mma_commit(&pipe.acc_ready);             // G2b
+      mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+      is.gemm(8, H, false); mma_commit(&pipe.acc_ready);            // G3
+      if (sweep) {
+        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G4
+        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G5
+        if (sweep > 1) {
+          mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+          is.gemm(8, C, false); mma_commit(&pipe.acc_ready);        // G6
+        }
+      }
+      mma_commit(&pipe.act_free);                                   // the activation buffer may be overwritten by the next PE tile
+    }
+  } else if (warp < 4) {
+    // ---------------- epilogue ----------------
+    const int r = tid;                                              // row in tile = TMEM lane
+    const uint32_t tl_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int p_local = tl * TP + r;
+    const bool valid = p_local < w.P;
+    const size_t q = (size_t)b * w.N + w.p0 + p_local;              // index into the caller's per-point arrays
+    const size_t row = g * TP + r;                                  // index into the pass-local per-point arrays
+    const float* pet = w.pet + g * (size_t)(C * TP) + r;
+    uint32_t ar = 0;
+    float v[32];
+    for (int k = 0; k < w.Kn; ++k) {
+      uint8_t* nt = net_tile(w, b, k, tl);
+      const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+      // ---- epilogue 1: h1 = relu(a1 + b1) ----
+      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(w.b1 + vb + cb * 32) + j4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = v[j4 * 4 + e] + bb[e];
+            v[j4 * 4 + e] = fmaxf(a, 0.f);
+          }
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint4 pk = pack8(v + qd * 8);
+          const uint32_t off = piece_off(r, cb * 4 + qd);
+          *reinterpret_cast<uint4*>(act + off) = pk;
+          *reinterpret_cast<uint4*>(blob_h(nt, B_H1) + off) = pk;
+        }
+      }
+      epi_done(&pipe);
+      // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
+      float osum = 0.f;
+      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(w.bsum + vb + cb * 32) + j4);
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(w.wo2 + vk + cb * 32) + j4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float cc = v[j4 * 4 + e] + bb[e];
+            osum = fmaf(ww[e], cc, osum);
+            v[j4 * 4 + e] = cc;
+          }
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint4 pk = pack8(v + qd * 8);
+          const uint32_t off = piece_off(r, cb * 4 + qd);
+          *reinterpret_cast<uint4*>(act + off) = pk;
+          *reinterpret_cast<uint4*>(blob_h(nt, B_CC) + off) = pk;
+        }
+      }
+      epi_done(&pipe);
+      // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
+      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        tmem_ld32(tl_addr + cb * 32, v);
+        float um[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(w.ba + vk + cb * 32) + j4);
+          const float4 uv = __ldg(reinterpret_cast<const float4*>(w.uvec + vk + cb * 32) + j4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = v[j4 * 4 + e] + bb[e];
+            const float gg = fmaxf(a, 0.f);
+            osum = fmaf(uu[e], gg, osum);
+            v[j4 * 4 + e] = gg;
+            um[j4 * 4 + e] = a > 0.f ? uu[e] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint32_t off = piece_off(r, cb * 4 + qd);
+          *reinterpret_cast<uint4*>(blob_h(nt, B_GG) + off) = pack8(v + qd * 8);
+          const uint4 pk = pack8(um + qd * 8);
+          if (sweep) *reinterpret_cast<uint4*>(act + off) = pk;     // without a sweep the buffer already belongs to the next PE tile
+          *reinterpret_cast<uint4*>(blob_h(nt, B_UM) + off) = pk;
+        }
+      }
+      if (valid) w.o[row * w.Kn + k] = osum + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
+      epi_done(&pipe);
+      if (!sweep) continue;
+      // ---- epilogue 4: y = acc + 2wo ----
+      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(w.wo2 + vk + cb * 32) + j4);
+          v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint4 pk = pack8(v + qd * 8);
+          const uint32_t off = piece_off(r, cb * 4 + qd);
+          *reinterpret_cast<uint4*>(act + off) = pk;
+          *reinterpret_cast<uint4*>(blob_h(nt, B_YT) + off) = pk;
+        }
+      }
+      epi_done(&pipe);
+      // ---- epilogue 5: qm = acc * m1 ----
+      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+#pragma unroll 1
+      for (int cb = 0; cb < 8; ++cb) {
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint32_t off = piece_off(r, cb * 4 + qd);
+          float h[8];
+          unpack8(*reinterpret_cast<const uint4*>(blob_h(nt, B_H1) + off), h);   // written by this thread in epilogue 1
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[qd * 8 + e] = h[e] > 0.f ? v[qd * 8 + e] : 0.f;
+          const uint4 pk = pack8(v + qd * 8);
+          if (sweep > 1) *reinterpret_cast<uint4*>(act + off) = pk;
+          *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;
+        }
+      }
+      epi_done(&pipe);
+      if (sweep < 2) continue;
+      // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c) ----
+      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      float dz[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int ob = 0; ob < 2; ++ob) {
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+          tmem_ld32(tl_addr + ob * 96 + ib * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int Jl = ib * 32 + j;                              // column inside the 96-block
+            const float pp = __ldg(pet + (size_t)(ob * 96 + DPE_PARTNER(Jl)) * TP);
+            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * w.band[ob * 16 + Jl / 6] * v[j], pp, dz[Jl % 3]);
+          }
+        }
+      }
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) w.od[(row * w.Kn + k) * 3 + c] = dz[c];
+      }
+      epi_done(&pipe);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 2: the combined tangent row and the Z-side operands of the weight gradients.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int tangent) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ Pipe pipe;
+  uint8_t* act = smem;
+  uint8_t* ring = smem + BLOB_H;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
+  const size_t g = blockIdx.x;
+  pipe_init(&pipe, warp, tid);
+  const uint32_t tmem = pipe.tmem_base;
+
+  if (warp == 4 && lane == 0) {
+    if (tangent) {
+      Producer pr{&pipe, ring};
+      for (int k = 0; k < w.Kn; ++k) {
+        const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * GEN_IMG;
+        const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
+        pr.stream(gen, 0, 6, STAGE_BYTES);                       // W1
+        pr.stream(gen + 2 * IMG_HC, 0, 8, STAGE_BYTES);          // W2
+        pr.stream(sta + IMG_HC, 0, 8, STAGE_BYTES);              // Wa
+      }
+    }
+  } else if (warp == 5 && lane == 0) {
+    if (tangent) {
+      Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+      uint32_t ae = 0;
+      for (int k = 0; k < w.Kn; ++k) {
+        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        is.gemm(6, H, false); mma_commit(&pipe.acc_ready);          // G7
+        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G8
+        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G9
+      }
+    }
+  } else if (warp < 4) {
+    const int r = tid;
+    const uint32_t tl_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const size_t row = g * TP + r;
+    const float* pet = w.pet + g * (size_t)(C * TP) + r;
+    const uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
+    uint32_t ar = 0;
+    float v[32];
+    for (int k = 0; k < w.Kn; ++k) {
+      uint8_t* nt = net_tile(w, b, k, tl);
+      const float dv = w.dov[row * w.Kn + k];
+      float dd[3] = {0.f, 0.f, 0.f};
+      if (tangent) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];
+      }
+      // ---- prologue: xt -> activation buffer; zp, zd -> workspace ----
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {                               // 24 columns = 4 frequencies = 3 pieces per iteration
+        float pe[24], xt[24], zp[24];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) pe[j] = __ldg(pet + (size_t)(it * 24 + j) * TP);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const int J = it * 24 + j;                                  // it*24 is a multiple of 6: partner stays inside the block
+          const int jp = DPE_PARTNER(j);
+          xt[j] = dd[j % 3] * (DPE_SIGN(j) * w.band[J / 6]) * pe[jp];
+          zp[j] = fmaf(dv, pe[j], xt[j]);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 3; ++qd) {
+          const uint32_t off = piece_off(r, it * 3 + qd);
+          if (tangent) *reinterpret_cast<uint4*>(act + off) = pack8(xt + qd * 8);
+          *reinterpret_cast<uint4*>(blob_zp(nt) + off) = pack8(zp + qd * 8);
+          float d6[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(pe6 + off)), d6);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d6[e] *= dv;
+          *reinterpret_cast<uint4*>(blob_zd(nt) + off) = pack8(d6);
+        }
+      }
+      if (tangent) epi_done(&pipe);
+      // ---- epilogue 7: ht = acc*m1, zh = dv*h1 + ht ;  8: ct = acc, zc = dv*c + ct ;  9: gz = dv*g + acc*m3 ----
+#pragma unroll 1
+      for (int st = 0; st < 3; ++st) {
+        const uint8_t* src = blob_h(nt, st == 0 ? B_H1 : (st == 1 ? B_CC : B_GG));
+        uint8_t* dst = blob_h(nt, st == 0 ? B_ZH : (st == 1 ? B_ZC : B_GZ));
+        if (tangent) { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); }
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) {
+          if (tangent) {
+            tmem_ld32(tl_addr + cb * 32, v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const uint32_t off = piece_off(r, cb * 4 + qd);
+            float s[8], z[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(src + off)), s);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float t = v[qd * 8 + e];
+              if (st != 1) t = s[e] > 0.f ? t : 0.f;                  // relu masks m1 (h1 > 0) / m3 (g > 0)
+              v[qd * 8 + e] = t;
+              z[e] = fmaf(dv, s[e], t);
+            }
+            *reinterpret_cast<uint4*>(dst + off) = pack8(z);
+            if (tangent && st < 2) *reinterpret_cast<uint4*>(act + off) = pack8(v + qd * 8);
+          }
+        }
+        if (tangent && st < 2) epi_done(&pipe);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradients: D[out-half (128 lanes) x in (N cols)] += sum over points  J[p,out] Z[p,in]
+// Both operands are MN-major views of the stored [128 points x width] blobs.  One CTA per
+// (sample, net, layer, out-half, split); single smem stage, 2 CTAs per SM interleave load and MMA.
+// ------------------------------------------------------------------------------------------------
+struct WgradWork {
+  int B, Kn, T, splits;
+  const uint8_t* blobs;
+  float *gW1, *gW2, *gWa, *gWd;
+};
+
+__global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full, empty, acc_ready;
+  __shared__ uint32_t tmem_s;
+  uint8_t* sJ = smem;                 // 32 KB: 128 points x 128 out (half)
+  uint8_t* sZ = smem + BLOB_H / 2;    // up to 64 KB
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int item = blockIdx.x;
+  const int split = item % w.splits; item /= w.splits;
+  const int mh = item & 1; item >>= 1;
+  const int layer = item & 3; item >>= 2;
+  const int k = item % w.Kn, b = item / w.Kn;
+  const int Nn = (layer == 0 || layer == 3) ? C : H;
+  const uint32_t zbytes = (uint32_t)TP * Nn * 2;
+  const int jsel = layer == 0 ? B_QM : (layer == 2 ? B_UM : B_YT);
+  const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
+  if (tid == 0) {
+    mbar_init(&full, 1); mbar_init(&empty, 1); mbar_init(&acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&tmem_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_s;
+  if (t1 > t0) {
+    if (warp == 4 && lane == 0) {
+      for (int t = t0; t < t1; ++t) {
+        const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * NET_TILE_BYTES;
+        const uint8_t* zsrc = layer == 0 ? nt + (size_t)NBLOB_H * BLOB_H
+                            : layer == 3 ? nt + (size_t)NBLOB_H * BLOB_H + BLOB_C
+                            : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * BLOB_H;
+        const uint32_t i = t - t0;
+        mbar_wait(&empty, (i & 1) ^ 1);
+        mbar_arrive_expect_tx(&full, BLOB_H / 2 + zbytes);
+        bulk_g2s(sJ, nt + (size_t)jsel * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
+        bulk_g2s(sZ, zsrc, zbytes, &full);
+      }
+    } else if (warp == 5 && lane == 0) {
+      const uint32_t idesc = idesc_bf16(Nn, 1, 1);
+      for (int t = t0; t < t1; ++t) {
+        const uint32_t i = t - t0;
+        mbar_wait(&full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                              // 16 points per MMA
+          const uint64_t ad = smem_desc(smem_u32(sJ) + ks * 256, 128, CORE_STRIDE);
+          const uint64_t bd = smem_desc(smem_u32(sZ) + ks * 256, 128, CORE_STRIDE);
+          mma_bf16(tmem, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty);
+      }
+      mma_commit(&acc_ready);
+    } else if (warp < 4) {
+      mbar_wait(&acc_ready, 0);
+      tc_fence_after();
+      float* dst = layer == 0 ? w.gW1 + ((size_t)b * w.Kn + k) * H * C
+                 : layer == 1 ? w.gW2 + ((size_t)b * w.Kn + k) * H * H
+                 : layer == 2 ? w.gWa + (size_t)k * H * H
+                 : w.gWd + (size_t)k * H * C;
+      dst += (size_t)(mh * TP + tid) * Nn;
+      float v[32];
+      for (int cb = 0; cb < Nn / 32; ++cb) {
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + cb * 32 + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT helpers of the tensor-core mode
+// ------------------------------------------------------------------------------------------------
+// fp32 weight matrix [R_src x K_src] -> bf16 image in layout (*) ; transpose = image rows are source columns
+__global__ void image_kernel(const float* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
+                             size_t dst_stride, int rows, int kd, int transpose) {
+  const float* S = src + blockIdx.y * src_stride;
+  uint8_t* D = dst + blockIdx.y * dst_stride;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;             // 16-byte piece index
+  if (q >= rows * kd / 8) return;
+  const int kc = q / rows, r = q % rows;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = transpose ? S[(size_t)(kc * 8 + e) * rows + r] : S[(size_t)r * kd + kc * 8 + e];
+  *reinterpret_cast<uint4*>(D + (size_t)q * 16) = pack8(v);
+}
+
+// coordinate / data features of one tile: bf16 blobs (GEMM operands) and the fp32 transposed copy (epilogues)
+__global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Work w, const float* __restrict__ x,
+                                                    const float* __restrict__ y, const float* __restrict__ t) {
+  const size_t g = blockIdx.x;
+  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T, r = threadIdx.x;
+  const int p_local = tl * TP + r;
+  const bool valid = p_local < w.P;
+  const size_t q = (size_t)b * w.N + w.p0 + p_local;
+  float z[3] = {0.f, 0.f, 0.f}, d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    z[0] = (x[q] / K.dxf) / K.wm1; z[1] = (y[q] / K.dyf) / K.hm1; z[2] = t[q] / K.t_span;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) d[c] = w.coord_data[q * 6 + c];
+  }
+  uint8_t* pe = w.pe_blob + g * BLOB_C;
+  uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
+  float* pet = w.pet + g * (size_t)(C * TP) + r;
+  float buf[24];
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {                                   // 4 frequencies x (3 sin, 3 cos)
+#pragma unroll
+    for (int ff = 0; ff < 4; ++ff) {
+      const float band = K.band[it * 4 + ff];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float s = 0.f, co = 0.f;
+        if (valid) sincosf(z[c] * band, &s, &co);
+        buf[ff * 6 + c] = s;
+        buf[ff * 6 + 3 + c] = co;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 24; ++j) pet[(size_t)(it * 24 + j) * TP] = buf[j];
+#pragma unroll
+    for (int qd = 0; qd < 3; ++qd) *reinterpret_cast<uint4*>(pe + piece_off(r, it * 3 + qd)) = pack8(buf + qd * 8);
+  }
+#pragma unroll 1
+  for (int it = 0; it < 8; ++it) {                                   // 2 frequencies x (6 sin, 6 cos)
+#pragma unroll
+    for (int ff = 0; ff < 2; ++ff) {
+      const float band = K.band6[it * 2 + ff];
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        float s = 0.f, co = 0.f;
+        if (valid) sincosf(d[c] * band, &s, &co);
+        buf[ff * 12 + c] = s;
+        buf[ff * 12 + 6 + c] = co;
+      }
+    }
+#pragma unroll
+    for (int qd = 0; qd < 3; ++qd) *reinterpret_cast<uint4*>(pe6 + piece_off(r, it * 3 + qd)) = pack8(buf + qd * 8);
+  }
+}
+
+// Column sums over the points of one tile (block = (tile, net), 256 threads = 32 cores x 8 row phases):
+//   gb1 += dov qm, gb2 += dov y (also e, bd), gba += dov um, vc += zc, vg += gz, sdo += dov
+struct ColsumWork {
+  int B, Kn, T;
+  const uint8_t* blobs;
+  const float* dov;
+  float *gb1, *gb2, *ge, *gbd, *gba, *vc, *vg, *sdo;
+};
+
+__global__ void __launch_bounds__(256) colsum_kernel(const ColsumWork w) {
+  const int tile = blockIdx.x, k = blockIdx.y;
+  const int b = tile / w.T, tl = tile % w.T;
+  const int core = threadIdx.x >> 3, rs = threadIdx.x & 7;
+  const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * NET_TILE_BYTES;
+  const float* dv = w.dov + (size_t)tile * TP * w.Kn + k;
+  const int sel[5] = {B_QM, B_YT, B_UM, B_ZC, B_GZ};
+  float acc[5][8];
+#pragma unroll
+  for (int s = 0; s < 5; ++s)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[s][e] = 0.f;
+  float sd = 0.f;
+  for (int r = rs; r < TP; r += 8) {
+    const float wgt = dv[(size_t)r * w.Kn];
+    if (core == 0) sd += wgt;
+    const uint32_t off = piece_off(r, core);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      float v[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(nt + (size_t)sel[s] * BLOB_H + off)), v);
+      const float ww = s < 3 ? wgt : 1.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[s][e] = fmaf(ww, v[e], acc[s][e]);
+    }
+  }
+#pragma unroll
+  for (int m = 1; m < 8; m <<= 1) {
+    sd += __shfl_xor_sync(0xffffffffu, sd, m);
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[s][e] += __shfl_xor_sync(0xffffffffu, acc[s][e], m);
+  }
+  if (rs == 0) {
+    const size_t gb = ((size_t)b * w.Kn + k) * H + core * 8, sb = (size_t)k * H + core * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(w.gb1 + gb + e, acc[0][e]);
+      atomicAdd(w.gb2 + gb + e, acc[1][e]);
+      atomicAdd(w.ge + gb + e, acc[1][e]);
+      atomicAdd(w.gbd + sb + e, acc[1][e]);
+      atomicAdd(w.gba + sb + e, acc[2][e]);
+      atomicAdd(w.vc + sb + e, acc[3][e]);
+      atomicAdd(w.vg + sb + e, acc[4][e]);
+    }
+    if (core == 0) atomicAdd(w.sdo + k, sd);
+  }
+}
+
+__global__ void seed_copy_kernel(const Work w, const float* __restrict__ d_o, float scale) {
+  // values-only backward: dov[row][k] = d_o[q][k] * scale for valid rows
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (size_t)w.B * w.T * TP) return;
+  const int tile = (int)(row / TP), r = (int)(row % TP);
+  const int b = tile / w.T, tl = tile % w.T;
+  const int p_local = tl * TP + r;
+  for (int k = 0; k < w.Kn; ++k)
+    w.dov[row * w.Kn + k] = p_local < w.P ? d_o[((size_t)b * w.N + w.p0 + p_local) * w.Kn + k] * scale : 0.f;
+}
+
+__global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
+  const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (size_t)w.B * w.T * TP) return;
+  const int tile = (int)(row / TP), r = (int)(row % TP);
+  const int b = tile / w.T, tl = tile % w.T;
+  const int p_local = tl * TP + r;
+  if (p_local >= w.P) return;
+  for (int k = 0; k < w.Kn; ++k) o_out[((size_t)b * w.N + w.p0 + p_local) * w.Kn + k] = w.o[row * w.Kn + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workspace and driver
+// ------------------------------------------------------------------------------------------------
+struct Carve {
+  uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
+  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sdo;
+  size_t bytes;
+};
+
+static inline size_t al(size_t n) { return (n + 1023) & ~(size_t)1023; }
+
+static Carve carve(uint8_t* base, int chunk, int Kn, int B) {
+  Carve c;
+  const size_t T = (size_t)(chunk + TP - 1) / TP, rows = (size_t)B * T * TP;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = base + off; off += al(bytes); return p; };
+  c.img_gen = take((size_t)B * Kn * GEN_IMG);
+  c.img_sta = take((size_t)Kn * STA_IMG);
+  c.pe_blob = take((size_t)B * T * BLOB_C);
+  c.pe6_blob = take((size_t)B * T * BLOB_C);
+  c.pet = reinterpret_cast<float*>(take((size_t)B * T * C * TP * 4));
+  c.blobs = take((size_t)B * Kn * T * NET_TILE_BYTES);
+  c.o = reinterpret_cast<float*>(take(rows * Kn * 4));
+  c.od = reinterpret_cast<float*>(take(rows * Kn * 12));
+  c.dov = reinterpret_cast<float*>(take(rows * Kn * 4));
+  c.dod = reinterpret_cast<float*>(take(rows * Kn * 12));
+  c.uvec = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
+  c.wo2 = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
+  c.cst = reinterpret_cast<float*>(take((size_t)Kn * 4));
+  c.bsum = reinterpret_cast<float*>(take((size_t)B * Kn * H * 4));
+  c.vc = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
+  c.vg = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
+  c.sdo = reinterpret_cast<float*>(take((size_t)Kn * 4));
+  c.bytes = off;
+  return c;
+}
+
+int default_chunk(int B) {
+  int c = DEFAULT_POINTS_IN_FLIGHT / (B > 0 ? B : 1);
+  c = c / TP * TP;
+  return c < TP ? TP : c;
+}
+
+size_t workspace_bytes(int chunk, int Kn, int B) { return carve(nullptr, chunk, Kn, B).bytes; }
+
+static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
+  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; };
+  const Spec specs[] = {
+      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen},                          // W1  : rows = out, k = in
+      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen},                     // W1T : rows = in,  k = out
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen},
+      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta},
+      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta},
+      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta},
+  };
+  for (const Spec& s : specs) {
+    const int pieces = s.rows * s.kd / 8;
+    image_kernel<<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff, s.dstride,
+                                                                        s.rows, s.kd, s.tr);
+    DPN_LAUNCH_OK();
+  }
+  return 0;
+}
+
+int run(const Job& J, cudaStream_t st) {
+  const int B = J.shape.B, N = J.shape.N, Kn = J.shape.K, chunk = J.chunk;
+  if (J.pts->coord_pe) {
+    set_error("bf16 mode derives the coordinate encoding from x,y,t; pre-encoded coord_pe is served by the fp32 kernels");
+    return DPN_E_UNSUPPORTED;
+  }
+  static bool attr_done = false;
+  const int smem_fused = BLOB_H + NSTAGE * STAGE_BYTES;             // 114688
+  const int smem_wgrad = BLOB_H / 2 + BLOB_H;                        // 98304
+  if (!attr_done) {
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+    DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
+    attr_done = true;
+  }
+  Carve c = carve(reinterpret_cast<uint8_t*>(J.workspace), chunk, Kn, B);
+  const DpnWeights& Wt = *J.w;
+  const bool pde = J.kind == JOB_PDE;
+  const bool want_bwd = J.grads != nullptr;
+  const int sweep = pde ? 2 : (J.kind == JOB_DEC_BWD ? 1 : 0);
+  const double inv_n = 1.0 / (double)(J.shape.n_norm > 0 ? J.shape.n_norm : N);
+  const double seed_scale = J.shape.seed_scale != 0.f ? (double)J.shape.seed_scale : 1.0;
+  int rc;
+  if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
+  if ((rc = make_images(Wt, c, B, Kn, st))) return rc;
+  if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
+  if (want_bwd) {
+    const DpnGrads& G = *J.grads;
+    const size_t BKn = (size_t)B * Kn;
+    DPN_CUDA_OK(cudaMemsetAsync(G.W1, 0, BKn * H * C * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.b1, 0, BKn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.W2, 0, BKn * H * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.b2, 0, BKn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.e, 0, BKn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.Wd, 0, (size_t)Kn * H * C * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.bd, 0, (size_t)Kn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.Wa, 0, (size_t)Kn * H * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(G.ba, 0, (size_t)Kn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(c.vc, 0, (size_t)Kn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(c.vg, 0, (size_t)Kn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(c.sdo, 0, (size_t)Kn * 4, st));
+  }
+  for (int p0 = 0; p0 < N; p0 += chunk) {
+    const int P = min(chunk, N - p0);
+    const int T = (P + TP - 1) / TP;
+    const size_t rows = (size_t)B * T * TP;
+    Work w;
+    memset(&w, 0, sizeof(w));
+    w.B = B; w.Kn = Kn; w.T = T; w.P = P; w.N = N; w.p0 = p0;
+    w.img_gen = c.img_gen; w.img_sta = c.img_sta;
+    w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst;
+    w.coord_data = J.pts->coord_data;
+    w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
+    w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
+    memcpy(w.band, J.dc.band, sizeof(w.band));
+    const int tiles = B * T;
+    encode_kernel<<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
+    DPN_LAUNCH_OK();
+    pass1_kernel<<<tiles, 192, smem_fused, st>>>(w, sweep);
+    DPN_LAUNCH_OK();
+    if (J.kind == JOB_DEC_FWD) {
+      gather_o_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.o);
+      DPN_LAUNCH_OK();
+      continue;
+    }
+    if (want_bwd || pde) {
+      DPN_CUDA_OK(cudaMemsetAsync(c.dov, 0, rows * Kn * 4, st));
+      DPN_CUDA_OK(cudaMemsetAsync(c.dod, 0, rows * Kn * 12, st));
+    }
+    if (pde) {
+      for (int b = 0; b < B; ++b) {
+        const size_t r0 = (size_t)b * T * TP, q0 = (size_t)b * N + p0;
+        if ((rc = f32::launch_residual(J.dc, P, c.o + r0 * 6, c.od + r0 * 18, J.pts->f + q0, inv_n, seed_scale,
+                                       J.out->loss_terms + (size_t)b * 6, c.dov + r0 * 6, c.dod + r0 * 18,
+                                       J.out->vals ? J.out->vals + q0 * 6 : nullptr,
+                                       J.out->jac ? J.out->jac + q0 * 18 : nullptr, st)))
+          return rc;
+      }
+    } else {
+      seed_copy_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.d_o, (float)seed_scale);
+      DPN_LAUNCH_OK();
+    }
+    if (!want_bwd) continue;
+    const DpnGrads& G = *J.grads;
+    pass2_kernel<<<tiles, 192, smem_fused, st>>>(w, pde ? 1 : 0);
+    DPN_LAUNCH_OK();
+    WgradWork ww;
+    ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs;
+    ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
+    const int items = B * Kn * 8;
+    int splits = (2 * 148 * 2 + items - 1) / items;
+    if (splits > T) splits = T;
+    if (splits < 1) splits = 1;
+    ww.splits = splits;
+    wgrad_kernel<<<items * splits, 192, smem_wgrad, st>>>(ww);
+    DPN_LAUNCH_OK();
+    ColsumWork cw;
+    cw.B = B; cw.Kn = Kn; cw.T = T; cw.blobs = c.blobs; cw.dov = c.dov;
+    cw.gb1 = G.b1; cw.gb2 = G.b2; cw.ge = G.e; cw.gbd = G.bd; cw.gba = G.ba; cw.vc = c.vc; cw.vg = c.vg; cw.sdo = c.sdo;
+    colsum_kernel<<<dim3(tiles, Kn), 256, 0, st>>>(cw);
+    DPN_LAUNCH_OK();
+  }
+  if (want_bwd) {
+    if ((rc = f32::launch_finalize(Kn, Wt, c.vc, c.vg, c.sdo, *J.grads, st))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace tc
+}  // namespace dpn

@@ -5,9 +5,10 @@
 namespace dpn {
 namespace tc {
 
-constexpr int DEFAULT_CHUNK = 131072;   // points per sample per pass (multiple of 128)
+constexpr int DEFAULT_POINTS_IN_FLIGHT = 262144;   // B * chunk: bounds the workspace (~34 KB per point)
 
-size_t workspace_bytes(int P, int Kn, int B);
+int default_chunk(int B);                          // points per sample per pass (multiple of 128)
+size_t workspace_bytes(int chunk, int Kn, int B);
 int run(const Job& job, cudaStream_t st);
 
 }  // namespace tc

@@ -1,0 +1,69 @@
+"""GPU (-m gpu): the tcgen05 (bf16 operand) mode against the fp64 CPU oracle.
+
+Stated tolerance of this mode: operands are rounded to bf16 (8-bit mantissa) before every
+tensor-core contraction, accumulation is fp32 in TMEM, everything else (biases, masks, folded output layer,
+residual physics, loss sums) is fp32/fp64.  Emulating exactly that rounding on the CPU (oracle/closed_form.py,
+rnd=bf16_round) gives 0.2 % on values, 2-4 % on the Jacobian and 0.3-7 % on weight gradients at N ~ 200 points;
+the bounds below are those figures with head-room.  The 1e-4 parity claim belongs to the fp32 mode only.
+"""
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(vals=2e-2, jac=1e-1, terms=0.2, grad=0.2)
+
+
+def _cmp(**kw):
+    from deepphysinet_b200 import testing as T
+    W, pts = T.random_decoder_weights(device="cuda", **kw)
+    rep = T.compare_with_oracle(W, pts, mode="bf16")
+    assert rep["vals_rel"] < TOL["vals"], rep
+    assert rep["jac_rel"] < TOL["jac"], rep
+    assert rep["terms_rel"] < TOL["terms"], rep
+    assert rep["grad_rel_max"] < TOL["grad"], rep
+    return rep
+
+
+@pytest.mark.parametrize("N", [1, 100, 128, 700])
+def test_bf16_random_weights_ragged_sizes(N):
+    _cmp(B=1, N=N, seed=N)
+
+
+def test_bf16_batch_of_samples():
+    _cmp(B=3, N=300, seed=21)
+
+
+def test_bf16_close_to_fp32_mode_and_emulation():
+    """The tensor-core mode must agree with the CPU emulation of its own rounding far better than with exact math."""
+    from deepphysinet_b200 import functional as Fn, testing as T
+    from oracle import closed_form as CF
+    W, pts = T.random_decoder_weights(B=1, N=256, seed=9, device="cuda")
+    got = T.run_library(W, pts, mode="bf16")
+    names = Fn.DecoderWeights._fields
+    Wb = {n: (w[0] if n in ("W1", "b1", "W2", "b2", "e") else w).double().cpu() for n, w in zip(names, W)}
+    col = lambda k: pts[k][0].double().cpu().reshape(-1, 1)
+    losses, G, vals, jac = CF.pde_fwd_bwd(col("x"), col("y"), col("t"), col("f"), pts["coord_data"][0].double().cpu(), Wb,
+                                          rnd=CF.bf16_round)
+    assert H.rel(got["vals"][0].cpu(), vals) < 2e-3
+    assert H.rel(got["jac"][0].cpu(), jac) < 2e-2
+    for n, g in zip(names, got["grads"]):
+        gb = g[0] if n in ("W1", "b1", "W2", "b2", "e") else g
+        assert H.rel(gb.cpu(), G[n]) < 5e-2, n
+
+
+def test_bf16_chunking_is_invisible():
+    from deepphysinet_b200 import functional as Fn, testing as T
+    W, pts = T.random_decoder_weights(B=2, N=600, seed=3, device="cuda")
+    a = T.run_library(W, pts, mode="bf16")
+    orig = Fn._shape
+    try:
+        Fn._shape = lambda *args, **kw: orig(*args, **{**kw, "chunk": 256})
+        b = T.run_library(W, pts, mode="bf16")
+    finally:
+        Fn._shape = orig
+    assert torch.allclose(a["terms"], b["terms"], rtol=1e-6)
+    for ga, gb in zip(a["grads"], b["grads"]):
+        assert H.rel(ga.cpu(), gb.cpu()) < 1e-4

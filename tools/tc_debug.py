@@ -1,0 +1,112 @@
+"""Stage-by-stage comparison of the tcgen05 path against the CPU closed form with bf16 operand rounding
+(oracle/closed_form.py, rnd=bf16_round).  Reads the library's workspace blobs back, so a single GPU run
+tells which GEMM / epilogue first goes wrong.   python tools/tc_debug.py [N] [B]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from deepphysinet_b200 import _native as Nat, functional as Fn, testing as T   # noqa: E402
+from oracle import closed_form as CF                                            # noqa: E402
+
+TP, H, C = 128, 256, 192
+BLOB_H, BLOB_C = TP * H * 2, TP * C * 2
+GEN_IMG, STA_IMG = 2 * H * C * 2 + 2 * H * H * 2, H * C * 2 + 2 * H * H * 2
+NET_TILE = 9 * BLOB_H + 2 * BLOB_C
+NAMES_H = ["h1", "c", "g", "um", "yv", "qm", "zh", "zc", "gz"]
+
+
+def al(n):
+    return (n + 1023) & ~1023
+
+
+def carve(chunk, Kn, B):
+    Tn = (chunk + TP - 1) // TP
+    rows = B * Tn * TP
+    off, out = 0, {}
+    for name, size in [("img_gen", B * Kn * GEN_IMG), ("img_sta", Kn * STA_IMG), ("pe", B * Tn * BLOB_C),
+                       ("pe6", B * Tn * BLOB_C), ("pet", B * Tn * C * TP * 4), ("blobs", B * Kn * Tn * NET_TILE),
+                       ("o", rows * Kn * 4), ("od", rows * Kn * 12), ("dov", rows * Kn * 4), ("dod", rows * Kn * 12)]:
+        out[name] = (off, size)
+        off += al(size)
+    return out, Tn
+
+
+def blob_to_matrix(raw, width):
+    """raw: uint8 tensor of TP*width*2 bytes in layout (*) -> [TP, width] float64"""
+    t = raw.view(torch.bfloat16).reshape(width // 8, TP, 8)       # [k-core][row][8]
+    return t.permute(1, 0, 2).reshape(TP, width).double()
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    W, pts = T.random_decoder_weights(B=B, N=N, seed=5, device="cuda")
+    got = T.run_library(W, pts, mode="bf16")
+    torch.cuda.synchronize()
+    ref32 = T.run_library(W, pts, mode="fp32")
+    print("bf16 terms", got["terms"].tolist())
+    print("fp32 terms", ref32["terms"].tolist())
+    ws = Nat._ws[("cuda", torch.cuda.current_device())].cpu()
+    lay, Tn = carve((N + TP - 1) // TP * TP, 6, B)
+    names = Fn.DecoderWeights._fields
+    for b in range(B):
+        Wb = {n: (w[b] if n in ("W1", "b1", "W2", "b2", "e") else w).double().cpu() for n, w in zip(names, W)}
+        col = lambda k: pts[k][b].double().cpu().reshape(-1, 1)
+        losses, G, vals, jac, stg = CF.pde_fwd_bwd(col("x"), col("y"), col("t"), col("f"), pts["coord_data"][b].double().cpu(),
+                                                   Wb, rnd=CF.bf16_round, return_stages=True, n_total=N)
+        if B > 1:
+            print("NOTE: closed-form seeds are not scaled by 1/B; compare shapes only for b>0")
+        print("sample %d  emulated terms %s" % (b, losses.tolist()))
+        rows = slice(b * Tn * TP, b * Tn * TP + N)
+        o = ws[lay["o"][0]:lay["o"][0] + lay["o"][1]].view(torch.float32).reshape(-1, 6)[rows].double()
+        od = ws[lay["od"][0]:lay["od"][0] + lay["od"][1]].view(torch.float32).reshape(-1, 6, 3)[rows].double()
+        dov = ws[lay["dov"][0]:lay["dov"][0] + lay["dov"][1]].view(torch.float32).reshape(-1, 6)[rows].double()
+        dod = ws[lay["dod"][0]:lay["dod"][0] + lay["dod"][1]].view(torch.float32).reshape(-1, 6, 3)[rows].double()
+        print("  o   rel per net", [round(rel(o[:, k], stg["o"][:, k]), 5) for k in range(6)])
+        print("  od  rel per net", [round(rel(od[:, k], stg["od"][:, k]), 5) for k in range(6)])
+        print("  dov rel per net", [round(rel(dov[:, k] * B, stg["dov"][:, k]), 5) for k in range(6)])
+        print("  dod rel per net", [round(rel(dod[:, k] * B, stg["dod"][:, k]), 5) for k in range(6)])
+        for tl in range(Tn):
+            r0, r1 = tl * TP, min(N, (tl + 1) * TP)
+            nv = r1 - r0
+            base = lay["pe"][0] + (b * Tn + tl) * BLOB_C
+            pe = blob_to_matrix(ws[base:base + BLOB_C], C)[:nv]
+            base = lay["pe6"][0] + (b * Tn + tl) * BLOB_C
+            pe6 = blob_to_matrix(ws[base:base + BLOB_C], C)[:nv]
+            print("  tile %d: pe %.4g pe6 %.4g" % (tl, rel(pe, stg["pe"][r0:r1]), rel(pe6, stg["pe6"][r0:r1])))
+            for k in range(6):
+                nt = lay["blobs"][0] + ((b * 6 + k) * Tn + tl) * NET_TILE
+                line = []
+                for i, nm in enumerate(NAMES_H):
+                    m = blob_to_matrix(ws[nt + i * BLOB_H: nt + (i + 1) * BLOB_H], H)[:nv]
+                    refm = stg["nets"][k][nm][r0:r1]
+                    if nm in ("zh", "zc", "gz"):
+                        m = m * B
+                    line.append("%s %.3g" % (nm, rel(m, refm)))
+                zp = blob_to_matrix(ws[nt + 9 * BLOB_H: nt + 9 * BLOB_H + BLOB_C], C)[:nv] * B
+                zd = blob_to_matrix(ws[nt + 9 * BLOB_H + BLOB_C: nt + 9 * BLOB_H + 2 * BLOB_C], C)[:nv] * B
+                line.append("zp %.3g" % rel(zp, stg["nets"][k]["zp"][r0:r1]))
+                line.append("zd %.3g" % rel(zd, dov_ref(stg, k)[r0:r1] * stg["pe6"][r0:r1]))
+                print("    net %d: %s" % (k, "  ".join(line)))
+        if b == 0:
+            print("  grads vs emulation / vs fp32 mode:")
+            for n, g, r32 in zip(names, got["grads"], ref32["grads"]):
+                gb = g[b] if n in ("W1", "b1", "W2", "b2", "e") else g
+                rb = r32[b] if n in ("W1", "b1", "W2", "b2", "e") else r32
+                e = rel(gb.double().cpu() * (B if n in ("W1", "b1", "W2", "b2", "e") else 1), G[n]) if B == 1 else float("nan")
+                print("    %-3s emu %.4g   fp32 %.4g" % (n, e, rel(gb.double().cpu(), rb.double().cpu())))
+    print("vals bf16 vs fp32:", rel(got["vals"].double().cpu(), ref32["vals"].double().cpu()),
+          " jac:", rel(got["jac"].double().cpu(), ref32["jac"].double().cpu()))
+
+
+def dov_ref(stg, k):
+    return stg["dov"][:, k:k + 1]
+
+
+if __name__ == "__main__":
+    main()
