@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the decoder-query + PDE-residual hot path on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3                # our arm, 1 GPU
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N   # our arm, N GPUs (weak scaling)
+    python bench.py --impl reference --steps K --warmup W          # the reference's CPU path (oracle port)
+
+Metric (BASELINE.json): PDE-residual query points/sec for forward + Jacobian + residual + backward on the
+0.25 degree configuration (145x257 grid geometry, batch 8, 65 536 query points per sample).  A "step" is one
+call of the fused operator on one batch of synthetic inputs.
+
+  value  whole-job points/s with inputs resident in HBM: one dpn_pde_fwd_bwd call per step and rank (all its
+         kernels), plus, for N > 1, the NCCL all-reduce of the decoder parameter gradients the call produced.
+  e2e    the same metric through the reference-facing API, InterfacePhysics.place_one_batch(host tensors):
+         pinned host -> device copies of every per-step input, PyTorch encoder + hyper-network, fused operator,
+         backward through hyper-network and encoder, gradient all-reduce (N > 1), loss.item().
+  roofline / cpu_baseline / clocks: see DESIGN.md section 7.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_FLOP_PER_POINT = 31.89e6      # fwd + Jacobian + bwd, GEMM work only
+EXEC_FLOP_PER_POINT = 6 * 2 * (407040 + 179200 + 228352)   # what the kernels issue
+METRIC = "pde_residual_query_points_per_sec_fwd_jacobian_bwd"
+UNIT = "points/s"
+
+META_CFG = dict(name="TransformerNet", enc_in=2405, c_out=256, d_model=256, n_heads=8, e_layers=4, d_ff=256,
+                dropout=0.5, activation="gelu", output_attention=False)
+NET_CFG = dict(name="PhysicsNet", in_channels=192, hidden_channels=256, out_channels=1, token_num=159,
+               learnable_token_num=256)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(bf16=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1400.0))),
+                    bf16_burst=float(d.get("bf16_tflops", 1590.0)), hbm=float(d.get("hbm_gbs", 6650.0)), source="measured")
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False):
+    """The reference's CPU path: oracle port (oracle/dpn_oracle.py, an autograd restatement of
+    InterfacePhysics.place_one_batch pinned to the reference's golden vectors) + the PyTorch encoder, all host
+    threads, one sample of n_points query points per step, backward included."""
+    import torch
+    from deepphysinet_b200.physics_net import PhysicsNet
+    from oracle import dpn_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    net = PhysicsNet(META_CFG, NET_CFG)
+    gen = torch.Generator().manual_seed(1234)
+    x, y, t, f, cd = O.synthetic_points(n_points, gen)
+    field = torch.randn(1, 159, 2405, generator=gen)
+    fh = torch.tensor([[[24.0 / 360.0]]])
+    params = O.split_params(dict(net.named_parameters()))
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        meta = net.meta_net(field, fh)
+        total, _ = O.place_one_batch(x, y, t, f, cd, fh, meta, params)
+        total.backward()
+        return float(total.detach())
+
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    if as_baseline:
+        best = min(times)
+        return dict(value=n_points / best, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                    sample="B=1 x %d query points of the same workload, fwd+bwd incl. encoder, best of %d after %d warm-up"
+                           % (n_points, steps, warmup))
+    mean = sum(times) / len(times)
+    val = n_points / mean
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": steps, "warmup": warmup,
+            "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "configs[1] 0.25deg grid (145x257), batch 8 x 65536 query points - bounded CPU sample per step",
+                       "sample_points_per_step": n_points},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "B=1 x %d query points per step, fwd+bwd incl. encoder" % n_points},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if emit:
+        print(json.dumps(line))
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--points", type=int, default=65536)
+    ap.add_argument("--cpu-points", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-modes", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            cpu_reference_arm(args.steps, args.warmup, args.cpu_points)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    ge.build()
+    from deepphysinet_b200 import InterfacePhysics, functional as Fn, parallel as P, _native as Nat
+    from deepphysinet_b200.config import DEFAULT_LOSS_FACTOR, DEFAULT_OBS_NORM
+
+    rank, local_rank, world = P.init_from_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.backends.cudnn.allow_tf32 = False
+    B, Np = args.batch, args.points
+
+    obs = {k: dict(v, norm_type="mean_norm", use_norm=True) for k, v in DEFAULT_OBS_NORM.items()}
+    torch.manual_seed(0)                                               # identical replicas on every rank
+    model = InterfacePhysics(META_CFG, NET_CFG, obs, None, dict(img_size=(145, 257), dx=27000, dy=27000)).to(dev)
+    model.mode = args.mode
+    consts = model.consts(DEFAULT_LOSS_FACTOR)
+
+    # synthetic inputs per SURVEY 8(d), per-rank seed (each rank owns B different samples: weak scaling)
+    g = torch.Generator().manual_seed(100 + rank)
+    hx = (torch.rand(B, Np, generator=g) * 256 * 27000.0).pin_memory()
+    hy = torch.rand(B, Np, generator=g) * 144
+    hf = (2 * 7.29e-5 * torch.sin((18.0 + hy * 0.25) / 180 * 3.141592653589793)).pin_memory()
+    hy = (hy * 27000.0).pin_memory()
+    ht = (torch.randint(0, 25, (B, Np), generator=g).float() * 3600.0).pin_memory()
+    hcd = (0.5 * torch.randn(B, Np, 6, generator=g)).pin_memory()
+    hfield = torch.randn(B, 159, 2405, generator=g).pin_memory()
+    hfh = torch.full((B, 1, 1), 24.0 / 360.0).pin_memory()
+    dx_, dy_, dt_, df_, dcd = (a.to(dev) for a in (hx, hy, ht, hf, hcd))
+    with torch.no_grad():
+        W = model.physics_net.decoder_weights(hfield.to(dev), hfh.to(dev))
+    leaves = [w.detach().clone().requires_grad_(True) for w in W]
+    static_idx = [5, 6, 7, 8, 9, 10, 11, 12]                           # Wd bd Wa ba Wb bb wo bo: parameter gradients
+    n_static = sum(leaves[i].numel() for i in static_idx)
+    flat = torch.zeros(n_static + 6, device=dev)
+
+    holder = {}
+
+    def op_step():
+        total, terms = Fn.pde_residual(dx_, dy_, dt_, df_, dcd, Fn.DecoderWeights(*leaves), consts=consts, mode=args.mode)
+        holder["launches"] = Nat.lib().dpn_last_launch_count()
+        if world > 1:
+            grads = total.grad_fn.grads if hasattr(total.grad_fn, "grads") else None
+            off = 0
+            if grads is not None:
+                for i in static_idx:
+                    n = grads[i].numel()
+                    flat[off:off + n].copy_(grads[i].reshape(-1))
+                    off += n
+            flat[n_static:].copy_(terms.mean(0).float())
+            dist.all_reduce(flat)
+        return total
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return P.allreduce_max(e0.elapsed_time(e1) / steps, dev)
+
+    with ClockSampler(local_rank) as clk:
+        ms = timed(op_step, args.steps, args.warmup)
+    clocks = clk.summary()
+    pts_step = B * Np * world
+    value = pts_step / (ms * 1e-3)
+
+    # ---- e2e through the reference-facing API, host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        reducer = P.FlatGradAllReduce(model.physics_net.parameters())
+        crit = torch.nn.MSELoss()
+
+        def e2e_step():
+            model.physics_net.zero_grad(set_to_none=True)
+            loss = model.place_one_batch(hx, hy, ht, hf, hfield, hcd, hfh, crit, DEFAULT_LOSS_FACTOR, 0, rank, dev)
+            loss.backward()
+            reducer()
+            return loss.item()
+
+        e_steps = max(3, min(args.steps, 10))
+        ms_e = timed(e2e_step, e_steps, 3)
+        h2d = sum(a.numel() * a.element_size() for a in (hx, hy, ht, hf, hcd, hfield, hfh))
+        e2e = {"value": pts_step / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e, "steps": e_steps,
+               "api": "InterfacePhysics.place_one_batch(host tensors) + backward + grad all-reduce + loss.item()"}
+
+    # ---- the 1e-4 parity mode, for the record (fewer steps) ----
+    modes = {}
+    if rank == 0 and world == 1 and args.mode == "bf16" and not args.no_modes:
+        def f32_step():
+            return Fn.pde_residual(dx_, dy_, dt_, df_, dcd, Fn.DecoderWeights(*leaves), consts=consts, mode="fp32")[0]
+        for _ in range(2):
+            f32_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            f32_step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms32 = e0.elapsed_time(e1) / 3
+        modes["fp32"] = {"value": B * Np / (ms32 * 1e-3), "unit": UNIT, "ms_per_step": ms32,
+                         "note": "CUDA-core fp32 mode: the one that carries the 1e-4 parity claim"}
+
+    pk = peaks()
+    per_gpu_pts = B * Np / (ms * 1e-3)
+    achieved = ALGO_FLOP_PER_POINT * per_gpu_pts / 1e12
+    roof_file = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    traffic = None
+    if os.path.exists(roof_file):
+        try:
+            traffic = json.load(open(roof_file)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
+                "traffic": traffic,
+                "kernel": "dpn_pde_fwd_bwd: all kernels of one call (pass1 / pass2 / wgrad tcgen05 kernels + encode, residual, colsum)",
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
+                "algorithmic_flop_per_point": ALGO_FLOP_PER_POINT, "executed_flop_per_point": EXEC_FLOP_PER_POINT,
+                "executed_tflops": EXEC_FLOP_PER_POINT * per_gpu_pts / 1e12}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference_arm(3, 1, args.cpu_points, emit=False, as_baseline=True)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "configs[1]: 0.25deg grid (145x257, dx=dy=27km), batch %d x %d query points per GPU, "
+                                       "fwd + Jacobian + 6 residual terms + bwd" % (B, Np),
+                           "batch_per_gpu": B, "points_per_sample": Np, "mode": args.mode,
+                           "parallelism": "dp%d (samples sharded, NCCL grad all-reduce)" % world,
+                           "l2": "per-step working set (%.1f GB workspace) >> 126 MB L2; no flush needed" %
+                                 (Nat.workspace(Fn._shape(B, Np, 6, args.mode), dev)[1] / 2 ** 30)},
+                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+                "gpu_launches": int(holder.get("launches", 0)) * args.steps, "modes": modes}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,18 +84,19 @@ def test_fp32_place_one_batch_matches_reference_golden(name):
     np.testing.assert_allclose(loss.item(), case["total64"], rtol=TOL_FP32)
     np.testing.assert_allclose(m.last_terms[0].cpu().numpy(), case["terms64"], rtol=TOL_FP32)
     grads = dict(m.physics_net.named_parameters())
-    gnorm = float(np.sqrt((case["grad_norm64"] ** 2).sum()))
     worst = 0.0
-    for k, n64 in zip(case["grad_names"], case["grad_norm64"]):
+    for k, n64, ref_noise in zip(case["grad_names"], case["grad_norm64"], case["grad_ref32_vs_ref64"]):
         g = grads[str(k)].grad.double().cpu()
         ref = torch.from_numpy(case["g64/" + str(k)])
-        got = g if g.numel() <= 4096 else g.flatten()[::997]
-        err = (got.reshape(ref.shape) - ref).norm().item()
-        # relative per tensor where the tensor carries signal, absolute-vs-global otherwise
-        # (key_projection.bias gradients are analytically zero; the reference's own fp32 value is noise there)
-        denom = max(ref.norm().item(), 1e-6 * gnorm * np.sqrt(ref.numel() / max(g.numel(), 1)))
-        worst = max(worst, err / denom)
-        assert err / denom < 5 * TOL_FP32, (k, err, ref.norm().item())
+        sampled = g.numel() > 4096
+        got = g.flatten()[::997] if sampled else g
+        err = (got.reshape(ref.shape) - ref).norm().item() * (np.sqrt(g.numel() / ref.numel()) if sampled else 1.0)
+        # 1e-4-class relative error per tensor against the fp64 reference, with the reference's OWN
+        # fp32-vs-fp64 discrepancy on that tensor as the yardstick where it is larger (e.g. key_projection.bias,
+        # whose gradient is analytically zero: the reference's fp32 value there is pure round-off noise).
+        bound = max(5 * TOL_FP32 * n64, 10.0 * ref_noise)
+        worst = max(worst, err / max(n64, 1e-300))
+        assert err <= bound, (k, err, n64, ref_noise)
     print(name, "worst sampled grad rel err", worst)
 
 
