@@ -1,0 +1,8 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+   bench.py --gpus 2 --steps 10 --warmup 3 2> gpurun_out/bench2_err.txt | tee gpurun_out/bench_n2.json
+tail -5 gpurun_out/bench2_err.txt
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+   bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tee gpurun_out/bench_ref_n2.json
