@@ -56,9 +56,12 @@ class FlatGradAllReduce:
             v = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
             views.append(v)
-        torch._foreach_zero_([v for v, p in zip(views, self.params) if p.grad is None])
+        dead = [v for v, p in zip(views, self.params) if p.grad is None]
         live = [(v, p) for v, p in zip(views, self.params) if p.grad is not None]
-        torch._foreach_copy_([v for v, _ in live], [p.grad for _, p in live])
+        if dead:
+            torch._foreach_zero_(dead)
+        if live:
+            torch._foreach_copy_([v for v, _ in live], [p.grad for _, p in live])
         work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
 
         def finish():

@@ -31,6 +31,12 @@ def _worker(rank, world, port, q):
     exp = sum(range(1, world + 1)) / world
     ok = all(torch.allclose(p.grad, torch.full_like(p, exp)) for n, p in lin.named_parameters() if n != "1.bias")
     ok = ok and torch.allclose(lin[1].bias.grad, torch.zeros(3))
+    # second step: every parameter has a gradient now (no "dead" list)
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(2 * rank))
+    P.FlatGradAllReduce(lin.parameters())()
+    exp2 = sum(2 * r for r in range(world)) / world
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, exp2)) for p in lin.parameters())
     # max-over-ranks timing reduction
     ok = ok and P.allreduce_max(float(rank), "cpu") == world - 1
     # sample sharding covers [0, n) exactly once
