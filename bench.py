@@ -166,6 +166,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--e2e-breakdown", action="store_true", help="print per-phase times of the e2e step to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -264,8 +265,32 @@ def main():
             reducer()
             return loss.item()
 
+        if args.e2e_breakdown:
+            def phase_times():
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+                t0 = time.perf_counter()
+                model.physics_net.zero_grad(set_to_none=True)
+                ev[0].record()
+                dev_in = [a.to(dev, non_blocking=True) for a in (hx, hy, ht, hf, hfield, hcd, hfh)]
+                ev[1].record()
+                Wd_ = model.physics_net.decoder_weights(dev_in[4], dev_in[6])
+                ev[2].record()
+                tot, _ = Fn.pde_residual(dev_in[0], dev_in[1], dev_in[2], dev_in[3], dev_in[5], Wd_, consts=consts, mode=args.mode)
+                ev[3].record()
+                tot.backward()
+                ev[4].record()
+                reducer()
+                ev[5].record()
+                t1 = time.perf_counter()
+                tot.item()
+                t2 = time.perf_counter()
+                names = ["h2d", "encoder+hypernet fwd", "fused op", "backward (hypernet+encoder)", "grad all-reduce"]
+                return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(names)} | {"cpu_issue_ms": (t1 - t0) * 1e3, "wall_ms": (t2 - t0) * 1e3}
+            for _ in range(3):
+                phase_times()
+            print("[rank %d] e2e phases (ms): %s" % (rank, json.dumps(phase_times())), file=sys.stderr)
         e_steps = max(3, min(args.steps, 10))
-        ms_e = timed(e2e_step, e_steps, 3)
+        ms_e = timed(e2e_step, e_steps, max(5, args.warmup))
         h2d = sum(a.numel() * a.element_size() for a in (hx, hy, ht, hf, hcd, hfield, hfh))
         e2e = {"value": pts_step / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e, "steps": e_steps,
