@@ -29,15 +29,17 @@ constexpr int TP = 128;                       // points per tile = TMEM lanes
 constexpr int BLOB_H = TP * H * 2;            // 65536  [128 x 256] bf16
 constexpr int BLOB_C = TP * C * 2;            // 49152  [128 x 192] bf16
 constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of a 128-row blob
-constexpr int STAGE_BYTES = 16384;            // one K=32 chunk of a [256 x K] weight image
-constexpr int NSTAGE = 3;
+constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a [256 x K] weight image
+constexpr int NSTAGE = 5;
+constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
 constexpr int GEN_IMG = 2 * IMG_HC + 2 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T
 constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
-constexpr int NBLOB_H = 9, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC GZ | ZP ZD
-constexpr size_t NET_TILE_BYTES = (size_t)NBLOB_H * BLOB_H + (size_t)NBLOB_C * BLOB_C;
-enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC, B_GZ };
+constexpr int NBLOB_H = 8, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX
+constexpr size_t NET_TILE_BYTES = (size_t)NBLOB_H * BLOB_H + (size_t)NBLOB_C * BLOB_C + AUX_BYTES;
+enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
+enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, NVEC };   // epilogue vectors staged in shared memory per net
 
 struct Work {
   // geometry of this pass
@@ -58,6 +60,7 @@ struct Work {
   float* pet;              // [B*T][C][TP] fp32 transposed coordinate features
   uint8_t* blobs;          // [B][Kn][T][NET_TILE_BYTES]
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
+  float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
   float band[NF];
 };
 
@@ -67,6 +70,7 @@ __device__ __forceinline__ uint8_t* net_tile(const Work& w, int b, int k, int tl
 __device__ __forceinline__ uint8_t* blob_h(uint8_t* nt, int which) { return nt + (size_t)which * BLOB_H; }
 __device__ __forceinline__ uint8_t* blob_zp(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H; }
 __device__ __forceinline__ uint8_t* blob_zd(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H + BLOB_C; }
+__device__ __forceinline__ uint8_t* blob_aux(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H + 2 * BLOB_C; }
 
 // ------------------------------------------------------------------------------------------------
 // Small helpers
@@ -115,17 +119,31 @@ struct Issuer {
       const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
       mbar_wait(&pp->full[s], ph);
       tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint64_t ad = smem_desc(act_addr + (uint32_t)(c * 4 + 2 * i) * CORE_STRIDE, CORE_STRIDE, 128);
-        const uint64_t bd = smem_desc(ring_addr + s * STAGE_BYTES + (uint32_t)(2 * i) * Nn * 16, Nn * 16, 128);
-        mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0 || i > 0) ? 1u : 0u);
-      }
+      const uint64_t ad = smem_desc(act_addr + (uint32_t)(c * 2) * CORE_STRIDE, CORE_STRIDE, 128);
+      const uint64_t bd = smem_desc(ring_addr + s * STAGE_BYTES, Nn * 16, 128);
+      mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0) ? 1u : 0u);
       mma_commit(&pp->empty[s]);
       ++n;
     }
   }
 };
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps only
+
+// Column sums over the 32 rows a warp owns: after the exchange lane l holds sum_rows v[row][l].  31 shuffles.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool up = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float keep = up ? v[i + w] : v[i];
+      const float send = up ? v[i] : v[i + w];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+    }
+  }
+  return v[0];
+}
 
 __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
   if (tid == 0) {
@@ -155,12 +173,26 @@ __device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my 
 // ------------------------------------------------------------------------------------------------
 // Pass 1: values + reverse sweep.  One CTA per tile of 128 points, loops over the nets; 2 CTAs per SM.
 // warps 0-3: epilogue (thread = point = TMEM lane), warp 4: bulk-copy producer, warp 5: MMA issuer.
+// Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | 5 epilogue vectors (b1, b2+bd+e, ba, u, 2wo) 5 KB.
 // ------------------------------------------------------------------------------------------------
+constexpr int SMEM_FUSED = BLOB_H + NSTAGE * STAGE_BYTES + NVEC * H * 4;   // 111616
+
+__device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, int k, int r) {
+  const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+  const float* src[NVEC] = {w.b1 + vb, w.bsum + vb, w.ba + vk, w.uvec + vk, w.wo2 + vk};
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) {
+    svec[i * H + r] = __ldg(src[i] + r);
+    svec[i * H + r + TP] = __ldg(src[i] + r + TP);
+  }
+}
+
 __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int sweep) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
   uint8_t* ring = smem + BLOB_H;
+  float* svec = reinterpret_cast<float*>(smem + BLOB_H + NSTAGE * STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;                       // global tile index
@@ -178,22 +210,22 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
       const uint8_t *iW1 = gen, *iW1T = gen + IMG_HC, *iW2 = gen + 2 * IMG_HC, *iW2T = gen + 2 * IMG_HC + IMG_HH;
       const uint8_t *iWd = sta, *iWa = sta + IMG_HC, *iWaT = sta + IMG_HC + IMG_HH;
-      pr.stream(iW1, 0, 2, STAGE_BYTES);
+      pr.stream(iW1, 0, 4, STAGE_BYTES);              // these do not depend on the activation buffer
       if (k > 0) { mbar_wait(&pipe.act_free, af & 1); ++af; }
       mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
       bulk_g2s(act, pe_src, BLOB_C, &pipe.a_bulk);
-      pr.stream(iW1, 2, 6, STAGE_BYTES);
-      pr.stream(iW2, 0, 8, STAGE_BYTES);
-      pr.stream(iWd, 0, 2, STAGE_BYTES);
+      pr.stream(iW1, 4, 12, STAGE_BYTES);
+      pr.stream(iW2, 0, 16, STAGE_BYTES);
+      pr.stream(iWd, 0, 4, STAGE_BYTES);
       mbar_wait(&pipe.act_free, af & 1); ++af;        // G2a has consumed h1
       mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
       bulk_g2s(act, pe6_src, BLOB_C, &pipe.a_bulk);
-      pr.stream(iWd, 2, 6, STAGE_BYTES);
-      pr.stream(iWa, 0, 8, STAGE_BYTES);
+      pr.stream(iWd, 4, 12, STAGE_BYTES);
+      pr.stream(iWa, 0, 16, STAGE_BYTES);
       if (sweep) {
-        pr.stream(iWaT, 0, 8, STAGE_BYTES);
-        pr.stream(iW2T, 0, 8, STAGE_BYTES);
-        if (sweep > 1) pr.stream(iW1T, 0, 8, 12288);
+        pr.stream(iWaT, 0, 16, STAGE_BYTES);
+        pr.stream(iW2T, 0, 16, STAGE_BYTES);
+        if (sweep > 1) pr.stream(iW1T, 0, 16, 6144);
       }
     }
   } else if (warp == 5 && lane == 0) {
@@ -203,24 +235,24 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
     for (int k = 0; k < w.Kn; ++k) {
       if (k > 0) { mbar_wait(&pipe.a_epi, ae & 1); ++ae; }          // last epilogue of the previous net has drained TMEM
       mbar_wait(&pipe.a_bulk, ab & 1); ++ab; tc_fence_after();
-      is.gemm(6, H, false); mma_commit(&pipe.acc_ready);            // G1
+      is.gemm(12, H, false); mma_commit(&pipe.acc_ready);           // G1
       mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-      is.gemm(8, H, false); mma_commit(&pipe.act_free);             // G2a
+      is.gemm(16, H, false); mma_commit(&pipe.act_free);            // G2a
       mbar_wait(&pipe.a_bulk, ab & 1); ++ab; tc_fence_after();
-      is.gemm(6, H, true); mma_commit(&pipe.acc_ready);             // G2b
+      is.gemm(12, H, true); mma_commit(&pipe.acc_ready);            // G2b
       mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-      is.gemm(8, H, false); mma_commit(&pipe.acc_ready);            // G3
+      is.gemm(16, H, false); mma_commit(&pipe.acc_ready);           // G3
       if (sweep) {
         mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G4
+        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G4
         mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G5
+        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G5
         if (sweep > 1) {
           mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-          is.gemm(8, C, false); mma_commit(&pipe.acc_ready);        // G6
+          is.gemm(16, C, false); mma_commit(&pipe.acc_ready);       // G6
         }
       }
-      mma_commit(&pipe.act_free);                                   // the activation buffer may be overwritten by the next PE tile
+      mma_commit(&pipe.act_free);                                   // the activation buffer may take the next PE tile
     }
   } else if (warp < 4) {
     // ---------------- epilogue ----------------
@@ -235,22 +267,29 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
     float v[32];
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile(w, b, k, tl);
-      const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+      epi_bar();                                                    // every warp is done with the previous net's vectors
+      load_vectors(svec, w, b, k, r);
+      epi_bar();
+      uint32_t m1w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};              // ReLU mask of a1, kept in registers (selects, no indexing)
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
       mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(w.b1 + vb + cb * 32) + j4);
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_B1 * H + cb * 32 + j4 * 4);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float a = v[j4 * 4 + e] + bb[e];
+            bits |= (a > 0.f ? 1u : 0u) << (j4 * 4 + e);
             v[j4 * 4 + e] = fmaxf(a, 0.f);
           }
         }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint4 pk = pack8(v + qd * 8);
@@ -268,8 +307,8 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
         tmem_ld32(tl_addr + cb * 32, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(w.bsum + vb + cb * 32) + j4);
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(w.wo2 + vk + cb * 32) + j4);
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cb * 32 + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cb * 32 + j4 * 4);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -292,26 +331,26 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
-        float um[32];
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(w.ba + vk + cb * 32) + j4);
-          const float4 uv = __ldg(reinterpret_cast<const float4*>(w.uvec + vk + cb * 32) + j4);
-          const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = v[j4 * 4 + e] + bb[e];
-            const float gg = fmaxf(a, 0.f);
-            osum = fmaf(uu[e], gg, osum);
-            v[j4 * 4 + e] = gg;
-            um[j4 * 4 + e] = a > 0.f ? uu[e] : 0.f;
-          }
-        }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
+          float um[8];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cb * 32 + qd * 8 + h2 * 4);
+            const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cb * 32 + qd * 8 + h2 * 4);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = v[qd * 8 + h2 * 4 + e] + bb[e];
+              const float gg = fmaxf(a, 0.f);
+              osum = fmaf(uu[e], gg, osum);
+              v[qd * 8 + h2 * 4 + e] = gg;
+              um[h2 * 4 + e] = a > 0.f ? uu[e] : 0.f;
+            }
+          }
           const uint32_t off = piece_off(r, cb * 4 + qd);
           *reinterpret_cast<uint4*>(blob_h(nt, B_GG) + off) = pack8(v + qd * 8);
-          const uint4 pk = pack8(um + qd * 8);
+          const uint4 pk = pack8(um);
           if (sweep) *reinterpret_cast<uint4*>(act + off) = pk;     // without a sweep the buffer already belongs to the next PE tile
           *reinterpret_cast<uint4*>(blob_h(nt, B_UM) + off) = pk;
         }
@@ -326,7 +365,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
         tmem_ld32(tl_addr + cb * 32, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(w.wo2 + vk + cb * 32) + j4);
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cb * 32 + j4 * 4);
           v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
         }
 #pragma unroll
@@ -343,14 +382,15 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bits = (cb == i) ? m1w[i] : bits;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const uint32_t off = piece_off(r, cb * 4 + qd);
-          float h[8];
-          unpack8(*reinterpret_cast<const uint4*>(blob_h(nt, B_H1) + off), h);   // written by this thread in epilogue 1
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[qd * 8 + e] = h[e] > 0.f ? v[qd * 8 + e] : 0.f;
           const uint4 pk = pack8(v + qd * 8);
+          const uint32_t off = piece_off(r, cb * 4 + qd);
           if (sweep > 1) *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;
         }
@@ -364,12 +404,14 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       for (int ob = 0; ob < 2; ++ob) {
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib) {
+          float pp[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pp[j] = __ldg(pet + (size_t)(ob * 96 + DPE_PARTNER(ib * 32 + j)) * TP);
           tmem_ld32(tl_addr + ob * 96 + ib * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int Jl = ib * 32 + j;                              // column inside the 96-block
-            const float pp = __ldg(pet + (size_t)(ob * 96 + DPE_PARTNER(Jl)) * TP);
-            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * w.band[ob * 16 + Jl / 6] * v[j], pp, dz[Jl % 3]);
+            const int Jl = ib * 32 + j;                              // column inside the 96-block (96 % 6 == 0)
+            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * w.band[ob * 16 + Jl / 6] * v[j], pp[j], dz[Jl % 3]);
           }
         }
       }
@@ -386,13 +428,17 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 2: the combined tangent row and the Z-side operands of the weight gradients.
+// Pass 2: the combined tangent row, the Z-side operands of the weight gradients and three column sums.
+// Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | column-sum accumulators 3 x 256 floats.
 // ------------------------------------------------------------------------------------------------
+constexpr int SMEM_PASS2 = BLOB_H + NSTAGE * STAGE_BYTES + 3 * H * 4 + 16;
+
 __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int tangent) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
   uint8_t* ring = smem + BLOB_H;
+  float* csum = reinterpret_cast<float*>(smem + BLOB_H + NSTAGE * STAGE_BYTES);   // [3][H] + sdo
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;
@@ -405,9 +451,9 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
       for (int k = 0; k < w.Kn; ++k) {
         const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * GEN_IMG;
         const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
-        pr.stream(gen, 0, 6, STAGE_BYTES);                       // W1
-        pr.stream(gen + 2 * IMG_HC, 0, 8, STAGE_BYTES);          // W2
-        pr.stream(sta + IMG_HC, 0, 8, STAGE_BYTES);              // Wa
+        pr.stream(gen, 0, 12, STAGE_BYTES);                      // W1
+        pr.stream(gen + 2 * IMG_HC, 0, 16, STAGE_BYTES);         // W2
+        pr.stream(sta + IMG_HC, 0, 16, STAGE_BYTES);             // Wa
       }
     }
   } else if (warp == 5 && lane == 0) {
@@ -416,11 +462,11 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
       uint32_t ae = 0;
       for (int k = 0; k < w.Kn; ++k) {
         mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-        is.gemm(6, H, false); mma_commit(&pipe.acc_ready);          // G7
+        is.gemm(12, H, false); mma_commit(&pipe.acc_ready);         // G7
         mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G8
+        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G8
         mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
-        is.gemm(8, H, false); mma_commit(&pipe.acc_ready);          // G9
+        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G9
       }
     }
   } else if (warp < 4) {
@@ -431,6 +477,8 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
     const uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
     uint32_t ar = 0;
     float v[32];
+    for (int i = r; i < 3 * H + 4; i += TP) csum[i] = 0.f;
+    epi_bar();
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile(w, b, k, tl);
       const float dv = w.dov[row * w.Kn + k];
@@ -439,12 +487,22 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
 #pragma unroll
         for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];
       }
+      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1 = bf16 hi/lo of dov, rest 0
+      {
+        const float hi = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
+        float a8[8] = {hi, dv - hi, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        *reinterpret_cast<uint4*>(blob_aux(nt) + piece_off(r, 0)) = pack8(a8);
+        *reinterpret_cast<uint4*>(blob_aux(nt) + piece_off(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+      }
       // ---- prologue: xt -> activation buffer; zp, zd -> workspace ----
 #pragma unroll 1
       for (int it = 0; it < 8; ++it) {                               // 24 columns = 4 frequencies = 3 pieces per iteration
         float pe[24], xt[24], zp[24];
+        uint4 p6[3];
 #pragma unroll
         for (int j = 0; j < 24; ++j) pe[j] = __ldg(pet + (size_t)(it * 24 + j) * TP);
+#pragma unroll
+        for (int qd = 0; qd < 3; ++qd) p6[qd] = __ldg(reinterpret_cast<const uint4*>(pe6 + piece_off(r, it * 3 + qd)));
 #pragma unroll
         for (int j = 0; j < 24; ++j) {
           const int J = it * 24 + j;                                  // it*24 is a multiple of 6: partner stays inside the block
@@ -458,7 +516,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
           if (tangent) *reinterpret_cast<uint4*>(act + off) = pack8(xt + qd * 8);
           *reinterpret_cast<uint4*>(blob_zp(nt) + off) = pack8(zp + qd * 8);
           float d6[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(pe6 + off)), d6);
+          unpack8(p6[qd], d6);
 #pragma unroll
           for (int e = 0; e < 8; ++e) d6[e] *= dv;
           *reinterpret_cast<uint4*>(blob_zd(nt) + off) = pack8(d6);
@@ -469,34 +527,68 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
 #pragma unroll 1
       for (int st = 0; st < 3; ++st) {
         const uint8_t* src = blob_h(nt, st == 0 ? B_H1 : (st == 1 ? B_CC : B_GG));
-        uint8_t* dst = blob_h(nt, st == 0 ? B_ZH : (st == 1 ? B_ZC : B_GZ));
-        if (tangent) { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); }
+        uint8_t* dst = blob_h(nt, st == 0 ? B_ZH : B_ZC);
+        uint4 nxt[4];
 #pragma unroll
+        for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, qd)));
+        if (tangent) { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); }
+#pragma unroll 1
         for (int cb = 0; cb < 8; ++cb) {
+          uint4 cur[4];
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) cur[qd] = nxt[qd];
+          if (cb < 7) {
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, (cb + 1) * 4 + qd)));
+          }
           if (tangent) {
             tmem_ld32(tl_addr + cb * 32, v);
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
+          float z[32], m3s[32];
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
-            const uint32_t off = piece_off(r, cb * 4 + qd);
-            float s[8], z[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(src + off)), s);
+            float s[8];
+            unpack8(cur[qd], s);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               float t = v[qd * 8 + e];
               if (st != 1) t = s[e] > 0.f ? t : 0.f;                  // relu masks m1 (h1 > 0) / m3 (g > 0)
               v[qd * 8 + e] = t;
-              z[e] = fmaf(dv, s[e], t);
+              z[qd * 8 + e] = fmaf(dv, s[e], t);
+              if (st == 2) m3s[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
             }
-            *reinterpret_cast<uint4*>(dst + off) = pack8(z);
+            const uint32_t off = piece_off(r, cb * 4 + qd);
+            if (st < 2) *reinterpret_cast<uint4*>(dst + off) = pack8(z + qd * 8);
             if (tangent && st < 2) *reinterpret_cast<uint4*>(act + off) = pack8(v + qd * 8);
+          }
+          if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
+            const float cs = warp_colsum32(z, lane);
+            atomicAdd(csum + (st - 1) * H + cb * 32 + lane, cs);
+            if (st == 2) {
+              const float c3 = warp_colsum32(m3s, lane);
+              atomicAdd(csum + 2 * H + cb * 32 + lane, c3);
+            }
           }
         }
         if (tangent && st < 2) epi_done(&pipe);
       }
+      // ---- flush this net's column sums ----
+      float sd = dv;
+#pragma unroll
+      for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
+      if (lane == 0) atomicAdd(csum + 3 * H, sd);
+      epi_bar();
+      for (int i = r; i < 3 * H; i += TP) {
+        const int qn = i / H, j = i % H;
+        float* dstv = qn == 0 ? w.vc : (qn == 1 ? w.vg : w.sm3);
+        atomicAdd(dstv + (size_t)k * H + j, csum[i]);
+        csum[i] = 0.f;
+      }
+      if (r == 0) { atomicAdd(w.sdo + k, csum[3 * H]); csum[3 * H] = 0.f; }
+      epi_bar();
     }
   }
   tc_fence_before();
@@ -508,12 +600,17 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
 // Weight gradients: D[out-half (128 lanes) x in (N cols)] += sum over points  J[p,out] Z[p,in]
 // Both operands are MN-major views of the stored [128 points x width] blobs.  One CTA per
 // (sample, net, layer, out-half, split); single smem stage, 2 CTAs per SM interleave load and MMA.
+// The two N = 192 layers have 64 spare TMEM columns: an extra N = 16 MMA against the seed tile (hi/lo of dov)
+// yields the dov-weighted column sums of their J operand = the bias gradients db1 (J = qm) and db2 (J = y).
 // ------------------------------------------------------------------------------------------------
 struct WgradWork {
   int B, Kn, T, splits;
   const uint8_t* blobs;
   float *gW1, *gW2, *gWa, *gWd;
+  float *gb1, *gb2, *ge, *gbd;
 };
+
+constexpr int SMEM_WGRAD = BLOB_H / 2 + BLOB_H + AUX_BYTES;          // 102400
 
 __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -521,6 +618,7 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
   __shared__ uint32_t tmem_s;
   uint8_t* sJ = smem;                 // 32 KB: 128 points x 128 out (half)
   uint8_t* sZ = smem + BLOB_H / 2;    // up to 64 KB
+  uint8_t* sX = smem + BLOB_H / 2 + BLOB_H;   // 4 KB seed tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int item = blockIdx.x;
   const int split = item % w.splits; item /= w.splits;
@@ -528,6 +626,7 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
   const int layer = item & 3; item >>= 2;
   const int k = item % w.Kn, b = item / w.Kn;
   const int Nn = (layer == 0 || layer == 3) ? C : H;
+  const bool aux = Nn == C;
   const uint32_t zbytes = (uint32_t)TP * Nn * 2;
   const int jsel = layer == 0 ? B_QM : (layer == 2 ? B_UM : B_YT);
   const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
@@ -549,12 +648,13 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
                             : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * BLOB_H;
         const uint32_t i = t - t0;
         mbar_wait(&empty, (i & 1) ^ 1);
-        mbar_arrive_expect_tx(&full, BLOB_H / 2 + zbytes);
+        mbar_arrive_expect_tx(&full, BLOB_H / 2 + zbytes + (aux ? AUX_BYTES : 0));
         bulk_g2s(sJ, nt + (size_t)jsel * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
         bulk_g2s(sZ, zsrc, zbytes, &full);
+        if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * BLOB_H + 2 * BLOB_C, AUX_BYTES, &full);
       }
     } else if (warp == 5 && lane == 0) {
-      const uint32_t idesc = idesc_bf16(Nn, 1, 1);
+      const uint32_t idesc = idesc_bf16(Nn, 1, 1), idesc_x = idesc_bf16(16, 1, 1);
       for (int t = t0; t < t1; ++t) {
         const uint32_t i = t - t0;
         mbar_wait(&full, i & 1);
@@ -564,6 +664,10 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
           const uint64_t ad = smem_desc(smem_u32(sJ) + ks * 256, 128, CORE_STRIDE);
           const uint64_t bd = smem_desc(smem_u32(sZ) + ks * 256, 128, CORE_STRIDE);
           mma_bf16(tmem, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          if (aux) {
+            const uint64_t xd = smem_desc(smem_u32(sX) + ks * 256, 128, CORE_STRIDE);
+            mma_bf16(tmem + C, ad, xd, idesc_x, (i > 0 || ks > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&empty);
       }
@@ -571,8 +675,9 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
     } else if (warp < 4) {
       mbar_wait(&acc_ready, 0);
       tc_fence_after();
-      float* dst = layer == 0 ? w.gW1 + ((size_t)b * w.Kn + k) * H * C
-                 : layer == 1 ? w.gW2 + ((size_t)b * w.Kn + k) * H * H
+      const size_t gk = ((size_t)b * w.Kn + k);
+      float* dst = layer == 0 ? w.gW1 + gk * H * C
+                 : layer == 1 ? w.gW2 + gk * H * H
                  : layer == 2 ? w.gWa + (size_t)k * H * H
                  : w.gWd + (size_t)k * H * C;
       dst += (size_t)(mh * TP + tid) * Nn;
@@ -581,6 +686,18 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) atomicAdd(dst + cb * 32 + j, v[j]);
+      }
+      if (aux) {
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + C, v);
+        const float bsum = v[0] + v[1];                                // hi + lo halves of the seed
+        const int out = mh * TP + tid;
+        if (layer == 0) {
+          atomicAdd(w.gb1 + gk * H + out, bsum);
+        } else {
+          atomicAdd(w.gb2 + gk * H + out, bsum);
+          atomicAdd(w.ge + gk * H + out, bsum);
+          atomicAdd(w.gbd + (size_t)k * H + out, bsum);
+        }
       }
     }
   }
@@ -660,63 +777,10 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
   }
 }
 
-// Column sums over the points of one tile (block = (tile, net), 256 threads = 32 cores x 8 row phases):
-//   gb1 += dov qm, gb2 += dov y (also e, bd), gba += dov um, vc += zc, vg += gz, sdo += dov
-struct ColsumWork {
-  int B, Kn, T;
-  const uint8_t* blobs;
-  const float* dov;
-  float *gb1, *gb2, *ge, *gbd, *gba, *vc, *vg, *sdo;
-};
-
-__global__ void __launch_bounds__(256) colsum_kernel(const ColsumWork w) {
-  const int tile = blockIdx.x, k = blockIdx.y;
-  const int b = tile / w.T, tl = tile % w.T;
-  const int core = threadIdx.x >> 3, rs = threadIdx.x & 7;
-  const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * NET_TILE_BYTES;
-  const float* dv = w.dov + (size_t)tile * TP * w.Kn + k;
-  const int sel[5] = {B_QM, B_YT, B_UM, B_ZC, B_GZ};
-  float acc[5][8];
-#pragma unroll
-  for (int s = 0; s < 5; ++s)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[s][e] = 0.f;
-  float sd = 0.f;
-  for (int r = rs; r < TP; r += 8) {
-    const float wgt = dv[(size_t)r * w.Kn];
-    if (core == 0) sd += wgt;
-    const uint32_t off = piece_off(r, core);
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      float v[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(nt + (size_t)sel[s] * BLOB_H + off)), v);
-      const float ww = s < 3 ? wgt : 1.f;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[s][e] = fmaf(ww, v[e], acc[s][e]);
-    }
-  }
-#pragma unroll
-  for (int m = 1; m < 8; m <<= 1) {
-    sd += __shfl_xor_sync(0xffffffffu, sd, m);
-#pragma unroll
-    for (int s = 0; s < 5; ++s)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[s][e] += __shfl_xor_sync(0xffffffffu, acc[s][e], m);
-  }
-  if (rs == 0) {
-    const size_t gb = ((size_t)b * w.Kn + k) * H + core * 8, sb = (size_t)k * H + core * 8;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      atomicAdd(w.gb1 + gb + e, acc[0][e]);
-      atomicAdd(w.gb2 + gb + e, acc[1][e]);
-      atomicAdd(w.ge + gb + e, acc[1][e]);
-      atomicAdd(w.gbd + sb + e, acc[1][e]);
-      atomicAdd(w.gba + sb + e, acc[2][e]);
-      atomicAdd(w.vc + sb + e, acc[3][e]);
-      atomicAdd(w.vg + sb + e, acc[4][e]);
-    }
-    if (core == 0) atomicAdd(w.sdo + k, sd);
-  }
+// gba = u * sum_p dov m3  (the column sum comes from pass 2)
+__global__ void finalize_ba_kernel(int n, const float* __restrict__ uvec, const float* __restrict__ sm3, float* __restrict__ gba) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) gba[i] = uvec[i] * sm3[i];
 }
 
 __global__ void seed_copy_kernel(const Work w, const float* __restrict__ d_o, float scale) {
@@ -745,7 +809,7 @@ __global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
 // ------------------------------------------------------------------------------------------------
 struct Carve {
   uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
-  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sdo;
+  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo;
   size_t bytes;
 };
 
@@ -772,6 +836,7 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B) {
   c.bsum = reinterpret_cast<float*>(take((size_t)B * Kn * H * 4));
   c.vc = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.vg = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
+  c.sm3 = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sdo = reinterpret_cast<float*>(take((size_t)Kn * 4));
   c.bytes = off;
   return c;
@@ -812,11 +877,10 @@ int run(const Job& J, cudaStream_t st) {
     return DPN_E_UNSUPPORTED;
   }
   static bool attr_done = false;
-  const int smem_fused = BLOB_H + NSTAGE * STAGE_BYTES;             // 114688
-  const int smem_wgrad = BLOB_H / 2 + BLOB_H;                        // 98304
+  const int smem_fused = SMEM_FUSED, smem_pass2 = SMEM_PASS2, smem_wgrad = SMEM_WGRAD;
   if (!attr_done) {
     DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
     DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
     attr_done = true;
   }
@@ -845,6 +909,7 @@ int run(const Job& J, cudaStream_t st) {
     DPN_CUDA_OK(cudaMemsetAsync(G.ba, 0, (size_t)Kn * H * 4, st));
     DPN_CUDA_OK(cudaMemsetAsync(c.vc, 0, (size_t)Kn * H * 4, st));
     DPN_CUDA_OK(cudaMemsetAsync(c.vg, 0, (size_t)Kn * H * 4, st));
+    DPN_CUDA_OK(cudaMemsetAsync(c.sm3, 0, (size_t)Kn * H * 4, st));
     DPN_CUDA_OK(cudaMemsetAsync(c.sdo, 0, (size_t)Kn * 4, st));
   }
   for (int p0 = 0; p0 < N; p0 += chunk) {
@@ -859,6 +924,7 @@ int run(const Job& J, cudaStream_t st) {
     w.coord_data = J.pts->coord_data;
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
+    w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
     encode_kernel<<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
@@ -889,11 +955,12 @@ int run(const Job& J, cudaStream_t st) {
     }
     if (!want_bwd) continue;
     const DpnGrads& G = *J.grads;
-    pass2_kernel<<<tiles, 192, smem_fused, st>>>(w, pde ? 1 : 0);
+    pass2_kernel<<<tiles, 192, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
+    ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd;
     const int items = B * Kn * 8;
     int splits = (2 * 148 * 2 + items - 1) / items;
     if (splits > T) splits = T;
@@ -901,14 +968,11 @@ int run(const Job& J, cudaStream_t st) {
     ww.splits = splits;
     wgrad_kernel<<<items * splits, 192, smem_wgrad, st>>>(ww);
     DPN_LAUNCH_OK();
-    ColsumWork cw;
-    cw.B = B; cw.Kn = Kn; cw.T = T; cw.blobs = c.blobs; cw.dov = c.dov;
-    cw.gb1 = G.b1; cw.gb2 = G.b2; cw.ge = G.e; cw.gbd = G.bd; cw.gba = G.ba; cw.vc = c.vc; cw.vg = c.vg; cw.sdo = c.sdo;
-    colsum_kernel<<<dim3(tiles, Kn), 256, 0, st>>>(cw);
-    DPN_LAUNCH_OK();
   }
   if (want_bwd) {
     if ((rc = f32::launch_finalize(Kn, Wt, c.vc, c.vg, c.sdo, *J.grads, st))) return rc;
+    finalize_ba_kernel<<<(Kn * H + 255) / 256, 256, 0, st>>>(Kn * H, c.uvec, c.sm3, J.grads->ba);
+    DPN_LAUNCH_OK();
   }
   return 0;
 }
