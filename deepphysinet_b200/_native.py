@@ -45,10 +45,16 @@ class DpnPdeOut(C.Structure):
     _fields_ = [("loss_terms", C.c_void_p), ("vals", C.c_void_p), ("jac", C.c_void_p)]
 
 
+class DpnSampler(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("Tt", C.c_int32), ("Hc", C.c_int32), ("Wc", C.c_int32),
+                ("pad_", C.c_int32), ("dx", C.c_double), ("dy", C.c_double), ("cells_per_coarse", C.c_double),
+                ("t_step", C.c_double), ("begin_lat", C.c_double), ("deg_per_cell", C.c_double), ("omega", C.c_double)]
+
+
 _lib = None
 
 EXPORTS = ("dpn_abi_version", "dpn_last_error", "dpn_workspace_bytes", "dpn_pde_fwd_bwd",
-           "dpn_decoder_fwd", "dpn_decoder_bwd", "dpn_last_launch_count")
+           "dpn_decoder_fwd", "dpn_decoder_bwd", "dpn_sample_field", "dpn_last_launch_count")
 
 
 def lib():
@@ -70,6 +76,7 @@ def lib():
         L.dpn_decoder_bwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
                                       C.POINTER(DpnWeights), C.c_void_p, C.POINTER(DpnGrads),
                                       C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dpn_sample_field.argtypes = [C.POINTER(DpnSampler)] + [C.c_void_p] * 7
         L.dpn_last_launch_count.restype = C.c_int
         if L.dpn_abi_version() != 1:
             raise RuntimeError("libdpn_b200.so ABI version mismatch")

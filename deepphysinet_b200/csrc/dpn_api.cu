@@ -6,6 +6,9 @@
 
 namespace dpn {
 
+int run_sampler(const DpnSampler& S, const float* coarse, const float* x, const float* y, const float* t,
+                float* coord_data, float* f, cudaStream_t st);
+
 static thread_local char g_err[1024] = "";
 thread_local int g_launches = 0;
 
@@ -169,6 +172,19 @@ int dpn_decoder_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoi
   job.pts = pts; job.w = w; job.d_o = d_o; job.grads = grads;
   job.workspace = workspace; job.workspace_bytes = workspace_bytes;
   return dispatch(job, cuda_stream);
+}
+
+int dpn_sample_field(const DpnSampler* s, const float* coarse, const float* x, const float* y, const float* t,
+                     float* coord_data, float* f, void* cuda_stream) {
+  if (!s || !coarse || !x || !y || !t || !coord_data) { set_error("dpn_sample_field: NULL argument"); return DPN_E_INVALID; }
+  if (s->B <= 0 || s->N <= 0 || s->Tt < 2 || s->Hc < 2 || s->Wc < 2 || !(s->cells_per_coarse > 0) || !(s->t_step > 0)) {
+    set_error("dpn_sample_field: bad sampler shape B=%d N=%d T=%d H=%d W=%d", s->B, s->N, s->Tt, s->Hc, s->Wc);
+    return DPN_E_INVALID;
+  }
+  g_launches = 0;
+  int rc = check_device();
+  if (rc) return rc;
+  return run_sampler(*s, coarse, x, y, t, coord_data, f, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 }  // extern "C"

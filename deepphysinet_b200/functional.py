@@ -206,3 +206,26 @@ def decoder_values(coord_pe, coord_data, W: DecoderWeights, ref=None, xyz=None, 
     x, y, t = xyz if xyz is not None else (None, None, None)
     o = DecoderValuesFn.apply(coord_pe, x, y, t, coord_data, ref, consts, mode or _DEFAULT_MODE, *W)
     return o[0] if coord_data.dim() == 2 else o
+
+
+def sample_field(coarse, x, y, t, consts: Optional[PhysicsConsts] = None, cells_per_coarse=4.0, t_step=6 * 3600.0,
+                 begin_lat=18.0, deg_per_cell=0.25, omega=7.29e-5, want_coriolis=True):
+    """On-GPU query-point producer: trilinear sample of the normalised coarse field stack
+    `coarse` [B,Tt,Hc,Wc,6] at the query coordinates x, y, t [B,N] (same units as pde_residual) -> coord_data [B,N,6]
+    and the Coriolis parameter f [B,N].  Replaces dataset/physics_dataset.py:477-486 / :521-526.  Not differentiable,
+    exactly like the CPU interpolation it replaces."""
+    consts = consts or PhysicsConsts()
+    cz = _prep(coarse)
+    if cz.dim() != 5 or cz.shape[-1] != 6:
+        raise ValueError("coarse must be [B,Tt,Hc,Wc,6], got %s" % (tuple(cz.shape),))
+    B, Tt, Hc, Wc, _ = cz.shape
+    xs = [_prep(a, (B, -1)) for a in (x, y, t)]
+    Np = xs[0].shape[1]
+    cd = torch.empty(B, Np, 6, device=cz.device)
+    f = torch.empty(B, Np, device=cz.device) if want_coriolis else None
+    S = N.DpnSampler(B=B, N=Np, Tt=Tt, Hc=Hc, Wc=Wc, pad_=0, dx=consts.dx, dy=consts.dy,
+                     cells_per_coarse=float(cells_per_coarse), t_step=float(t_step), begin_lat=float(begin_lat),
+                     deg_per_cell=float(deg_per_cell), omega=float(omega))
+    N.check(N.lib().dpn_sample_field(C.byref(S), N.ptr(cz), N.ptr(xs[0]), N.ptr(xs[1]), N.ptr(xs[2]), N.ptr(cd), N.ptr(f),
+                                     N.stream_ptr()), "dpn_sample_field")
+    return cd, f

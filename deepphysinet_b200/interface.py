@@ -119,3 +119,62 @@ class InterfacePhysics(nn.Module):
                     summary.add_scalar("%s/%s" % (prefix, name), v, global_step)
             print("%s:" % prefix + ",".join("%s:%f" % (n, v) for n, v in zip(TERM_NAMES, vals)))
         return total.float()
+
+    # ---- rows N1 / N3 / N4 of SURVEY 8(f): the callers either side of the hot path --------------------------------
+    def margin_loss(self, W, x, y, t, input_data, target, beta=0.1, factor=1.0e6):
+        """Supervised data loss of the train loop (interface_physics.py:464-474): values of the six nets at the label
+        points against the observations, WeightSmoothL1Loss(beta) (losses/weights_loss.py:12-20) times margin_factor.
+        W = physics_net.decoder_weights(...) so the encoder runs once per step instead of three times."""
+        B = W.W1.shape[0]
+        o = Fn.decoder_values(None, input_data.reshape(B, -1, 6), W, xyz=(x.reshape(B, -1), y.reshape(B, -1), t.reshape(B, -1)),
+                              consts=self.consts(self._last_factor()), mode=self.mode)
+        return torch.nn.functional.smooth_l1_loss(o, target.reshape(o.shape).to(o.dtype), beta=beta, reduction="none").mean() * factor
+
+    def _last_factor(self):
+        from .config import DEFAULT_LOSS_FACTOR
+        return getattr(self, "_loss_factor", DEFAULT_LOSS_FACTOR)
+
+    def training_losses(self, batch, loss_factor, with_pde=True, beta=0.1):
+        """One training step's loss exactly as interface_physics.py:464-501 composes it (margin data loss + interior
+        PDE loss + PDE loss on the margin points), with ONE encoder / hyper-network pass shared by the three terms
+        (the reference re-runs MetaNet for each, physics_net.py:42).  `batch` holds device tensors:
+        field_data [B,159,2405], forecast_h [B,1,1], margin_{x,y,t,f} [B,M], margin_input_data [B,M,6], margin_data [B,M,6],
+        inter_{x,y,t,f} [B,N], inter_data [B,N,6].  Returns (train_loss, parts dict)."""
+        self._loss_factor = loss_factor
+        W = self.physics_net.decoder_weights(batch["field_data"], batch["forecast_h"])
+        consts = self.consts(loss_factor)
+        parts = {}
+        parts["margin_loss"] = self.margin_loss(W, batch["margin_x"], batch["margin_y"], batch["margin_t"],
+                                                batch["margin_input_data"], batch["margin_data"], beta=beta,
+                                                factor=loss_factor.get("margin_factor", 1.0e6))
+        total = parts["margin_loss"]
+        if with_pde:
+            for prefix, dkey in (("inter", "inter_data"), ("margin", "margin_input_data")):
+                tot, terms = Fn.pde_residual(batch[prefix + "_x"], batch[prefix + "_y"], batch[prefix + "_t"],
+                                             batch[prefix + "_f"], batch[dkey], W, consts=consts, mode=self.mode)
+                parts[prefix + "_pde_loss"] = tot
+                parts[prefix + "_terms"] = terms
+                total = total + tot
+        return total, parts
+
+    @torch.no_grad()
+    def predict_grid(self, field_data, coarse, forecast_h, time_ids, dt=3600.0):
+        """Dense-grid continuous-time forward (the working inference of the reference, interface_physics.py:538-606):
+        every node of the lat_size x lon_size grid at each lead time `time_ids[i] * dt`, x-major node order (:541-545),
+        coord_data from the coarse field by the on-GPU trilinear sampler (dataset.get_margin_grid :528-588), values only,
+        inverse_norm WITHOUT clip (:533).  Returns physical fields [len(time_ids), lat_size, lon_size, 6]."""
+        dev = field_data.device
+        Hh, Ww = int(self.lat_size), int(self.lon_size)
+        W = self.physics_net.decoder_weights(field_data[:1], forecast_h[:1])
+        xs, ys = torch.meshgrid(torch.arange(Ww, device=dev, dtype=torch.float32),
+                                torch.arange(Hh, device=dev, dtype=torch.float32), indexing="ij")
+        x = (xs.reshape(1, -1) * self.dx).repeat(1, len(time_ids))
+        y = (ys.reshape(1, -1) * self.dy).repeat(1, len(time_ids))
+        t = torch.tensor(list(time_ids), device=dev, dtype=torch.float32).repeat_interleave(Hh * Ww).reshape(1, -1) * dt
+        consts = self.consts(self._last_factor())
+        cd, _ = Fn.sample_field(coarse[:1], x, y, t, consts=consts, want_coriolis=False)
+        o = Fn.decoder_values(None, cd, W, xyz=(x, y, t), consts=consts, mode=self.mode)[0]      # [T*W*H, 6]
+        mean = torch.tensor(consts.mean, device=dev, dtype=o.dtype)
+        std = torch.tensor(consts.std, device=dev, dtype=o.dtype)
+        phys = o * std + mean
+        return phys.reshape(len(time_ids), Ww, Hh, 6).permute(0, 2, 1, 3).contiguous()

@@ -143,6 +143,25 @@ int dpn_decoder_bwd(const DpnShape *shape, const DpnConsts *consts, const DpnPoi
                     const DpnWeights *w, const float *d_o, const DpnGrads *grads,
                     void *workspace, size_t workspace_bytes, void *cuda_stream);
 
+/* Query-point producer.  Replaces the CPU xarray trilinear interpolation of the normalised coarse
+ * field stack (dataset/physics_dataset.py:477-486, :406-415, :567-576) and get_coriolis (:521-526).
+ *   coarse     [B, Tt, Hc, Wc, 6]  normalised coarse field, channel-last (u10,v10,pres,t2,q2,rio)
+ *   x, y, t    [B*N]   query coordinates in the units of DpnPoints (x = fine-cell index * dx, t in seconds)
+ *   coord_data [B*N,6] out;   f [B*N] out (may be NULL): 2 omega sin(begin_lat + (y/dy) deg_per_cell)
+ * Values only: the reference never differentiates through this interpolation. */
+typedef struct DpnSampler {
+  int32_t B, N;
+  int32_t Tt, Hc, Wc;          /* 5, 37, 65 in the reference configuration */
+  int32_t pad_;
+  double dx, dy;               /* fine grid spacing [m] */
+  double cells_per_coarse;     /* fine cells per coarse cell: 4 (0.25 deg over 1 deg) */
+  double t_step;               /* seconds between coarse time slices: 6 h */
+  double begin_lat, deg_per_cell, omega;
+} DpnSampler;
+
+int dpn_sample_field(const DpnSampler *s, const float *coarse, const float *x, const float *y, const float *t,
+                     float *coord_data, float *f, void *cuda_stream);
+
 /* Introspection for tests and bench: number of kernels the last call on this thread launched. */
 int dpn_last_launch_count(void);
 
