@@ -17,6 +17,8 @@
 // Every [128 x Kd] bf16 operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh, in shared memory and in
 // the workspace alike, so a tile written once by an epilogue is (a) the K-major A operand of the next GEMM and
 // (b) an MN-major operand of the weight-gradient contraction, and moves with plain 1-D bulk copies.
+#include <stdlib.h>
+
 #include "dpn_tc.cuh"
 #include "dpn_umma.cuh"
 
@@ -61,6 +63,7 @@ struct Work {
   uint8_t* blobs;          // [B][Kn][T][NET_TILE_BYTES]
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
   float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
+  long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (DPN_PHASE_DEBUG=1), summed over CTAs
   float band[NF];
 };
 
@@ -95,6 +98,12 @@ struct Pipe {            // shared-memory barriers of the fused kernels
   uint32_t tmem_base;
 };
 
+__device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
 // Producer side of the weight ring: one elected thread.
 struct Producer {
   Pipe* pp; uint8_t* ring; uint32_t n = 0;
@@ -112,12 +121,12 @@ struct Producer {
 
 // MMA side: one elected thread.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major, Nn rows).
 struct Issuer {
-  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t n = 0;
+  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t n = 0; long long t_full = 0;
   __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate) {
     const uint32_t idesc = idesc_bf16(Nn, 0, 0);
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
-      mbar_wait(&pp->full[s], ph);
+      mbar_wait_t(&pp->full[s], ph, t_full);
       tc_fence_after();
       const uint64_t ad = smem_desc(act_addr + (uint32_t)(c * 2) * CORE_STRIDE, CORE_STRIDE, 128);
       const uint64_t bd = smem_desc(ring_addr + s * STAGE_BYTES, Nn * 16, 128);
@@ -232,27 +241,35 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
     // ---------------- MMA issuer ----------------
     Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
     uint32_t ab = 0, ae = 0;
+    long long t_epi = 0, t_bulk = 0;
+    const long long t_begin = clock64();
     for (int k = 0; k < w.Kn; ++k) {
-      if (k > 0) { mbar_wait(&pipe.a_epi, ae & 1); ++ae; }          // last epilogue of the previous net has drained TMEM
-      mbar_wait(&pipe.a_bulk, ab & 1); ++ab; tc_fence_after();
+      if (k > 0) { mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; }          // last epilogue of the previous net has drained TMEM
+      mbar_wait_t(&pipe.a_bulk, ab & 1, t_bulk); ++ab; tc_fence_after();
       is.gemm(12, H, false); mma_commit(&pipe.acc_ready);           // G1
-      mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+      mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
       is.gemm(16, H, false); mma_commit(&pipe.act_free);            // G2a
-      mbar_wait(&pipe.a_bulk, ab & 1); ++ab; tc_fence_after();
+      mbar_wait_t(&pipe.a_bulk, ab & 1, t_bulk); ++ab; tc_fence_after();
       is.gemm(12, H, true); mma_commit(&pipe.acc_ready);            // G2b
-      mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+      mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
       is.gemm(16, H, false); mma_commit(&pipe.acc_ready);           // G3
       if (sweep) {
-        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
         is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G4
-        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
         is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G5
         if (sweep > 1) {
-          mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+          mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
           is.gemm(16, C, false); mma_commit(&pipe.acc_ready);       // G6
         }
       }
       mma_commit(&pipe.act_free);                                   // the activation buffer may take the next PE tile
+    }
+    if (w.phase_dbg) {
+      atomicAdd((unsigned long long*)w.phase_dbg + 0, (unsigned long long)(clock64() - t_begin));
+      atomicAdd((unsigned long long*)w.phase_dbg + 1, (unsigned long long)is.t_full);
+      atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)t_epi);
+      atomicAdd((unsigned long long*)w.phase_dbg + 3, (unsigned long long)t_bulk);
     }
   } else if (warp < 4) {
     // ---------------- epilogue ----------------
@@ -265,6 +282,8 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     uint32_t ar = 0;
     float v[32];
+    long long t_acc = 0;
+    const long long t_begin = clock64();
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile(w, b, k, tl);
       epi_bar();                                                    // every warp is done with the previous net's vectors
@@ -272,7 +291,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       epi_bar();
       uint32_t m1w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};              // ReLU mask of a1, kept in registers (selects, no indexing)
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
-      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       epi_done(&pipe);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
       float osum = 0.f;
-      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
@@ -327,7 +346,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       }
       epi_done(&pipe);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
-      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
@@ -359,7 +378,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       epi_done(&pipe);
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
-      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
@@ -378,7 +397,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       }
       epi_done(&pipe);
       // ---- epilogue 5: qm = acc * m1 ----
-      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
 #pragma unroll 1
       for (int cb = 0; cb < 8; ++cb) {
         tmem_ld32(tl_addr + cb * 32, v);
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       epi_done(&pipe);
       if (sweep < 2) continue;
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c) ----
-      mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       float dz[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
       for (int ob = 0; ob < 2; ++ob) {
@@ -420,6 +439,11 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
         for (int c = 0; c < 3; ++c) w.od[(row * w.Kn + k) * 3 + c] = dz[c];
       }
       epi_done(&pipe);
+    }
+    if (w.phase_dbg && tid == 0) {
+      atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)(clock64() - t_begin));
+      atomicAdd((unsigned long long*)w.phase_dbg + 5, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 6, 1ull);
     }
   }
   tc_fence_before();
@@ -460,13 +484,20 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
     if (tangent) {
       Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
       uint32_t ae = 0;
+      long long t_epi = 0;
+      const long long t_begin = clock64();
       for (int k = 0; k < w.Kn; ++k) {
-        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
         is.gemm(12, H, false); mma_commit(&pipe.acc_ready);         // G7
-        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
         is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G8
-        mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after();
+        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
         is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G9
+      }
+      if (w.phase_dbg) {
+        atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
+        atomicAdd((unsigned long long*)w.phase_dbg + 9, (unsigned long long)is.t_full);
+        atomicAdd((unsigned long long*)w.phase_dbg + 10, (unsigned long long)t_epi);
       }
     }
   } else if (warp < 4) {
@@ -477,6 +508,8 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
     const uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
     uint32_t ar = 0;
     float v[32];
+    long long t_acc = 0;
+    const long long t_begin = clock64();
     for (int i = r; i < 3 * H + 4; i += TP) csum[i] = 0.f;
     epi_bar();
     for (int k = 0; k < w.Kn; ++k) {
@@ -531,7 +564,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
         uint4 nxt[4];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, qd)));
-        if (tangent) { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); }
+        if (tangent) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
 #pragma unroll 1
         for (int cb = 0; cb < 8; ++cb) {
           uint4 cur[4];
@@ -589,6 +622,11 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
       }
       if (r == 0) { atomicAdd(w.sdo + k, csum[3 * H]); csum[3 * H] = 0.f; }
       epi_bar();
+    }
+    if (w.phase_dbg && tid == 0) {
+      atomicAdd((unsigned long long*)w.phase_dbg + 12, (unsigned long long)(clock64() - t_begin));
+      atomicAdd((unsigned long long*)w.phase_dbg + 13, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 14, 1ull);
     }
   }
   tc_fence_before();
@@ -810,6 +848,7 @@ __global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
 struct Carve {
   uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
   float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo;
+  long long* dbg;
   size_t bytes;
 };
 
@@ -838,6 +877,7 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B) {
   c.vg = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sm3 = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sdo = reinterpret_cast<float*>(take((size_t)Kn * 4));
+  c.dbg = reinterpret_cast<long long*>(take(16 * 8));
   c.bytes = off;
   return c;
 }
@@ -892,6 +932,8 @@ int run(const Job& J, cudaStream_t st) {
   const double inv_n = 1.0 / (double)(J.shape.n_norm > 0 ? J.shape.n_norm : N);
   const double seed_scale = J.shape.seed_scale != 0.f ? (double)J.shape.seed_scale : 1.0;
   int rc;
+  static const bool phase_debug = getenv("DPN_PHASE_DEBUG") != nullptr;
+  if (phase_debug) DPN_CUDA_OK(cudaMemsetAsync(c.dbg, 0, 16 * 8, st));
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
   if ((rc = make_images(Wt, c, B, Kn, st))) return rc;
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
@@ -925,6 +967,7 @@ int run(const Job& J, cudaStream_t st) {
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
     w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
+    w.phase_dbg = phase_debug ? c.dbg : nullptr;
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
     encode_kernel<<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
@@ -968,6 +1011,16 @@ int run(const Job& J, cudaStream_t st) {
     ww.splits = splits;
     wgrad_kernel<<<items * splits, 192, smem_wgrad, st>>>(ww);
     DPN_LAUNCH_OK();
+  }
+  if (phase_debug) {
+    long long h[16];
+    DPN_CUDA_OK(cudaStreamSynchronize(st));
+    DPN_CUDA_OK(cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    const double n1 = h[6] > 0 ? (double)h[6] : 1.0, n2 = h[14] > 0 ? (double)h[14] : 1.0;
+    fprintf(stderr, "[dpn phase] pass1 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f | wait A tile %.0f || "
+                    "epilogue-thread total %.0f | wait accumulator %.0f\n", h[0] / n1, h[1] / n1, h[2] / n1, h[3] / n1, h[4] / n1, h[5] / n1);
+    fprintf(stderr, "[dpn phase] pass2 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f || "
+                    "epilogue-thread total %.0f | wait accumulator %.0f\n", h[8] / n2, h[9] / n2, h[10] / n2, h[12] / n2, h[13] / n2);
   }
   if (want_bwd) {
     if ((rc = f32::launch_finalize(Kn, Wt, c.vc, c.vg, c.sdo, *J.grads, st))) return rc;

@@ -17,9 +17,10 @@ def _queries(n, seed=1, lat=145, lon=257):
     y = rng.random(n) * (lat - 1) * 27000.0
     t = rng.integers(0, 25, n) * 3600.0
     # edge cases: exact nodes, the last node of every axis, the origin
-    x[:4] = [0.0, (lon - 1) * 27000.0, 4 * 27000.0, (lon - 1) * 27000.0]
-    y[:4] = [0.0, (lat - 1) * 27000.0, 8 * 27000.0, 0.0]
-    t[:4] = [0.0, 24 * 3600.0, 6 * 3600.0, 24 * 3600.0]
+    k = min(n, 4)
+    x[:k] = [0.0, (lon - 1) * 27000.0, 4 * 27000.0, (lon - 1) * 27000.0][:k]
+    y[:k] = [0.0, (lat - 1) * 27000.0, 8 * 27000.0, 0.0][:k]
+    t[:k] = [0.0, 24 * 3600.0, 6 * 3600.0, 24 * 3600.0][:k]
     return x, y, t
 
 
