@@ -281,7 +281,6 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
     const size_t row = g * TP + r;                                  // index into the pass-local per-point arrays
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     uint32_t ar = 0;
-    float v[32];
     long long t_acc = 0;
     const long long t_begin = clock64();
     for (int k = 0; k < w.Kn; ++k) {
@@ -292,9 +291,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       uint32_t m1w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};              // ReLU mask of a1, kept in registers (selects, no indexing)
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
-        tmem_ld32(tl_addr + cb * 32, v);
+      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
         uint32_t bits = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -316,14 +313,12 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
           *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_H1) + off) = pk;
         }
-      }
+            });
       epi_done(&pipe);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
       float osum = 0.f;
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
-        tmem_ld32(tl_addr + cb * 32, v);
+      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cb * 32 + j4 * 4);
@@ -343,13 +338,11 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
           *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_CC) + off) = pk;
         }
-      }
+            });
       epi_done(&pipe);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
-        tmem_ld32(tl_addr + cb * 32, v);
+      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           float um[8];
@@ -373,15 +366,13 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
           if (sweep) *reinterpret_cast<uint4*>(act + off) = pk;     // without a sweep the buffer already belongs to the next PE tile
           *reinterpret_cast<uint4*>(blob_h(nt, B_UM) + off) = pk;
         }
-      }
+            });
       if (valid) w.o[row * w.Kn + k] = osum + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
       epi_done(&pipe);
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
-        tmem_ld32(tl_addr + cb * 32, v);
+      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cb * 32 + j4 * 4);
@@ -394,13 +385,11 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
           *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_YT) + off) = pk;
         }
-      }
+            });
       epi_done(&pipe);
       // ---- epilogue 5: qm = acc * m1 ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-#pragma unroll 1
-      for (int cb = 0; cb < 8; ++cb) {
-        tmem_ld32(tl_addr + cb * 32, v);
+      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
         uint32_t bits = 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) bits = (cb == i) ? m1w[i] : bits;
@@ -413,27 +402,28 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
           if (sweep > 1) *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;
         }
-      }
+            });
       epi_done(&pipe);
       if (sweep < 2) continue;
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c) ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       float dz[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int ob = 0; ob < 2; ++ob) {
+      tmem_for_each_block<6>(tl_addr, [&](const int cb, float (&v)[32]) {
+        const int ob = cb / 3, ib = cb - 3 * ob;                       // 96-column halves: 96 % 6 == 0 keeps the sin/cos pattern static
+        float pp[32];
 #pragma unroll
-        for (int ib = 0; ib < 3; ++ib) {
-          float pp[32];
+        for (int i3 = 0; i3 < 3; ++i3) {
+          if (ib == i3) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pp[j] = __ldg(pet + (size_t)(ob * 96 + DPE_PARTNER(ib * 32 + j)) * TP);
-          tmem_ld32(tl_addr + ob * 96 + ib * 32, v);
+            for (int j = 0; j < 32; ++j) pp[j] = __ldg(pet + (size_t)(ob * 96 + DPE_PARTNER(i3 * 32 + j)) * TP);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int Jl = ib * 32 + j;                              // column inside the 96-block (96 % 6 == 0)
-            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * w.band[ob * 16 + Jl / 6] * v[j], pp[j], dz[Jl % 3]);
+            for (int j = 0; j < 32; ++j) {
+              const int Jl = i3 * 32 + j;
+              dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * w.band[ob * 16 + Jl / 6] * v[j], pp[j], dz[Jl % 3]);
+            }
           }
         }
-      }
+      });
       if (valid) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) w.od[(row * w.Kn + k) * 3 + c] = dz[c];
@@ -507,7 +497,6 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     const uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
     uint32_t ar = 0;
-    float v[32];
     long long t_acc = 0;
     const long long t_begin = clock64();
     for (int i = r; i < 3 * H + 4; i += TP) csum[i] = 0.f;
@@ -565,8 +554,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, qd)));
         if (tangent) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
-#pragma unroll 1
-        for (int cb = 0; cb < 8; ++cb) {
+        auto process = [&](const int cb, float (&v)[32]) {
           uint4 cur[4];
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) cur[qd] = nxt[qd];
@@ -574,13 +562,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, (cb + 1) * 4 + qd)));
           }
-          if (tangent) {
-            tmem_ld32(tl_addr + cb * 32, v);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          float z[32], m3s[32];
+          float z[32];
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             float s[8];
@@ -591,7 +573,6 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
               if (st != 1) t = s[e] > 0.f ? t : 0.f;                  // relu masks m1 (h1 > 0) / m3 (g > 0)
               v[qd * 8 + e] = t;
               z[qd * 8 + e] = fmaf(dv, s[e], t);
-              if (st == 2) m3s[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
             }
             const uint32_t off = piece_off(r, cb * 4 + qd);
             if (st < 2) *reinterpret_cast<uint4*>(dst + off) = pack8(z + qd * 8);
@@ -601,9 +582,27 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
             const float cs = warp_colsum32(z, lane);
             atomicAdd(csum + (st - 1) * H + cb * 32 + lane, cs);
             if (st == 2) {
-              const float c3 = warp_colsum32(m3s, lane);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                float s[8];
+                unpack8(cur[qd], s);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) z[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
+              }
+              const float c3 = warp_colsum32(z, lane);
               atomicAdd(csum + 2 * H + cb * 32 + lane, c3);
             }
+          }
+        };
+        if (tangent) {
+          tmem_for_each_block<8>(tl_addr, process);
+        } else {
+#pragma unroll 1
+          for (int cb = 0; cb < 8; ++cb) {
+            float v0[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v0[j] = 0.f;
+            process(cb, v0);
           }
         }
         if (tangent && st < 2) epi_done(&pipe);

@@ -89,6 +89,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Split form for software pipelining: issue the load of the NEXT 32 columns, work on the current ones, then wait.
+// The wait takes the destination registers as in/out operands so that no consumer can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// Visits NB consecutive 32-column blocks of this thread's TMEM lane, double-buffered: while f works on block i the
+// load of block i+1 is in flight.  f(block_index, float (&v)[32]).
+template <int NB, class F>
+__device__ __forceinline__ void tmem_for_each_block(uint32_t taddr, F&& f) {
+  uint32_t ra[32], rb[32];
+  tmem_ld32_issue(taddr, ra);
+#pragma unroll 1
+  for (int cb = 0; cb < NB; cb += 2) {
+    tmem_ld_wait(ra);
+    if (cb + 1 < NB) tmem_ld32_issue(taddr + (cb + 1) * 32, rb);
+    f(cb, reinterpret_cast<float(&)[32]>(ra));
+    if (cb + 1 < NB) {
+      tmem_ld_wait(rb);
+      if (cb + 2 < NB) tmem_ld32_issue(taddr + (cb + 2) * 32, ra);
+      f(cb + 1, reinterpret_cast<float(&)[32]>(rb));
+    }
+  }
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start[0,14) | LBO[16,30) | SBO[32,46) | 1<<46
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
