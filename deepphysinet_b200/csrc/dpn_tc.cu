@@ -137,7 +137,6 @@ struct Issuer {
   }
 };
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps only
 
 // Column sums over the 32 rows a warp owns: after the exchange lane l holds sum_rows v[row][l].  31 shuffles.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -158,12 +157,12 @@ __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], 1); }
     mbar_init(&pp->a_bulk, 1);
-    mbar_init(&pp->a_epi, TP);
+    mbar_init(&pp->a_epi, 256);                 // every epilogue thread (8 warps) arrives
     mbar_init(&pp->acc_ready, 1);
     mbar_init(&pp->act_free, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(&pp->tmem_base, 256);
+  if (warp == 9) tmem_alloc(&pp->tmem_base, 256);   // the MMA warp of the fused kernels owns the allocation
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -184,31 +183,46 @@ __device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my 
 // warps 0-3: epilogue (thread = point = TMEM lane), warp 4: bulk-copy producer, warp 5: MMA issuer.
 // Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | 5 epilogue vectors (b1, b2+bd+e, ba, u, 2wo) 5 KB.
 // ------------------------------------------------------------------------------------------------
-constexpr int SMEM_FUSED = BLOB_H + NSTAGE * STAGE_BYTES + NVEC * H * 4;   // 111616
+constexpr int EPI_WARPS = 8;                        // warps w and w+4 share TMEM lanes and split the 256 columns
+constexpr int EPI_THREADS = EPI_WARPS * 32;         // 256
+constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1;
+constexpr int FUSED_THREADS = EPI_THREADS + 64;     // 320
+constexpr int SMEM_FUSED = BLOB_H + NSTAGE * STAGE_BYTES + NVEC * H * 4 + TP * 4 * 4;   // + per-row partial sums (o, dz[3])
 
-__device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, int k, int r) {
-  const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
-  const float* src[NVEC] = {w.b1 + vb, w.bsum + vb, w.ba + vk, w.uvec + vk, w.wo2 + vk};
-#pragma unroll
-  for (int i = 0; i < NVEC; ++i) {
-    svec[i * H + r] = __ldg(src[i] + r);
-    svec[i * H + r + TP] = __ldg(src[i] + r + TP);
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+
+// NB consecutive 32-column blocks of this thread's TMEM lane: f(block, float (&v)[32])
+template <int NB, class F>
+__device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f) {
+#pragma unroll 1
+  for (int cb = 0; cb < NB; ++cb) {
+    float v[32];
+    tmem_ld32(taddr + cb * 32, v);
+    f(cb, v);
   }
 }
 
-__global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int sweep) {
+__device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, int k, int t) {
+  const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+  const float* src[NVEC] = {w.b1 + vb, w.bsum + vb, w.ba + vk, w.uvec + vk, w.wo2 + vk};
+#pragma unroll
+  for (int i = 0; i < NVEC; ++i) svec[i * H + t] = __ldg(src[i] + t);       // t = 0..255
+}
+
+__global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, const int sweep) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
   uint8_t* ring = smem + BLOB_H;
   float* svec = reinterpret_cast<float*>(smem + BLOB_H + NSTAGE * STAGE_BYTES);
+  float* rowsum = svec + NVEC * H;                                // [TP][4]: o partial, dz[3]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;                       // global tile index
   pipe_init(&pipe, warp, tid);
   const uint32_t tmem = pipe.tmem_base;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     // ---------------- producer ----------------
     Producer pr{&pipe, ring};
     uint32_t af = 0;
@@ -237,14 +251,14 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
         if (sweep > 1) pr.stream(iW1T, 0, 16, 6144);
       }
     }
-  } else if (warp == 5 && lane == 0) {
+  } else if (warp == W_MMA && lane == 0) {
     // ---------------- MMA issuer ----------------
     Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
     uint32_t ab = 0, ae = 0;
     long long t_epi = 0, t_bulk = 0;
     const long long t_begin = clock64();
     for (int k = 0; k < w.Kn; ++k) {
-      if (k > 0) { mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; }          // last epilogue of the previous net has drained TMEM
+      if (k > 0) { mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; }  // last epilogue of the previous net has drained TMEM
       mbar_wait_t(&pipe.a_bulk, ab & 1, t_bulk); ++ab; tc_fence_after();
       is.gemm(12, H, false); mma_commit(&pipe.acc_ready);           // G1
       mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
@@ -271,10 +285,12 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
       atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)t_epi);
       atomicAdd((unsigned long long*)w.phase_dbg + 3, (unsigned long long)t_bulk);
     }
-  } else if (warp < 4) {
-    // ---------------- epilogue ----------------
-    const int r = tid;                                              // row in tile = TMEM lane
-    const uint32_t tl_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  } else if (warp < EPI_WARPS) {
+    // ---------------- epilogue: thread = (point r, column half) ----------------
+    const int half = warp >> 2;                                     // columns [128*half, 128*half+128)
+    const int r = (warp & 3) * 32 + lane;                           // row in tile = TMEM lane
+    const int c0 = half * 4;                                        // first 32-column block of this thread
+    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 128;
     const int p_local = tl * TP + r;
     const bool valid = p_local < w.P;
     const size_t q = (size_t)b * w.N + w.p0 + p_local;              // index into the caller's per-point arrays
@@ -283,19 +299,21 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
     uint32_t ar = 0;
     long long t_acc = 0;
     const long long t_begin = clock64();
+    if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile(w, b, k, tl);
       epi_bar();                                                    // every warp is done with the previous net's vectors
-      load_vectors(svec, w, b, k, r);
+      load_vectors(svec, w, b, k, tid);
       epi_bar();
-      uint32_t m1w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};              // ReLU mask of a1, kept in registers (selects, no indexing)
+      uint32_t m1w[4] = {0u, 0u, 0u, 0u};                            // ReLU mask of a1 for this thread's 128 columns
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+        const int cg = c0 + cb;
         uint32_t bits = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = *reinterpret_cast<const float4*>(svec + V_B1 * H + cb * 32 + j4 * 4);
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_B1 * H + cg * 32 + j4 * 4);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
@@ -305,130 +323,146 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
           }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
+        for (int i = 0; i < 4; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cb * 4 + qd);
+          const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_H1) + off) = pk;
         }
-            });
+      });
       epi_done(&pipe);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
-      float osum = 0.f;
+      float os0 = 0.f, os1 = 0.f;
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+        const int cg = c0 + cb;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cb * 32 + j4 * 4);
-          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cb * 32 + j4 * 4);
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cg * 32 + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float cc = v[j4 * 4 + e] + bb[e];
-            osum = fmaf(ww[e], cc, osum);
+            if (e & 1) os1 = fmaf(ww[e], cc, os1); else os0 = fmaf(ww[e], cc, os0);
             v[j4 * 4 + e] = cc;
           }
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cb * 4 + qd);
+          const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_CC) + off) = pk;
         }
-            });
+      });
       epi_done(&pipe);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+        const int cg = c0 + cb;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           float um[8];
 #pragma unroll
           for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cb * 32 + qd * 8 + h2 * 4);
-            const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cb * 32 + qd * 8 + h2 * 4);
+            const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cg * 32 + qd * 8 + h2 * 4);
+            const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cg * 32 + qd * 8 + h2 * 4);
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float a = v[qd * 8 + h2 * 4 + e] + bb[e];
               const float gg = fmaxf(a, 0.f);
-              osum = fmaf(uu[e], gg, osum);
+              if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
               v[qd * 8 + h2 * 4 + e] = gg;
               um[h2 * 4 + e] = a > 0.f ? uu[e] : 0.f;
             }
           }
-          const uint32_t off = piece_off(r, cb * 4 + qd);
+          const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(blob_h(nt, B_GG) + off) = pack8(v + qd * 8);
           const uint4 pk = pack8(um);
           if (sweep) *reinterpret_cast<uint4*>(act + off) = pk;     // without a sweep the buffer already belongs to the next PE tile
           *reinterpret_cast<uint4*>(blob_h(nt, B_UM) + off) = pk;
         }
-            });
-      if (valid) w.o[row * w.Kn + k] = osum + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
+      });
+      atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
       epi_done(&pipe);
+      epi_bar();
+      if (half == 0) {
+        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
+        rowsum[r * 4] = 0.f;
+      }
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+        const int cg = c0 + cb;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cb * 32 + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
           v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cb * 4 + qd);
+          const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_YT) + off) = pk;
         }
-            });
+      });
       epi_done(&pipe);
       // ---- epilogue 5: qm = acc * m1 ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
-      tmem_for_each_block<8>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+        const int cg = c0 + cb;
         uint32_t bits = 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bits = (cb == i) ? m1w[i] : bits;
+        for (int i = 0; i < 4; ++i) bits = (cb == i) ? m1w[i] : bits;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cb * 4 + qd);
+          const uint32_t off = piece_off(r, cg * 4 + qd);
           if (sweep > 1) *reinterpret_cast<uint4*>(act + off) = pk;
           *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;
         }
-            });
+      });
       epi_done(&pipe);
       if (sweep < 2) continue;
-      // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c) ----
+      // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       float dz[3] = {0.f, 0.f, 0.f};
-      tmem_for_each_block<6>(tl_addr, [&](const int cb, float (&v)[32]) {
-        const int ob = cb / 3, ib = cb - 3 * ob;                       // 96-column halves: 96 % 6 == 0 keeps the sin/cos pattern static
-        float pp[32];
+      {
+        const uint32_t a6 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 96;
+        const float bsel = half ? 1.f : 0.f;
 #pragma unroll
-        for (int i3 = 0; i3 < 3; ++i3) {
-          if (ib == i3) {
+        for (int ib = 0; ib < 3; ++ib) {                             // 96 % 6 == 0 keeps the sin/cos pattern static per block
+          float pp[32], v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) pp[j] = __ldg(pet + (size_t)(ob * 96 + DPE_PARTNER(i3 * 32 + j)) * TP);
+          for (int j = 0; j < 32; ++j) pp[j] = __ldg(pet + (size_t)(half * 96 + DPE_PARTNER(ib * 32 + j)) * TP);
+          tmem_ld32(a6 + ib * 32, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int Jl = i3 * 32 + j;
-              dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * w.band[ob * 16 + Jl / 6] * v[j], pp[j], dz[Jl % 3]);
-            }
+          for (int j = 0; j < 32; ++j) {
+            const int Jl = ib * 32 + j;
+            const float bnd = bsel * w.band[16 + Jl / 6] + (1.f - bsel) * w.band[Jl / 6];
+            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * bnd * v[j], pp[j], dz[Jl % 3]);
           }
         }
-      });
-      if (valid) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) w.od[(row * w.Kn + k) * 3 + c] = dz[c];
       }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, dz[c]);
       epi_done(&pipe);
+      epi_bar();
+      if (half == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (valid) w.od[(row * w.Kn + k) * 3 + c] = rowsum[r * 4 + 1 + c];
+          rowsum[r * 4 + 1 + c] = 0.f;
+        }
+      }
     }
     if (w.phase_dbg && tid == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)(clock64() - t_begin));
@@ -438,7 +472,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
+  if (warp == W_MMA) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -447,7 +481,7 @@ __global__ void __launch_bounds__(192, 2) pass1_kernel(const Work w, const int s
 // ------------------------------------------------------------------------------------------------
 constexpr int SMEM_PASS2 = BLOB_H + NSTAGE * STAGE_BYTES + 3 * H * 4 + 16;
 
-__global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int tangent) {
+__global__ void __launch_bounds__(FUSED_THREADS, 2) pass2_kernel(const Work w, const int tangent) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
@@ -459,7 +493,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
   pipe_init(&pipe, warp, tid);
   const uint32_t tmem = pipe.tmem_base;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == W_PROD && lane == 0) {
     if (tangent) {
       Producer pr{&pipe, ring};
       for (int k = 0; k < w.Kn; ++k) {
@@ -470,7 +504,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
         pr.stream(sta + IMG_HC, 0, 16, STAGE_BYTES);             // Wa
       }
     }
-  } else if (warp == 5 && lane == 0) {
+  } else if (warp == W_MMA && lane == 0) {
     if (tangent) {
       Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
       uint32_t ae = 0;
@@ -490,16 +524,18 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
         atomicAdd((unsigned long long*)w.phase_dbg + 10, (unsigned long long)t_epi);
       }
     }
-  } else if (warp < 4) {
-    const int r = tid;
-    const uint32_t tl_addr = tmem + ((uint32_t)(warp * 32) << 16);
+  } else if (warp < EPI_WARPS) {
+    const int half = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const int c0 = half * 4;
+    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 128;
     const size_t row = g * TP + r;
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     const uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
     uint32_t ar = 0;
     long long t_acc = 0;
     const long long t_begin = clock64();
-    for (int i = r; i < 3 * H + 4; i += TP) csum[i] = 0.f;
+    for (int i = tid; i < 3 * H + 4; i += EPI_THREADS) csum[i] = 0.f;
     epi_bar();
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile(w, b, k, tl);
@@ -510,15 +546,15 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
         for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];
       }
       // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1 = bf16 hi/lo of dov, rest 0
-      {
+      if (half == 0) {
         const float hi = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
         float a8[8] = {hi, dv - hi, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         *reinterpret_cast<uint4*>(blob_aux(nt) + piece_off(r, 0)) = pack8(a8);
         *reinterpret_cast<uint4*>(blob_aux(nt) + piece_off(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
       }
-      // ---- prologue: xt -> activation buffer; zp, zd -> workspace ----
+      // ---- prologue: xt -> activation buffer; zp, zd -> workspace (each half takes 4 of the 8 column groups) ----
 #pragma unroll 1
-      for (int it = 0; it < 8; ++it) {                               // 24 columns = 4 frequencies = 3 pieces per iteration
+      for (int it = half * 4; it < half * 4 + 4; ++it) {             // 24 columns = 4 frequencies = 3 pieces per iteration
         float pe[24], xt[24], zp[24];
         uint4 p6[3];
 #pragma unroll
@@ -552,15 +588,16 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
         uint8_t* dst = blob_h(nt, st == 0 ? B_ZH : B_ZC);
         uint4 nxt[4];
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, qd)));
+        for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, c0 * 4 + qd)));
         if (tangent) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
         auto process = [&](const int cb, float (&v)[32]) {
+          const int cg = c0 + cb;
           uint4 cur[4];
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) cur[qd] = nxt[qd];
-          if (cb < 7) {
+          if (cb < 3) {
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, (cb + 1) * 4 + qd)));
+            for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, (cg + 1) * 4 + qd)));
           }
           float z[32];
 #pragma unroll
@@ -574,13 +611,13 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
               v[qd * 8 + e] = t;
               z[qd * 8 + e] = fmaf(dv, s[e], t);
             }
-            const uint32_t off = piece_off(r, cb * 4 + qd);
+            const uint32_t off = piece_off(r, cg * 4 + qd);
             if (st < 2) *reinterpret_cast<uint4*>(dst + off) = pack8(z + qd * 8);
             if (tangent && st < 2) *reinterpret_cast<uint4*>(act + off) = pack8(v + qd * 8);
           }
           if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
             const float cs = warp_colsum32(z, lane);
-            atomicAdd(csum + (st - 1) * H + cb * 32 + lane, cs);
+            atomicAdd(csum + (st - 1) * H + cg * 32 + lane, cs);
             if (st == 2) {
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
@@ -590,15 +627,15 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
                 for (int e = 0; e < 8; ++e) z[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
               }
               const float c3 = warp_colsum32(z, lane);
-              atomicAdd(csum + 2 * H + cb * 32 + lane, c3);
+              atomicAdd(csum + 2 * H + cg * 32 + lane, c3);
             }
           }
         };
         if (tangent) {
-          tmem_for_each_block<8>(tl_addr, process);
+          tmem_blocks<4>(tl_addr, process);
         } else {
 #pragma unroll 1
-          for (int cb = 0; cb < 8; ++cb) {
+          for (int cb = 0; cb < 4; ++cb) {
             float v0[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v0[j] = 0.f;
@@ -608,18 +645,20 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
         if (tangent && st < 2) epi_done(&pipe);
       }
       // ---- flush this net's column sums ----
-      float sd = dv;
+      if (half == 0) {
+        float sd = dv;
 #pragma unroll
-      for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
-      if (lane == 0) atomicAdd(csum + 3 * H, sd);
+        for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
+        if (lane == 0) atomicAdd(csum + 3 * H, sd);
+      }
       epi_bar();
-      for (int i = r; i < 3 * H; i += TP) {
+      for (int i = tid; i < 3 * H; i += EPI_THREADS) {
         const int qn = i / H, j = i % H;
         float* dstv = qn == 0 ? w.vc : (qn == 1 ? w.vg : w.sm3);
         atomicAdd(dstv + (size_t)k * H + j, csum[i]);
         csum[i] = 0.f;
       }
-      if (r == 0) { atomicAdd(w.sdo + k, csum[3 * H]); csum[3 * H] = 0.f; }
+      if (tid == 0) { atomicAdd(w.sdo + k, csum[3 * H]); csum[3 * H] = 0.f; }
       epi_bar();
     }
     if (w.phase_dbg && tid == 0) {
@@ -630,7 +669,7 @@ __global__ void __launch_bounds__(192, 2) pass2_kernel(const Work w, const int t
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
+  if (warp == W_MMA) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -971,7 +1010,7 @@ int run(const Job& J, cudaStream_t st) {
     const int tiles = B * T;
     encode_kernel<<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
     DPN_LAUNCH_OK();
-    pass1_kernel<<<tiles, 192, smem_fused, st>>>(w, sweep);
+    pass1_kernel<<<tiles, FUSED_THREADS, smem_fused, st>>>(w, sweep);
     DPN_LAUNCH_OK();
     if (J.kind == JOB_DEC_FWD) {
       gather_o_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.o);
@@ -997,7 +1036,7 @@ int run(const Job& J, cudaStream_t st) {
     }
     if (!want_bwd) continue;
     const DpnGrads& G = *J.grads;
-    pass2_kernel<<<tiles, 192, smem_pass2, st>>>(w, pde ? 1 : 0);
+    pass2_kernel<<<tiles, FUSED_THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs;

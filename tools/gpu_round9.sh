@@ -1,7 +1,8 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,temperature.gpu,clocks_event_reasons.active --format=csv
+timeout 900 python -m pytest tests/test_gpu_bf16.py tests/test_gpu_decoder.py -m gpu -x -q 2>&1 | tail -4
+DPN_PHASE_DEBUG=1 timeout 600 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-modes 2>&1 >/dev/null | grep "dpn phase" | tail -2
 for i in 1 2; do
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-modes 2>/dev/null | python -c "
 import json,sys
