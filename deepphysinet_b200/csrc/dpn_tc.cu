@@ -64,6 +64,7 @@ struct Work {
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
   float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
   long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (DPN_PHASE_DEBUG=1), summed over CTAs
+  int dbg_flags;               // timing experiments only (DPN_DEBUG_FLAGS): 1 = no blob stores, 2 = no act stores, 4 = no TMEM loads
   float band[NF];
 };
 
@@ -95,6 +96,7 @@ __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)
 struct Pipe {            // shared-memory barriers of the fused kernels
   uint64_t full[NSTAGE], empty[NSTAGE];
   uint64_t a_bulk, a_epi, acc_ready, act_free;
+  uint64_t st_done;        // the bulk store that drains the activation tile has finished reading it
   uint32_t tmem_base;
 };
 
@@ -160,6 +162,7 @@ __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
     mbar_init(&pp->a_epi, 256);                 // every epilogue thread (8 warps) arrives
     mbar_init(&pp->acc_ready, 1);
     mbar_init(&pp->act_free, 1);
+    mbar_init(&pp->st_done, 1);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(&pp->tmem_base, 256);   // the MMA warp of the fused kernels owns the allocation
@@ -193,11 +196,16 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: 
 
 // NB consecutive 32-column blocks of this thread's TMEM lane: f(block, float (&v)[32])
 template <int NB, class F>
-__device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f) {
+__device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f, const bool SKIP_TMEM_DBG = false) {
 #pragma unroll 1
   for (int cb = 0; cb < NB; ++cb) {
     float v[32];
-    tmem_ld32(taddr + cb * 32, v);
+    if (SKIP_TMEM_DBG) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 1.0f;
+    } else {
+      tmem_ld32(taddr + cb * 32, v);
+    }
     f(cb, v);
   }
 }
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
   if (warp == W_PROD && lane == 0) {
     // ---------------- producer ----------------
     Producer pr{&pipe, ring};
-    uint32_t af = 0;
+    uint32_t af = 0, sd = 0;
     const uint8_t* pe_src = w.pe_blob + g * BLOB_C;
     const uint8_t* pe6_src = w.pe6_blob + g * BLOB_C;
     for (int k = 0; k < w.Kn; ++k) {
@@ -234,13 +242,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
       const uint8_t *iW1 = gen, *iW1T = gen + IMG_HC, *iW2 = gen + 2 * IMG_HC, *iW2T = gen + 2 * IMG_HC + IMG_HH;
       const uint8_t *iWd = sta, *iWa = sta + IMG_HC, *iWaT = sta + IMG_HC + IMG_HH;
       pr.stream(iW1, 0, 4, STAGE_BYTES);              // these do not depend on the activation buffer
-      if (k > 0) { mbar_wait(&pipe.act_free, af & 1); ++af; }
+      if (k > 0) {
+        mbar_wait(&pipe.act_free, af & 1); ++af;
+        if (sweep) { mbar_wait(&pipe.st_done, sd & 1); ++sd; }      // last tile of the previous net has been drained
+      }
       mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
       bulk_g2s(act, pe_src, BLOB_C, &pipe.a_bulk);
       pr.stream(iW1, 4, 12, STAGE_BYTES);
       pr.stream(iW2, 0, 16, STAGE_BYTES);
       pr.stream(iWd, 0, 4, STAGE_BYTES);
       mbar_wait(&pipe.act_free, af & 1); ++af;        // G2a has consumed h1
+      if (sweep) { mbar_wait(&pipe.st_done, sd & 1); ++sd; }        // ... and the bulk store has drained it to the workspace
       mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
       bulk_g2s(act, pe6_src, BLOB_C, &pipe.a_bulk);
       pr.stream(iWd, 4, 12, STAGE_BYTES);
@@ -299,6 +311,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
     uint32_t ar = 0;
     long long t_acc = 0;
     const long long t_begin = clock64();
+    // Drain of a finished activation tile to the workspace: one bulk store by the TMA engine instead of 32 st.global
+    // per thread.  Call after epi_done(); `to_producer` when the next writer of the buffer is the bulk-load producer.
+    auto drain = [&](uint8_t* blob, const bool to_producer) {
+      epi_bar();                                                    // every thread has written and fenced its part
+      if (tid == 0) {
+        bulk_s2g(blob, act, BLOB_H);
+        bulk_commit();
+        bulk_wait_read_all();
+        if (to_producer) mbar_arrive(&pipe.st_done);
+      }
+    };
     if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile(w, b, k, tl);
@@ -329,11 +352,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
           const uint4 pk = pack8(v + qd * 8);
           const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(act + off) = pk;
-          *reinterpret_cast<uint4*>(blob_h(nt, B_H1) + off) = pk;
         }
-      });
+      }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe);
+      if (sweep) drain(blob_h(nt, B_H1), true);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
+      if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
       float os0 = 0.f, os1 = 0.f;
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
@@ -355,11 +379,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
           const uint4 pk = pack8(v + qd * 8);
           const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(act + off) = pk;
-          *reinterpret_cast<uint4*>(blob_h(nt, B_CC) + off) = pk;
         }
-      });
+      }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe);
+      if (sweep) drain(blob_h(nt, B_CC), false);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
+      if (sweep) epi_bar();
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
@@ -381,21 +406,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
             }
           }
           const uint32_t off = piece_off(r, cg * 4 + qd);
-          *reinterpret_cast<uint4*>(blob_h(nt, B_GG) + off) = pack8(v + qd * 8);
-          const uint4 pk = pack8(um);
-          if (sweep) *reinterpret_cast<uint4*>(act + off) = pk;     // without a sweep the buffer already belongs to the next PE tile
-          *reinterpret_cast<uint4*>(blob_h(nt, B_UM) + off) = pk;
+          if (sweep) {                                                // values-only calls keep nothing for a backward pass,
+            *reinterpret_cast<uint4*>(blob_h(nt, B_GG) + off) = pack8(v + qd * 8);
+            *reinterpret_cast<uint4*>(act + off) = pack8(um);         // and their buffer already belongs to the next PE tile
+          }
         }
-      });
+      }, (w.dbg_flags & 4) != 0);
       atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
       epi_done(&pipe);
-      epi_bar();
+      if (sweep) drain(blob_h(nt, B_UM), false); else epi_bar();
       if (half == 0) {
         if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
         rowsum[r * 4] = 0.f;
       }
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
+      if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
@@ -409,11 +435,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
           const uint4 pk = pack8(v + qd * 8);
           const uint32_t off = piece_off(r, cg * 4 + qd);
           *reinterpret_cast<uint4*>(act + off) = pk;
-          *reinterpret_cast<uint4*>(blob_h(nt, B_YT) + off) = pk;
         }
-      });
+      }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe);
+      drain(blob_h(nt, B_YT), sweep < 2);
       // ---- epilogue 5: qm = acc * m1 ----
+      if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
@@ -427,11 +454,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
           const uint4 pk = pack8(v + qd * 8);
           const uint32_t off = piece_off(r, cg * 4 + qd);
           if (sweep > 1) *reinterpret_cast<uint4*>(act + off) = pk;
-          *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;
+          else *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;      // decoder-only backward: no G6, the tile goes straight out
         }
-      });
+      }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe);
       if (sweep < 2) continue;
+      drain(blob_h(nt, B_QM), true);
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
       float dz[3] = {0.f, 0.f, 0.f};
@@ -464,6 +492,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
         }
       }
     }
+    if (tid == 0) bulk_wait_all();
     if (w.phase_dbg && tid == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)(clock64() - t_begin));
       atomicAdd((unsigned long long*)w.phase_dbg + 5, (unsigned long long)t_acc);
@@ -1006,6 +1035,7 @@ int run(const Job& J, cudaStream_t st) {
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
     w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
     w.phase_dbg = phase_debug ? c.dbg : nullptr;
+    w.dbg_flags = getenv("DPN_DEBUG_FLAGS") ? atoi(getenv("DPN_DEBUG_FLAGS")) : 0;
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
     encode_kernel<<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
