@@ -33,6 +33,7 @@ constexpr int BLOB_C = TP * C * 2;            // 49152  [128 x 192] bf16
 constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of a 128-row blob
 constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a [256 x K] weight image
 constexpr int NSTAGE = 5;
+constexpr int CLUSTER = 2;                     // CTAs (tiles of the same sample) sharing every weight chunk through one multicast L2 read
 constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
@@ -108,12 +109,17 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long
 
 // Producer side of the weight ring: one elected thread.
 struct Producer {
-  Pipe* pp; uint8_t* ring; uint32_t n = 0;
+  Pipe* pp; uint8_t* ring; uint32_t rank; uint32_t n = 0;
   __device__ __forceinline__ void put(const uint8_t* src, uint32_t bytes) {
     const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
-    mbar_wait(&pp->empty[s], ph ^ 1);
-    mbar_arrive_expect_tx(&pp->full[s], bytes);
-    bulk_g2s(ring + s * STAGE_BYTES, src, bytes, &pp->full[s]);
+    mbar_wait(&pp->empty[s], ph ^ 1);                // every CTA of the cluster has consumed the previous occupant
+    mbar_arrive_expect_tx(&pp->full[s], bytes);      // my copy of the chunk: my slice + the slices my peers multicast to me
+    if (CLUSTER == 1) {
+      bulk_g2s(ring + s * STAGE_BYTES, src, bytes, &pp->full[s]);
+    } else {
+      const uint32_t slice = bytes / CLUSTER;
+      bulk_g2s_mc(ring + s * STAGE_BYTES + rank * slice, src + rank * slice, slice, &pp->full[s], (uint16_t)((1u << CLUSTER) - 1));
+    }
     ++n;
   }
   __device__ __forceinline__ void stream(const uint8_t* img, int first, int last, uint32_t bytes) {
@@ -133,7 +139,7 @@ struct Issuer {
       const uint64_t ad = smem_desc(act_addr + (uint32_t)(c * 2) * CORE_STRIDE, CORE_STRIDE, 128);
       const uint64_t bd = smem_desc(ring_addr + s * STAGE_BYTES, Nn * 16, 128);
       mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0) ? 1u : 0u);
-      mma_commit(&pp->empty[s]);
+      if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
       ++n;
     }
   }
@@ -157,7 +163,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 
 __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], 1); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], CLUSTER); }
     mbar_init(&pp->a_bulk, 1);
     mbar_init(&pp->a_epi, 256);                 // every epilogue thread (8 warps) arrives
     mbar_init(&pp->acc_ready, 1);
@@ -169,6 +175,7 @@ __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CLUSTER > 1) cluster_sync_all();              // peers' barriers exist before anything is multicast to them
 }
 
 __device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my smem writes / TMEM reads are finished
@@ -217,7 +224,7 @@ __device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, 
   for (int i = 0; i < NVEC; ++i) svec[i * H + t] = __ldg(src[i] + t);       // t = 0..255
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, const int sweep) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, const int sweep) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
 
   if (warp == W_PROD && lane == 0) {
     // ---------------- producer ----------------
-    Producer pr{&pipe, ring};
+    Producer pr{&pipe, ring, cluster_ctarank()};
     uint32_t af = 0, sd = 0;
     const uint8_t* pe_src = w.pe_blob + g * BLOB_C;
     const uint8_t* pe6_src = w.pe6_blob + g * BLOB_C;
@@ -501,6 +508,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
   if (warp == W_MMA) tmem_dealloc(tmem, 256);
 }
 
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, c
 // ------------------------------------------------------------------------------------------------
 constexpr int SMEM_PASS2 = BLOB_H + NSTAGE * STAGE_BYTES + 3 * H * 4 + 16;
 
-__global__ void __launch_bounds__(FUSED_THREADS, 2) pass2_kernel(const Work w, const int tangent) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, 2) pass2_kernel(const Work w, const int tangent) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
@@ -524,7 +532,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass2_kernel(const Work w, c
 
   if (warp == W_PROD && lane == 0) {
     if (tangent) {
-      Producer pr{&pipe, ring};
+      Producer pr{&pipe, ring, cluster_ctarank()};
       for (int k = 0; k < w.Kn; ++k) {
         const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * GEN_IMG;
         const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
@@ -698,6 +706,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 2) pass2_kernel(const Work w, c
   }
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
   if (warp == W_MMA) tmem_dealloc(tmem, 256);
 }
 
@@ -923,7 +932,7 @@ static inline size_t al(size_t n) { return (n + 1023) & ~(size_t)1023; }
 
 static Carve carve(uint8_t* base, int chunk, int Kn, int B) {
   Carve c;
-  const size_t T = (size_t)(chunk + TP - 1) / TP, rows = (size_t)B * T * TP;
+  const size_t T = ((size_t)(chunk + TP - 1) / TP + CLUSTER - 1) / CLUSTER * CLUSTER, rows = (size_t)B * T * TP;
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base + off; off += al(bytes); return p; };
   c.img_gen = take((size_t)B * Kn * GEN_IMG);
@@ -1023,7 +1032,7 @@ int run(const Job& J, cudaStream_t st) {
   }
   for (int p0 = 0; p0 < N; p0 += chunk) {
     const int P = min(chunk, N - p0);
-    const int T = (P + TP - 1) / TP;
+    const int T = ((P + TP - 1) / TP + CLUSTER - 1) / CLUSTER * CLUSTER;   // clusters pair tiles of the same sample
     const size_t rows = (size_t)B * T * TP;
     Work w;
     memset(&w, 0, sizeof(w));

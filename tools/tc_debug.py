@@ -21,7 +21,7 @@ def al(n):
 
 
 def carve(chunk, Kn, B):
-    Tn = (chunk + TP - 1) // TP
+    Tn = ((chunk + TP - 1) // TP + 1) // 2 * 2          # tiles are padded to a multiple of the cluster size
     rows = B * Tn * TP
     off, out = 0, {}
     for name, size in [("img_gen", B * Kn * GEN_IMG), ("img_sta", Kn * STA_IMG), ("pe", B * Tn * BLOB_C),
