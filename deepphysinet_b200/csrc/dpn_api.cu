@@ -24,8 +24,10 @@ static int f32_chunk(const DpnShape& s) {
   return c < s.N ? c : s.N;
 }
 
+static int planes(const DpnShape& s) { return s.mode == DPN_MODE_BF16X3 ? 2 : 1; }
+
 static int tc_chunk(const DpnShape& s) {
-  int c = s.chunk > 0 ? (s.chunk + 127) / 128 * 128 : tc::default_chunk(s.B);
+  int c = s.chunk > 0 ? (s.chunk + 127) / 128 * 128 : tc::default_chunk(s.B, planes(s));
   const int n = (s.N + 127) / 128 * 128;
   return c < n ? c : n;
 }
@@ -36,7 +38,7 @@ static int check_shape(const DpnShape* s) {
     set_error("bad shape B=%d N=%d K=%d (need B>0, N>0, 1<=K<=6)", s->B, s->N, s->K);
     return DPN_E_INVALID;
   }
-  if (s->mode != DPN_MODE_FP32 && s->mode != DPN_MODE_BF16) {
+  if (s->mode != DPN_MODE_FP32 && s->mode != DPN_MODE_BF16 && s->mode != DPN_MODE_BF16X3) {
     set_error("unknown mode %d", s->mode);
     return DPN_E_INVALID;
   }
@@ -44,12 +46,17 @@ static int check_shape(const DpnShape* s) {
 }
 
 static int check_device() {
+  // cudaGetDeviceProperties costs milliseconds per call: ask for the one attribute, once per device
+  static int major_of[64] = {0};
   int dev = 0;
-  cudaDeviceProp prop;
   DPN_CUDA_OK(cudaGetDevice(&dev));
-  DPN_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) {
-    set_error("libdpn_b200 is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+  int major = (dev >= 0 && dev < 64) ? major_of[dev] : 0;
+  if (major == 0) {
+    DPN_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (dev >= 0 && dev < 64) major_of[dev] = major;
+  }
+  if (major != 10) {
+    set_error("libdpn_b200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
     return DPN_E_UNSUPPORTED;
   }
   return 0;
@@ -59,7 +66,7 @@ static size_t ws_bytes(const DpnShape& s) {
   // the CUDA-core kernels also serve the pre-encoded (coord_pe) surface in bf16 mode, so that mode needs the larger of the two
   const size_t a = f32::workspace_bytes(f32_chunk(s), s.K, s.B);
   if (s.mode == DPN_MODE_FP32) return a;
-  const size_t b = tc::workspace_bytes(tc_chunk(s), s.K, s.B);
+  const size_t b = tc::workspace_bytes(tc_chunk(s), s.K, s.B, planes(s));
   return a > b ? a : b;
 }
 
@@ -77,7 +84,7 @@ static int dispatch(Job& job, void* stream) {
     return DPN_E_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool tensor = job.shape.mode == DPN_MODE_BF16 && !job.pts->coord_pe && !job.pts->ref && job.shape.K == 6;
+  const bool tensor = job.shape.mode != DPN_MODE_FP32 && !job.pts->coord_pe && !job.pts->ref && job.shape.K == 6;
   job.chunk = tensor ? tc_chunk(job.shape) : f32_chunk(job.shape);
   return tensor ? tc::run(job, st) : f32::run(job, st);
 }

@@ -14,6 +14,10 @@
 //   wgrad   dW1 = qm^T zp, dW2 = y^T zh, dWa = (u*m3)^T zc, dWd = y^T zd  : K = points contractions, MN-major operands
 //   colsum  bias gradients and the two vectors the folded output layer needs (vc, vg)
 //
+// DPN_MODE_BF16X3 (template parameter PL = 2): every operand - weight images, activation tiles, workspace blobs - is kept
+// as TWO bf16 planes, hi = bf16(v) and lo = bf16(v - hi) (16 mantissa bits together), and every contraction issues three
+// MMAs into the same fp32 accumulator: lo*hi + hi*lo + hi*hi.  Same kernels, same pipeline, 1 CTA per SM.
+//
 // Every [128 x Kd] bf16 operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh, in shared memory and in
 // the workspace alike, so a tile written once by an epilogue is (a) the K-major A operand of the next GEMM and
 // (b) an MN-major operand of the weight-gradient contraction, and moves with plain 1-D bulk copies.
@@ -40,8 +44,19 @@ constexpr int IMG_HH = H * H * 2;             // 131072
 constexpr int GEN_IMG = 2 * IMG_HC + 2 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T
 constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
 constexpr int NBLOB_H = 8, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX
-constexpr size_t NET_TILE_BYTES = (size_t)NBLOB_H * BLOB_H + (size_t)NBLOB_C * BLOB_C + AUX_BYTES;
 enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
+
+// Sizes that depend on the number of operand planes PL (1: bf16, 2: bf16 hi + lo).  Planes of one tile are contiguous,
+// in shared memory and in the workspace alike, so a tile still moves with one bulk copy.
+template <int PL>
+struct Geo {
+  static constexpr int STAGE = STAGE_BYTES * PL;                 // ring stage: [hi chunk | lo chunk]
+  static constexpr int ACT = BLOB_H * PL;                        // activation buffer: plane p at p * BLOB_H
+  static constexpr int BH = BLOB_H * PL, BC = BLOB_C * PL;       // workspace blobs: plane p at p * BLOB_H (p * BLOB_C)
+  static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
+  static constexpr size_t NET_TILE = (size_t)NBLOB_H * BH + (size_t)NBLOB_C * BC + AUX_BYTES;
+  static constexpr int CTAS_PER_SM = PL == 1 ? 2 : 1;
+};
 enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, NVEC };   // epilogue vectors staged in shared memory per net
 
 struct Work {
@@ -58,8 +73,8 @@ struct Work {
   const float *ba, *uvec, *wo2, *cst;   // [Kn][H], cst [Kn]
   // per-point
   const float* coord_data; // [B*N][6]
-  uint8_t* pe_blob;        // [B*T][BLOB_C]
-  uint8_t* pe6_blob;       // [B*T][BLOB_C]
+  uint8_t* pe_blob;        // [B*T][PL][BLOB_C]
+  uint8_t* pe6_blob;       // [B*T][PL][BLOB_C]
   float* pet;              // [B*T][C][TP] fp32 transposed coordinate features
   uint8_t* blobs;          // [B][Kn][T][NET_TILE_BYTES]
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
@@ -69,13 +84,14 @@ struct Work {
   float band[NF];
 };
 
+template <int PL>
 __device__ __forceinline__ uint8_t* net_tile(const Work& w, int b, int k, int tl) {
-  return w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * NET_TILE_BYTES;
+  return w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * Geo<PL>::NET_TILE;
 }
-__device__ __forceinline__ uint8_t* blob_h(uint8_t* nt, int which) { return nt + (size_t)which * BLOB_H; }
-__device__ __forceinline__ uint8_t* blob_zp(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H; }
-__device__ __forceinline__ uint8_t* blob_zd(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H + BLOB_C; }
-__device__ __forceinline__ uint8_t* blob_aux(uint8_t* nt) { return nt + (size_t)NBLOB_H * BLOB_H + 2 * BLOB_C; }
+template <int PL> __device__ __forceinline__ uint8_t* blob_h(uint8_t* nt, int which) { return nt + (size_t)which * Geo<PL>::BH; }
+template <int PL> __device__ __forceinline__ uint8_t* blob_zp(uint8_t* nt) { return nt + (size_t)NBLOB_H * Geo<PL>::BH; }
+template <int PL> __device__ __forceinline__ uint8_t* blob_zd(uint8_t* nt) { return nt + (size_t)NBLOB_H * Geo<PL>::BH + Geo<PL>::BC; }
+template <int PL> __device__ __forceinline__ uint8_t* blob_aux(uint8_t* nt) { return nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC; }
 
 // ------------------------------------------------------------------------------------------------
 // Small helpers
@@ -90,6 +106,33 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
     v[2 * i] = __uint_as_float(w[i] << 16);
     v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
+}
+// 8 fp32 values -> one 16-byte piece per plane: hi = bf16(v), lo = bf16(v - hi)  (v - hi is exact in fp32)
+template <int PL>
+__device__ __forceinline__ void split8(const float* v, uint4 (&q)[PL]) {
+  q[0] = pack8(v);
+  if (PL == 2) {
+    float h[8], l[8];
+    unpack8(q[0], h);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) l[e] = v[e] - h[e];
+    q[PL - 1] = pack8(l);
+  }
+}
+// store a piece into a tile whose planes are `plane` bytes apart: shared memory (sts8) / workspace, streaming (stg8)
+template <int PL>
+__device__ __forceinline__ void sts8(uint8_t* tile, uint32_t plane, uint32_t off, const float* v) {
+  uint4 q[PL];
+  split8<PL>(v, q);
+#pragma unroll
+  for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(tile + p * plane + off) = q[p];
+}
+template <int PL>
+__device__ __forceinline__ void stg8(uint8_t* tile, uint32_t plane, uint32_t off, const float* v) {
+  uint4 q[PL];
+  split8<PL>(v, q);
+#pragma unroll
+  for (int p = 0; p < PL; ++p) __stcs(reinterpret_cast<uint4*>(tile + p * plane + off), q[p]);
 }
 // element (r, 8*kc .. 8*kc+7) of a 128-row blob
 __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)kc * CORE_STRIDE + (uint32_t)r * 16; }
@@ -108,26 +151,30 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long
 }
 
 // Producer side of the weight ring: one elected thread.
+template <int PL>
 struct Producer {
   Pipe* pp; uint8_t* ring; uint32_t rank; uint32_t n = 0;
+  uint64_t pol = l2_policy_evict_last();       // weight images: re-read by every tile of the sample, keep them in L2
   __device__ __forceinline__ void put(const uint8_t* src, uint32_t bytes) {
     const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
     mbar_wait(&pp->empty[s], ph ^ 1);                // every CTA of the cluster has consumed the previous occupant
     mbar_arrive_expect_tx(&pp->full[s], bytes);      // my copy of the chunk: my slice + the slices my peers multicast to me
     if (CLUSTER == 1) {
-      bulk_g2s(ring + s * STAGE_BYTES, src, bytes, &pp->full[s]);
+      bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src, bytes, &pp->full[s], pol);
     } else {
       const uint32_t slice = bytes / CLUSTER;
-      bulk_g2s_mc(ring + s * STAGE_BYTES + rank * slice, src + rank * slice, slice, &pp->full[s], (uint16_t)((1u << CLUSTER) - 1));
+      bulk_g2s_mc_hint(ring + s * Geo<PL>::STAGE + rank * slice, src + rank * slice, slice, &pp->full[s], (uint16_t)((1u << CLUSTER) - 1), pol);
     }
     ++n;
   }
+  // chunks [first, last) of a weight image whose K = 16 chunks are `bytes` per plane
   __device__ __forceinline__ void stream(const uint8_t* img, int first, int last, uint32_t bytes) {
-    for (int i = first; i < last; ++i) put(img + (size_t)i * bytes, bytes);
+    for (int i = first; i < last; ++i) put(img + (size_t)i * bytes * PL, bytes * PL);
   }
 };
 
 // MMA side: one elected thread.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major, Nn rows).
+template <int PL>
 struct Issuer {
   Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t n = 0; long long t_full = 0;
   __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate) {
@@ -136,9 +183,16 @@ struct Issuer {
       const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
       mbar_wait_t(&pp->full[s], ph, t_full);
       tc_fence_after();
-      const uint64_t ad = smem_desc(act_addr + (uint32_t)(c * 2) * CORE_STRIDE, CORE_STRIDE, 128);
-      const uint64_t bd = smem_desc(ring_addr + s * STAGE_BYTES, Nn * 16, 128);
-      mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0) ? 1u : 0u);
+      const uint32_t a0 = act_addr + (uint32_t)(c * 2) * CORE_STRIDE, b0 = ring_addr + s * Geo<PL>::STAGE;
+      const uint64_t ad = smem_desc(a0, CORE_STRIDE, 128);
+      const uint64_t bd = smem_desc(b0, Nn * 16, 128);
+      if (PL == 2) {                                   // small terms first: lo*hi + hi*lo + hi*hi into one accumulator
+        mma_bf16(tmem, smem_desc(a0 + BLOB_H, CORE_STRIDE, 128), bd, idesc, (accumulate || c > 0) ? 1u : 0u);
+        mma_bf16(tmem, ad, smem_desc(b0 + Nn * 32, Nn * 16, 128), idesc, 1u);
+        mma_bf16(tmem, ad, bd, idesc, 1u);
+      } else {
+        mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0) ? 1u : 0u);
+      }
       if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
       ++n;
     }
@@ -197,7 +251,7 @@ constexpr int EPI_WARPS = 8;                        // warps w and w+4 share TME
 constexpr int EPI_THREADS = EPI_WARPS * 32;         // 256
 constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1;
 constexpr int FUSED_THREADS = EPI_THREADS + 64;     // 320
-constexpr int SMEM_FUSED = BLOB_H + NSTAGE * STAGE_BYTES + NVEC * H * 4 + TP * 4 * 4;   // + per-row partial sums (o, dz[3])
+template <int PL> constexpr int smem_fused() { return Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE + NVEC * H * 4 + TP * 4 * 4; }   // + per-row partial sums (o, dz[3])
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
 
@@ -224,12 +278,13 @@ __device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, 
   for (int i = 0; i < NVEC; ++i) svec[i * H + t] = __ldg(src[i] + t);       // t = 0..255
 }
 
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, 2) pass1_kernel(const Work w, const int sweep) {
+template <int PL>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, Geo<PL>::CTAS_PER_SM) pass1_kernel(const Work w, const int sweep) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
-  uint8_t* ring = smem + BLOB_H;
-  float* svec = reinterpret_cast<float*>(smem + BLOB_H + NSTAGE * STAGE_BYTES);
+  uint8_t* ring = smem + Geo<PL>::ACT;
+  float* svec = reinterpret_cast<float*>(smem + Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE);
   float* rowsum = svec + NVEC * H;                                // [TP][4]: o partial, dz[3]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
@@ -239,29 +294,32 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 
   if (warp == W_PROD && lane == 0) {
     // ---------------- producer ----------------
-    Producer pr{&pipe, ring, cluster_ctarank()};
+    Producer<PL> pr{&pipe, ring, cluster_ctarank()};
     uint32_t af = 0, sd = 0;
-    const uint8_t* pe_src = w.pe_blob + g * BLOB_C;
-    const uint8_t* pe6_src = w.pe6_blob + g * BLOB_C;
+    const uint8_t* pe_src = w.pe_blob + g * Geo<PL>::BC;
+    const uint8_t* pe6_src = w.pe6_blob + g * Geo<PL>::BC;
+    auto load_a_tile = [&](const uint8_t* src) {                  // [128 x 192] tile, plane p -> act + p * BLOB_H
+      mbar_arrive_expect_tx(&pipe.a_bulk, PL * BLOB_C);
+#pragma unroll
+      for (int p = 0; p < PL; ++p) bulk_g2s_hint(act + p * BLOB_H, src + p * BLOB_C, BLOB_C, &pipe.a_bulk, pr.pol);
+    };
     for (int k = 0; k < w.Kn; ++k) {
-      const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * GEN_IMG;
-      const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
-      const uint8_t *iW1 = gen, *iW1T = gen + IMG_HC, *iW2 = gen + 2 * IMG_HC, *iW2T = gen + 2 * IMG_HC + IMG_HH;
-      const uint8_t *iWd = sta, *iWa = sta + IMG_HC, *iWaT = sta + IMG_HC + IMG_HH;
+      const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
+      const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
+      const uint8_t *iW1 = gen, *iW1T = gen + PL * IMG_HC, *iW2 = gen + PL * 2 * IMG_HC, *iW2T = gen + PL * (2 * IMG_HC + IMG_HH);
+      const uint8_t *iWd = sta, *iWa = sta + PL * IMG_HC, *iWaT = sta + PL * (IMG_HC + IMG_HH);
       pr.stream(iW1, 0, 4, STAGE_BYTES);              // these do not depend on the activation buffer
       if (k > 0) {
         mbar_wait(&pipe.act_free, af & 1); ++af;
         if (sweep) { mbar_wait(&pipe.st_done, sd & 1); ++sd; }      // last tile of the previous net has been drained
       }
-      mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
-      bulk_g2s(act, pe_src, BLOB_C, &pipe.a_bulk);
+      load_a_tile(pe_src);
       pr.stream(iW1, 4, 12, STAGE_BYTES);
       pr.stream(iW2, 0, 16, STAGE_BYTES);
       pr.stream(iWd, 0, 4, STAGE_BYTES);
       mbar_wait(&pipe.act_free, af & 1); ++af;        // G2a has consumed h1
       if (sweep) { mbar_wait(&pipe.st_done, sd & 1); ++sd; }        // ... and the bulk store has drained it to the workspace
-      mbar_arrive_expect_tx(&pipe.a_bulk, BLOB_C);
-      bulk_g2s(act, pe6_src, BLOB_C, &pipe.a_bulk);
+      load_a_tile(pe6_src);
       pr.stream(iWd, 4, 12, STAGE_BYTES);
       pr.stream(iWa, 0, 16, STAGE_BYTES);
       if (sweep) {
@@ -272,7 +330,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     }
   } else if (warp == W_MMA && lane == 0) {
     // ---------------- MMA issuer ----------------
-    Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+    Issuer<PL> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
     uint32_t ab = 0, ae = 0;
     long long t_epi = 0, t_bulk = 0;
     const long long t_begin = clock64();
@@ -316,14 +374,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     const size_t row = g * TP + r;                                  // index into the pass-local per-point arrays
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     uint32_t ar = 0;
-    long long t_acc = 0;
+    long long t_acc = 0, t_comp = 0, t_mark = 0;
     const long long t_begin = clock64();
     // Drain of a finished activation tile to the workspace: one bulk store by the TMA engine instead of 32 st.global
     // per thread.  Call after epi_done(); `to_producer` when the next writer of the buffer is the bulk-load producer.
+    const uint64_t pol_stream = l2_policy_evict_first();              // activation tiles are written once, read much later
+    const uint64_t pol_keep = l2_policy_evict_last();                 // the tile's coordinate features are re-read for every net
     auto drain = [&](uint8_t* blob, const bool to_producer) {
       epi_bar();                                                    // every thread has written and fenced its part
       if (tid == 0) {
-        bulk_s2g(blob, act, BLOB_H);
+        bulk_s2g_hint(blob, act, Geo<PL>::ACT, pol_stream);        // all planes: they are contiguous on both sides
         bulk_commit();
         bulk_wait_read_all();
         if (to_producer) mbar_arrive(&pipe.st_done);
@@ -331,13 +391,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     };
     if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
-      uint8_t* nt = net_tile(w, b, k, tl);
+      uint8_t* nt = net_tile<PL>(w, b, k, tl);
       epi_bar();                                                    // every warp is done with the previous net's vectors
       load_vectors(svec, w, b, k, tid);
       epi_bar();
       uint32_t m1w[4] = {0u, 0u, 0u, 0u};                            // ReLU mask of a1 for this thread's 128 columns
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
         uint32_t bits = 0;
@@ -356,17 +416,15 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         for (int i = 0; i < 4; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cg * 4 + qd);
-          *reinterpret_cast<uint4*>(act + off) = pk;
+          sts8<PL>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
       }, (w.dbg_flags & 4) != 0);
-      epi_done(&pipe);
-      if (sweep) drain(blob_h(nt, B_H1), true);
+      epi_done(&pipe); t_comp += clock64() - t_mark;
+      if (sweep) drain(blob_h<PL>(nt, B_H1), true);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
       if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
       float os0 = 0.f, os1 = 0.f;
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
 #pragma unroll
@@ -383,16 +441,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cg * 4 + qd);
-          *reinterpret_cast<uint4*>(act + off) = pk;
+          sts8<PL>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
       }, (w.dbg_flags & 4) != 0);
-      epi_done(&pipe);
-      if (sweep) drain(blob_h(nt, B_CC), false);
+      epi_done(&pipe); t_comp += clock64() - t_mark;
+      if (sweep) drain(blob_h<PL>(nt, B_CC), false);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
       if (sweep) epi_bar();
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
 #pragma unroll
@@ -414,14 +470,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           }
           const uint32_t off = piece_off(r, cg * 4 + qd);
           if (sweep) {                                                // values-only calls keep nothing for a backward pass,
-            *reinterpret_cast<uint4*>(blob_h(nt, B_GG) + off) = pack8(v + qd * 8);
-            *reinterpret_cast<uint4*>(act + off) = pack8(um);         // and their buffer already belongs to the next PE tile
+            stg8<PL>(blob_h<PL>(nt, B_GG), BLOB_H, off, v + qd * 8);
+            sts8<PL>(act, BLOB_H, off, um);                           // and their buffer already belongs to the next PE tile
           }
         }
       }, (w.dbg_flags & 4) != 0);
       atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
-      epi_done(&pipe);
-      if (sweep) drain(blob_h(nt, B_UM), false); else epi_bar();
+      epi_done(&pipe); t_comp += clock64() - t_mark;
+      if (sweep) drain(blob_h<PL>(nt, B_UM), false); else epi_bar();
       if (half == 0) {
         if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
         rowsum[r * 4] = 0.f;
@@ -429,7 +485,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
       if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
 #pragma unroll
@@ -439,16 +495,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const uint4 pk = pack8(v + qd * 8);
-          const uint32_t off = piece_off(r, cg * 4 + qd);
-          *reinterpret_cast<uint4*>(act + off) = pk;
+          sts8<PL>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
       }, (w.dbg_flags & 4) != 0);
-      epi_done(&pipe);
-      drain(blob_h(nt, B_YT), sweep < 2);
+      epi_done(&pipe); t_comp += clock64() - t_mark;
+      drain(blob_h<PL>(nt, B_YT), sweep < 2);
       // ---- epilogue 5: qm = acc * m1 ----
       if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
         uint32_t bits = 0u;
@@ -458,17 +512,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          const uint4 pk = pack8(v + qd * 8);
           const uint32_t off = piece_off(r, cg * 4 + qd);
-          if (sweep > 1) *reinterpret_cast<uint4*>(act + off) = pk;
-          else *reinterpret_cast<uint4*>(blob_h(nt, B_QM) + off) = pk;      // decoder-only backward: no G6, the tile goes straight out
+          if (sweep > 1) sts8<PL>(act, BLOB_H, off, v + qd * 8);
+          else stg8<PL>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
         }
       }, (w.dbg_flags & 4) != 0);
-      epi_done(&pipe);
+      epi_done(&pipe); t_comp += clock64() - t_mark;
       if (sweep < 2) continue;
-      drain(blob_h(nt, B_QM), true);
+      drain(blob_h<PL>(nt, B_QM), true);
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after();
+      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       float dz[3] = {0.f, 0.f, 0.f};
       {
         const uint32_t a6 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 96;
@@ -477,7 +530,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         for (int ib = 0; ib < 3; ++ib) {                             // 96 % 6 == 0 keeps the sin/cos pattern static per block
           float pp[32], v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) pp[j] = __ldg(pet + (size_t)(half * 96 + DPE_PARTNER(ib * 32 + j)) * TP);
+          for (int j = 0; j < 32; ++j) pp[j] = ldg_f32_hint(pet + (size_t)(half * 96 + DPE_PARTNER(ib * 32 + j)) * TP, pol_keep);
           tmem_ld32(a6 + ib * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -489,7 +542,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, dz[c]);
-      epi_done(&pipe);
+      epi_done(&pipe); t_comp += clock64() - t_mark;
       epi_bar();
       if (half == 0) {
 #pragma unroll
@@ -503,6 +556,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     if (w.phase_dbg && tid == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)(clock64() - t_begin));
       atomicAdd((unsigned long long*)w.phase_dbg + 5, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 7, (unsigned long long)t_comp);
       atomicAdd((unsigned long long*)w.phase_dbg + 6, 1ull);
     }
   }
@@ -516,14 +570,27 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 // Pass 2: the combined tangent row, the Z-side operands of the weight gradients and three column sums.
 // Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | column-sum accumulators 3 x 256 floats.
 // ------------------------------------------------------------------------------------------------
-constexpr int SMEM_PASS2 = BLOB_H + NSTAGE * STAGE_BYTES + 3 * H * 4 + 16;
+template <int PL> constexpr int smem_pass2() { return Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE + 3 * H * 4 + 16; }
 
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, 2) pass2_kernel(const Work w, const int tangent) {
+// 8 consecutive values of a stored tile: sum of its planes
+template <int PL>
+__device__ __forceinline__ void unpack_planes(const uint4 (&q)[PL], float* v) {
+  unpack8(q[0], v);
+  if (PL == 2) {
+    float l[8];
+    unpack8(q[PL - 1], l);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] += l[e];
+  }
+}
+
+template <int PL>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, Geo<PL>::CTAS_PER_SM) pass2_kernel(const Work w, const int tangent) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
-  uint8_t* ring = smem + BLOB_H;
-  float* csum = reinterpret_cast<float*>(smem + BLOB_H + NSTAGE * STAGE_BYTES);   // [3][H] + sdo
+  uint8_t* ring = smem + Geo<PL>::ACT;
+  float* csum = reinterpret_cast<float*>(smem + Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE);   // [3][H] + sdo
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;
@@ -532,18 +599,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 
   if (warp == W_PROD && lane == 0) {
     if (tangent) {
-      Producer pr{&pipe, ring, cluster_ctarank()};
+      Producer<PL> pr{&pipe, ring, cluster_ctarank()};
       for (int k = 0; k < w.Kn; ++k) {
-        const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * GEN_IMG;
-        const uint8_t* sta = w.img_sta + (size_t)k * STA_IMG;
+        const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
+        const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
         pr.stream(gen, 0, 12, STAGE_BYTES);                      // W1
-        pr.stream(gen + 2 * IMG_HC, 0, 16, STAGE_BYTES);         // W2
-        pr.stream(sta + IMG_HC, 0, 16, STAGE_BYTES);             // Wa
+        pr.stream(gen + PL * 2 * IMG_HC, 0, 16, STAGE_BYTES);    // W2
+        pr.stream(sta + PL * IMG_HC, 0, 16, STAGE_BYTES);        // Wa
       }
     }
   } else if (warp == W_MMA && lane == 0) {
     if (tangent) {
-      Issuer is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+      Issuer<PL> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
       uint32_t ae = 0;
       long long t_epi = 0;
       const long long t_begin = clock64();
@@ -568,36 +635,41 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 128;
     const size_t row = g * TP + r;
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
-    const uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
+    const uint8_t* pe6 = w.pe6_blob + g * Geo<PL>::BC;
     uint32_t ar = 0;
-    long long t_acc = 0;
+    long long t_acc = 0, t_comp = 0, t_mark = 0;
     const long long t_begin = clock64();
+    const uint64_t pol_keep = l2_policy_evict_last();                 // the tile's coordinate features are re-read for every net
     for (int i = tid; i < 3 * H + 4; i += EPI_THREADS) csum[i] = 0.f;
     epi_bar();
     for (int k = 0; k < w.Kn; ++k) {
-      uint8_t* nt = net_tile(w, b, k, tl);
+      uint8_t* nt = net_tile<PL>(w, b, k, tl);
       const float dv = w.dov[row * w.Kn + k];
       float dd[3] = {0.f, 0.f, 0.f};
       if (tangent) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];
       }
-      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1 = bf16 hi/lo of dov, rest 0
+      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three bf16 terms, rest 0
       if (half == 0) {
         const float hi = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
-        float a8[8] = {hi, dv - hi, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        *reinterpret_cast<uint4*>(blob_aux(nt) + piece_off(r, 0)) = pack8(a8);
-        *reinterpret_cast<uint4*>(blob_aux(nt) + piece_off(r, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        const float mid = __uint_as_float(__float_as_uint(dv - hi) & 0xFFFF0000u);
+        float a8[8] = {hi, mid, (dv - hi) - mid, 0.f, 0.f, 0.f, 0.f, 0.f};
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 0)), pack8(a8));
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 1)), make_uint4(0u, 0u, 0u, 0u));
       }
       // ---- prologue: xt -> activation buffer; zp, zd -> workspace (each half takes 4 of the 8 column groups) ----
+      t_mark = clock64();
 #pragma unroll 1
       for (int it = half * 4; it < half * 4 + 4; ++it) {             // 24 columns = 4 frequencies = 3 pieces per iteration
         float pe[24], xt[24], zp[24];
-        uint4 p6[3];
+        uint4 p6[3][PL];
 #pragma unroll
-        for (int j = 0; j < 24; ++j) pe[j] = __ldg(pet + (size_t)(it * 24 + j) * TP);
+        for (int j = 0; j < 24; ++j) pe[j] = ldg_f32_hint(pet + (size_t)(it * 24 + j) * TP, pol_keep);
 #pragma unroll
-        for (int qd = 0; qd < 3; ++qd) p6[qd] = __ldg(reinterpret_cast<const uint4*>(pe6 + piece_off(r, it * 3 + qd)));
+        for (int qd = 0; qd < 3; ++qd)
+#pragma unroll
+          for (int p = 0; p < PL; ++p) p6[qd][p] = ldg_v4_hint(pe6 + p * BLOB_C + piece_off(r, it * 3 + qd), pol_keep);
 #pragma unroll
         for (int j = 0; j < 24; ++j) {
           const int J = it * 24 + j;                                  // it*24 is a multiple of 6: partner stays inside the block
@@ -608,39 +680,46 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
         for (int qd = 0; qd < 3; ++qd) {
           const uint32_t off = piece_off(r, it * 3 + qd);
-          if (tangent) *reinterpret_cast<uint4*>(act + off) = pack8(xt + qd * 8);
-          *reinterpret_cast<uint4*>(blob_zp(nt) + off) = pack8(zp + qd * 8);
+          if (tangent) sts8<PL>(act, BLOB_H, off, xt + qd * 8);
+          stg8<PL>(blob_zp<PL>(nt), BLOB_C, off, zp + qd * 8);
           float d6[8];
-          unpack8(p6[qd], d6);
+          unpack_planes<PL>(p6[qd], d6);
 #pragma unroll
           for (int e = 0; e < 8; ++e) d6[e] *= dv;
-          *reinterpret_cast<uint4*>(blob_zd(nt) + off) = pack8(d6);
+          stg8<PL>(blob_zd<PL>(nt), BLOB_C, off, d6);
         }
       }
-      if (tangent) epi_done(&pipe);
+      if (tangent) { epi_done(&pipe); t_comp += clock64() - t_mark; }
       // ---- epilogue 7: ht = acc*m1, zh = dv*h1 + ht ;  8: ct = acc, zc = dv*c + ct ;  9: gz = dv*g + acc*m3 ----
 #pragma unroll 1
       for (int st = 0; st < 3; ++st) {
-        const uint8_t* src = blob_h(nt, st == 0 ? B_H1 : (st == 1 ? B_CC : B_GG));
-        uint8_t* dst = blob_h(nt, st == 0 ? B_ZH : B_ZC);
-        uint4 nxt[4];
+        const uint8_t* src = blob_h<PL>(nt, st == 0 ? B_H1 : (st == 1 ? B_CC : B_GG));
+        uint8_t* dst = blob_h<PL>(nt, st == 0 ? B_ZH : B_ZC);
+        uint4 nxt[4][PL];
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, c0 * 4 + qd)));
-        if (tangent) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
+        for (int qd = 0; qd < 4; ++qd)
+#pragma unroll
+          for (int p = 0; p < PL; ++p) nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + piece_off(r, c0 * 4 + qd)));
+        if (tangent) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64(); }
         auto process = [&](const int cb, float (&v)[32]) {
           const int cg = c0 + cb;
-          uint4 cur[4];
+          uint4 cur[4][PL];
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) cur[qd] = nxt[qd];
+          for (int qd = 0; qd < 4; ++qd)
+#pragma unroll
+            for (int p = 0; p < PL; ++p) cur[qd][p] = nxt[qd][p];
           if (cb < 3) {
 #pragma unroll
-            for (int qd = 0; qd < 4; ++qd) nxt[qd] = __ldg(reinterpret_cast<const uint4*>(src + piece_off(r, (cg + 1) * 4 + qd)));
+            for (int qd = 0; qd < 4; ++qd)
+#pragma unroll
+              for (int p = 0; p < PL; ++p)
+                nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + piece_off(r, (cg + 1) * 4 + qd)));
           }
           float z[32];
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             float s[8];
-            unpack8(cur[qd], s);
+            unpack_planes<PL>(cur[qd], s);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
               float t = v[qd * 8 + e];
@@ -649,8 +728,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
               z[qd * 8 + e] = fmaf(dv, s[e], t);
             }
             const uint32_t off = piece_off(r, cg * 4 + qd);
-            if (st < 2) *reinterpret_cast<uint4*>(dst + off) = pack8(z + qd * 8);
-            if (tangent && st < 2) *reinterpret_cast<uint4*>(act + off) = pack8(v + qd * 8);
+            if (st < 2) stg8<PL>(dst, BLOB_H, off, z + qd * 8);
+            if (tangent && st < 2) sts8<PL>(act, BLOB_H, off, v + qd * 8);
           }
           if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
             const float cs = warp_colsum32(z, lane);
@@ -659,7 +738,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
                 float s[8];
-                unpack8(cur[qd], s);
+                unpack8(cur[qd][0], s);                                // sign of the hi plane = sign of the value
 #pragma unroll
                 for (int e = 0; e < 8; ++e) z[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
               }
@@ -680,6 +759,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           }
         }
         if (tangent && st < 2) epi_done(&pipe);
+        t_comp += clock64() - t_mark;
       }
       // ---- flush this net's column sums ----
       if (half == 0) {
@@ -701,6 +781,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     if (w.phase_dbg && tid == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 12, (unsigned long long)(clock64() - t_begin));
       atomicAdd((unsigned long long*)w.phase_dbg + 13, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 15, (unsigned long long)t_comp);
       atomicAdd((unsigned long long*)w.phase_dbg + 14, 1ull);
     }
   }
@@ -724,15 +805,16 @@ struct WgradWork {
   float *gb1, *gb2, *ge, *gbd;
 };
 
-constexpr int SMEM_WGRAD = BLOB_H / 2 + BLOB_H + AUX_BYTES;          // 102400
+template <int PL> constexpr int smem_wgrad() { return PL * (BLOB_H / 2 + BLOB_H) + AUX_BYTES; }   // 102400 / 200704
 
-__global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
+template <int PL>
+__global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const WgradWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full, empty, acc_ready;
   __shared__ uint32_t tmem_s;
-  uint8_t* sJ = smem;                 // 32 KB: 128 points x 128 out (half)
-  uint8_t* sZ = smem + BLOB_H / 2;    // up to 64 KB
-  uint8_t* sX = smem + BLOB_H / 2 + BLOB_H;   // 4 KB seed tile
+  uint8_t* sJ = smem;                          // PL x 32 KB: 128 points x 128 out (half), plane p at p * 32 KB
+  uint8_t* sZ = smem + PL * (BLOB_H / 2);      // PL x up to 64 KB, plane p at p * zbytes
+  uint8_t* sX = smem + PL * (BLOB_H / 2 + BLOB_H);   // 4 KB seed tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   int item = blockIdx.x;
   const int split = item % w.splits; item /= w.splits;
@@ -756,16 +838,18 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
   if (t1 > t0) {
     if (warp == 4 && lane == 0) {
       for (int t = t0; t < t1; ++t) {
-        const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * NET_TILE_BYTES;
-        const uint8_t* zsrc = layer == 0 ? nt + (size_t)NBLOB_H * BLOB_H
-                            : layer == 3 ? nt + (size_t)NBLOB_H * BLOB_H + BLOB_C
-                            : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * BLOB_H;
+        const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
+        const uint8_t* zsrc = layer == 0 ? nt + (size_t)NBLOB_H * Geo<PL>::BH
+                            : layer == 3 ? nt + (size_t)NBLOB_H * Geo<PL>::BH + Geo<PL>::BC
+                            : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * Geo<PL>::BH;
         const uint32_t i = t - t0;
         mbar_wait(&empty, (i & 1) ^ 1);
-        mbar_arrive_expect_tx(&full, BLOB_H / 2 + zbytes + (aux ? AUX_BYTES : 0));
-        bulk_g2s(sJ, nt + (size_t)jsel * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
-        bulk_g2s(sZ, zsrc, zbytes, &full);
-        if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * BLOB_H + 2 * BLOB_C, AUX_BYTES, &full);
+        mbar_arrive_expect_tx(&full, PL * (BLOB_H / 2 + zbytes) + (aux ? AUX_BYTES : 0));
+#pragma unroll
+        for (int p = 0; p < PL; ++p)
+          bulk_g2s(sJ + p * (BLOB_H / 2), nt + (size_t)jsel * Geo<PL>::BH + (size_t)p * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
+        bulk_g2s(sZ, zsrc, PL * zbytes, &full);                        // the planes of a tile are contiguous
+        if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC, AUX_BYTES, &full);
       }
     } else if (warp == 5 && lane == 0) {
       const uint32_t idesc = idesc_bf16(Nn, 1, 1), idesc_x = idesc_bf16(16, 1, 1);
@@ -775,12 +859,22 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {                              // 16 points per MMA
+          const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
           const uint64_t ad = smem_desc(smem_u32(sJ) + ks * 256, 128, CORE_STRIDE);
           const uint64_t bd = smem_desc(smem_u32(sZ) + ks * 256, 128, CORE_STRIDE);
-          mma_bf16(tmem, ad, bd, idesc, (i > 0 || ks > 0) ? 1u : 0u);
+          if (PL == 2) {
+            const uint64_t al = smem_desc(smem_u32(sJ) + BLOB_H / 2 + ks * 256, 128, CORE_STRIDE);
+            const uint64_t bl = smem_desc(smem_u32(sZ) + zbytes + ks * 256, 128, CORE_STRIDE);
+            mma_bf16(tmem, al, bd, idesc, first);
+            mma_bf16(tmem, ad, bl, idesc, 1u);
+            mma_bf16(tmem, ad, bd, idesc, 1u);
+          } else {
+            mma_bf16(tmem, ad, bd, idesc, first);
+          }
           if (aux) {
             const uint64_t xd = smem_desc(smem_u32(sX) + ks * 256, 128, CORE_STRIDE);
-            mma_bf16(tmem + C, ad, xd, idesc_x, (i > 0 || ks > 0) ? 1u : 0u);
+            mma_bf16(tmem + C, ad, xd, idesc_x, first);
+            if (PL == 2) mma_bf16(tmem + C, smem_desc(smem_u32(sJ) + BLOB_H / 2 + ks * 256, 128, CORE_STRIDE), xd, idesc_x, 1u);
           }
         }
         mma_commit(&empty);
@@ -803,7 +897,7 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
       }
       if (aux) {
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + C, v);
-        const float bsum = v[0] + v[1];                                // hi + lo halves of the seed
+        const float bsum = v[0] + v[1] + v[2];                         // the three bf16 terms of the seed
         const int out = mh * TP + tid;
         if (layer == 0) {
           atomicAdd(w.gb1 + gk * H + out, bsum);
@@ -823,7 +917,10 @@ __global__ void __launch_bounds__(192, 2) wgrad_kernel(const WgradWork w) {
 // ------------------------------------------------------------------------------------------------
 // SIMT helpers of the tensor-core mode
 // ------------------------------------------------------------------------------------------------
-// fp32 weight matrix [R_src x K_src] -> bf16 image in layout (*) ; transpose = image rows are source columns
+// fp32 weight matrix [R_src x K_src] -> bf16 image in layout (*) ; transpose = image rows are source columns.
+// The image is a sequence of K = 16 chunks (two k-cores, rows*32 bytes per plane); with PL planes a chunk is
+// [hi plane | lo plane], so the producer still fetches one contiguous block per chunk.
+template <int PL>
 __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
                              size_t dst_stride, int rows, int kd, int transpose) {
   const float* S = src + blockIdx.y * src_stride;
@@ -834,10 +931,15 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = transpose ? S[(size_t)(kc * 8 + e) * rows + r] : S[(size_t)r * kd + kc * 8 + e];
-  *reinterpret_cast<uint4*>(D + (size_t)q * 16) = pack8(v);
+  uint4 pq[PL];
+  split8<PL>(v, pq);
+  const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)(kc & 1) * rows * 16 + (size_t)r * 16;
+#pragma unroll
+  for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * rows * 32) = pq[p];
 }
 
 // coordinate / data features of one tile: bf16 blobs (GEMM operands) and the fp32 transposed copy (epilogues)
+template <int PL>
 __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Work w, const float* __restrict__ x,
                                                     const float* __restrict__ y, const float* __restrict__ t) {
   const size_t g = blockIdx.x;
@@ -851,8 +953,8 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
 #pragma unroll
     for (int c = 0; c < 6; ++c) d[c] = w.coord_data[q * 6 + c];
   }
-  uint8_t* pe = w.pe_blob + g * BLOB_C;
-  uint8_t* pe6 = w.pe6_blob + g * BLOB_C;
+  uint8_t* pe = w.pe_blob + g * Geo<PL>::BC;
+  uint8_t* pe6 = w.pe6_blob + g * Geo<PL>::BC;
   float* pet = w.pet + g * (size_t)(C * TP) + r;
   float buf[24];
 #pragma unroll 1
@@ -871,7 +973,7 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
 #pragma unroll
     for (int j = 0; j < 24; ++j) pet[(size_t)(it * 24 + j) * TP] = buf[j];
 #pragma unroll
-    for (int qd = 0; qd < 3; ++qd) *reinterpret_cast<uint4*>(pe + piece_off(r, it * 3 + qd)) = pack8(buf + qd * 8);
+    for (int qd = 0; qd < 3; ++qd) sts8<PL>(pe, BLOB_C, piece_off(r, it * 3 + qd), buf + qd * 8);      // (plain global stores)
   }
 #pragma unroll 1
   for (int it = 0; it < 8; ++it) {                                   // 2 frequencies x (6 sin, 6 cos)
@@ -887,7 +989,7 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
       }
     }
 #pragma unroll
-    for (int qd = 0; qd < 3; ++qd) *reinterpret_cast<uint4*>(pe6 + piece_off(r, it * 3 + qd)) = pack8(buf + qd * 8);
+    for (int qd = 0; qd < 3; ++qd) sts8<PL>(pe6, BLOB_C, piece_off(r, it * 3 + qd), buf + qd * 8);
   }
 }
 
@@ -930,17 +1032,17 @@ struct Carve {
 
 static inline size_t al(size_t n) { return (n + 1023) & ~(size_t)1023; }
 
-static Carve carve(uint8_t* base, int chunk, int Kn, int B) {
+static Carve carve(uint8_t* base, int chunk, int Kn, int B, int pl) {
   Carve c;
   const size_t T = ((size_t)(chunk + TP - 1) / TP + CLUSTER - 1) / CLUSTER * CLUSTER, rows = (size_t)B * T * TP;
   size_t off = 0;
   auto take = [&](size_t bytes) { uint8_t* p = base + off; off += al(bytes); return p; };
-  c.img_gen = take((size_t)B * Kn * GEN_IMG);
-  c.img_sta = take((size_t)Kn * STA_IMG);
-  c.pe_blob = take((size_t)B * T * BLOB_C);
-  c.pe6_blob = take((size_t)B * T * BLOB_C);
+  c.img_gen = take((size_t)B * Kn * GEN_IMG * pl);
+  c.img_sta = take((size_t)Kn * STA_IMG * pl);
+  c.pe_blob = take((size_t)B * T * BLOB_C * pl);
+  c.pe6_blob = take((size_t)B * T * BLOB_C * pl);
   c.pet = reinterpret_cast<float*>(take((size_t)B * T * C * TP * 4));
-  c.blobs = take((size_t)B * Kn * T * NET_TILE_BYTES);
+  c.blobs = take((size_t)B * Kn * T * (pl == 2 ? Geo<2>::NET_TILE : Geo<1>::NET_TILE));
   c.o = reinterpret_cast<float*>(take(rows * Kn * 4));
   c.od = reinterpret_cast<float*>(take(rows * Kn * 12));
   c.dov = reinterpret_cast<float*>(take(rows * Kn * 4));
@@ -958,14 +1060,15 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B) {
   return c;
 }
 
-int default_chunk(int B) {
-  int c = DEFAULT_POINTS_IN_FLIGHT / (B > 0 ? B : 1);
+int default_chunk(int B, int planes) {
+  int c = DEFAULT_POINTS_IN_FLIGHT / planes / (B > 0 ? B : 1);
   c = c / TP * TP;
   return c < TP ? TP : c;
 }
 
-size_t workspace_bytes(int chunk, int Kn, int B) { return carve(nullptr, chunk, Kn, B).bytes; }
+size_t workspace_bytes(int chunk, int Kn, int B, int planes) { return carve(nullptr, chunk, Kn, B, planes).bytes; }
 
+template <int PL>
 static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
   struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; };
   const Spec specs[] = {
@@ -979,28 +1082,29 @@ static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cuda
   };
   for (const Spec& s : specs) {
     const int pieces = s.rows * s.kd / 8;
-    image_kernel<<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff, s.dstride,
-                                                                        s.rows, s.kd, s.tr);
+    image_kernel<PL><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
+                                                                            s.rows, s.kd, s.tr);
     DPN_LAUNCH_OK();
   }
   return 0;
 }
 
-int run(const Job& J, cudaStream_t st) {
+template <int PL>
+static int run_planes(const Job& J, cudaStream_t st) {
   const int B = J.shape.B, N = J.shape.N, Kn = J.shape.K, chunk = J.chunk;
   if (J.pts->coord_pe) {
-    set_error("bf16 mode derives the coordinate encoding from x,y,t; pre-encoded coord_pe is served by the fp32 kernels");
+    set_error("the tensor-core modes derive the coordinate encoding from x,y,t; pre-encoded coord_pe is served by the fp32 kernels");
     return DPN_E_UNSUPPORTED;
   }
   static bool attr_done = false;
-  const int smem_fused = SMEM_FUSED, smem_pass2 = SMEM_PASS2, smem_wgrad = SMEM_WGRAD;
+  const int smem_fused = tc::smem_fused<PL>(), smem_pass2 = tc::smem_pass2<PL>(), smem_wgrad = tc::smem_wgrad<PL>();
   if (!attr_done) {
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
-    DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
+    DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
     attr_done = true;
   }
-  Carve c = carve(reinterpret_cast<uint8_t*>(J.workspace), chunk, Kn, B);
+  Carve c = carve(reinterpret_cast<uint8_t*>(J.workspace), chunk, Kn, B, PL);
   const DpnWeights& Wt = *J.w;
   const bool pde = J.kind == JOB_PDE;
   const bool want_bwd = J.grads != nullptr;
@@ -1011,7 +1115,7 @@ int run(const Job& J, cudaStream_t st) {
   static const bool phase_debug = getenv("DPN_PHASE_DEBUG") != nullptr;
   if (phase_debug) DPN_CUDA_OK(cudaMemsetAsync(c.dbg, 0, 16 * 8, st));
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
-  if ((rc = make_images(Wt, c, B, Kn, st))) return rc;
+  if ((rc = make_images<PL>(Wt, c, B, Kn, st))) return rc;
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
   if (want_bwd) {
     const DpnGrads& G = *J.grads;
@@ -1047,9 +1151,9 @@ int run(const Job& J, cudaStream_t st) {
     w.dbg_flags = getenv("DPN_DEBUG_FLAGS") ? atoi(getenv("DPN_DEBUG_FLAGS")) : 0;
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
-    encode_kernel<<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
+    encode_kernel<PL><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
     DPN_LAUNCH_OK();
-    pass1_kernel<<<tiles, FUSED_THREADS, smem_fused, st>>>(w, sweep);
+    pass1_kernel<PL><<<tiles, FUSED_THREADS, smem_fused, st>>>(w, sweep);
     DPN_LAUNCH_OK();
     if (J.kind == JOB_DEC_FWD) {
       gather_o_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.o);
@@ -1075,18 +1179,18 @@ int run(const Job& J, cudaStream_t st) {
     }
     if (!want_bwd) continue;
     const DpnGrads& G = *J.grads;
-    pass2_kernel<<<tiles, FUSED_THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
+    pass2_kernel<PL><<<tiles, FUSED_THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd;
     const int items = B * Kn * 8;
-    int splits = (2 * 148 * 2 + items - 1) / items;
+    int splits = (Geo<PL>::CTAS_PER_SM * 148 * 2 + items - 1) / items;
     if (splits > T) splits = T;
     if (splits < 1) splits = 1;
     ww.splits = splits;
-    wgrad_kernel<<<items * splits, 192, smem_wgrad, st>>>(ww);
+    wgrad_kernel<PL><<<items * splits, 192, smem_wgrad, st>>>(ww);
     DPN_LAUNCH_OK();
   }
   if (phase_debug) {
@@ -1095,9 +1199,9 @@ int run(const Job& J, cudaStream_t st) {
     DPN_CUDA_OK(cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost));
     const double n1 = h[6] > 0 ? (double)h[6] : 1.0, n2 = h[14] > 0 ? (double)h[14] : 1.0;
     fprintf(stderr, "[dpn phase] pass1 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f | wait A tile %.0f || "
-                    "epilogue-thread total %.0f | wait accumulator %.0f\n", h[0] / n1, h[1] / n1, h[2] / n1, h[3] / n1, h[4] / n1, h[5] / n1);
+                    "epilogue-thread total %.0f | wait accumulator %.0f | acc ready -> tile handed over %.0f\n", h[0] / n1, h[1] / n1, h[2] / n1, h[3] / n1, h[4] / n1, h[5] / n1, h[7] / n1);
     fprintf(stderr, "[dpn phase] pass2 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f || "
-                    "epilogue-thread total %.0f | wait accumulator %.0f\n", h[8] / n2, h[9] / n2, h[10] / n2, h[12] / n2, h[13] / n2);
+                    "epilogue-thread total %.0f | wait accumulator %.0f | compute %.0f\n", h[8] / n2, h[9] / n2, h[10] / n2, h[12] / n2, h[13] / n2, h[15] / n2);
   }
   if (want_bwd) {
     if ((rc = f32::launch_finalize(Kn, Wt, c.vc, c.vg, c.sdo, *J.grads, st))) return rc;
@@ -1106,6 +1210,8 @@ int run(const Job& J, cudaStream_t st) {
   }
   return 0;
 }
+
+int run(const Job& J, cudaStream_t st) { return J.shape.mode == DPN_MODE_BF16X3 ? run_planes<2>(J, st) : run_planes<1>(J, st); }
 
 }  // namespace tc
 }  // namespace dpn

@@ -1,14 +1,14 @@
-// DPN_MODE_BF16: tcgen05 / TMEM / bulk-copy path (see dpn_tc.cu).
+// DPN_MODE_BF16 / DPN_MODE_BF16X3: tcgen05 / TMEM / bulk-copy path (see dpn_tc.cu); planes = 1 / 2 bf16 terms per operand.
 #pragma once
 #include "dpn_fp32.cuh"
 
 namespace dpn {
 namespace tc {
 
-constexpr int DEFAULT_POINTS_IN_FLIGHT = 262144;   // B * chunk: bounds the workspace (~34 KB per point)
+constexpr int DEFAULT_POINTS_IN_FLIGHT = 262144;   // B * chunk * planes: bounds the workspace (~34 KB per point and plane)
 
-int default_chunk(int B);                          // points per sample per pass (multiple of 128)
-size_t workspace_bytes(int chunk, int Kn, int B);
+int default_chunk(int B, int planes);              // points per sample per pass (multiple of 128)
+size_t workspace_bytes(int chunk, int Kn, int B, int planes);
 int run(const Job& job, cudaStream_t st);
 
 }  // namespace tc

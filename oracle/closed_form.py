@@ -30,6 +30,13 @@ def bf16_round(a):
     return a.to(torch.bfloat16).to(a.dtype)
 
 
+def bf16_split_round(a):
+    """Operand as the bf16x3 mode sees it: hi = bf16(a) plus lo = bf16(a - hi) (16 mantissa bits).  The emulation keeps
+    the lo*lo product the kernels drop (2^-18 relative, below the representation error)."""
+    hi = bf16_round(a)
+    return hi + bf16_round(a - hi)
+
+
 def coord_features(x, y, t, dx, dy, lat_size, lon_size, t_span):
     """PE [N,192] and dPE/dz [N,192] (z-space derivative; column j differentiates w.r.t. z_{j%3})."""
     z = torch.cat((x / dx / (lon_size - 1), y / dy / (lat_size - 1), t / t_span), dim=1)   # [N,3]

@@ -30,5 +30,10 @@ print("mode %s: per-step ms: first %s ... min %.2f median %.2f max %.2f mean %.2
       (mode, ["%.2f" % m for m in ms[:6]], min(ms), sorted(ms)[len(ms)//2], max(ms), sum(ms)/len(ms), (t1-t0)*1e3, (t2-t0)*1e3))
 print("every 5th:", ["%.1f" % m for m in ms[::5]])
 smi.terminate(); smi.wait()
+cpu = []
+for _ in range(10):
+    torch.cuda.synchronize(); a = time.perf_counter(); step(); cpu.append((time.perf_counter() - a) * 1e3)
+torch.cuda.synchronize()
+print("CPU issue time of one call on an idle queue (ms): min %.2f median %.2f" % (min(cpu), sorted(cpu)[5]))
 lines = open("/tmp/smi.csv").read().strip().splitlines()
 print("smi samples %d; first/last few:" % len(lines)); print("\n".join(lines[:3] + ["..."] + lines[-12:]))
