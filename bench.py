@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "fp32"])
+    ap.add_argument("--mode", default="bf16", choices=["bf16", "bf16x3", "f16x3", "fp32"])
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--points", type=int, default=65536)
     ap.add_argument("--cpu-points", type=int, default=4096)

@@ -59,6 +59,8 @@ struct Geo {
 };
 enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, NVEC };   // epilogue vectors staged in shared memory per net
 
+struct NetScales;
+
 struct Work {
   // geometry of this pass
   int B, Kn, T;            // samples, nets, tiles per sample
@@ -79,6 +81,7 @@ struct Work {
   uint8_t* blobs;          // [B][Kn][T][NET_TILE_BYTES]
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
   float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
+  const NetScales* sc;         // [B][Kn] scaling plan (fp16 variant only)
   long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (DPN_PHASE_DEBUG=1), summed over CTAs
   int dbg_flags;               // timing experiments only (DPN_DEBUG_FLAGS): 1 = no blob stores, 2 = no act stores, 4 = no TMEM loads
   float band[NF];
@@ -107,33 +110,81 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* v) {
     v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
   }
 }
-// 8 fp32 values -> one 16-byte piece per plane: hi = bf16(v), lo = bf16(v - hi)  (v - hi is exact in fp32)
-template <int PL>
+// 16-bit operand format: bf16 (8-bit mantissa, fp32 range) or fp16 (11-bit mantissa; callers pre-scale into its range)
+template <bool F16>
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  if (F16) return make_uint4(pack_f16(v[0], v[1]), pack_f16(v[2], v[3]), pack_f16(v[4], v[5]), pack_f16(v[6], v[7]));
+  return pack8(v);
+}
+template <bool F16>
+__device__ __forceinline__ void unpack8f(const uint4& q, float* v) {
+  if (F16) {
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  } else {
+    unpack8(q, v);
+  }
+}
+// 8 fp32 values -> one 16-byte piece per plane: hi = rn16(v), lo = rn16(v - hi)  (v - hi is exact in fp32)
+template <int PL, bool F16 = false>
 __device__ __forceinline__ void split8(const float* v, uint4 (&q)[PL]) {
-  q[0] = pack8(v);
+  q[0] = pack8f<F16>(v);
   if (PL == 2) {
     float h[8], l[8];
-    unpack8(q[0], h);
+    unpack8f<F16>(q[0], h);
 #pragma unroll
     for (int e = 0; e < 8; ++e) l[e] = v[e] - h[e];
-    q[PL - 1] = pack8(l);
+    q[PL - 1] = pack8f<F16>(l);
   }
 }
 // store a piece into a tile whose planes are `plane` bytes apart: shared memory (sts8) / workspace, streaming (stg8)
-template <int PL>
+template <int PL, bool F16 = false>
 __device__ __forceinline__ void sts8(uint8_t* tile, uint32_t plane, uint32_t off, const float* v) {
   uint4 q[PL];
-  split8<PL>(v, q);
+  split8<PL, F16>(v, q);
 #pragma unroll
   for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(tile + p * plane + off) = q[p];
 }
-template <int PL>
+template <int PL, bool F16 = false>
 __device__ __forceinline__ void stg8(uint8_t* tile, uint32_t plane, uint32_t off, const float* v) {
   uint4 q[PL];
-  split8<PL>(v, q);
+  split8<PL, F16>(v, q);
 #pragma unroll
   for (int p = 0; p < PL; ++p) __stcs(reinterpret_cast<uint4*>(tile + p * plane + off), q[p]);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Scaling plan of the fp16 variant (DPN_MODE_F16X3).  fp16 carries 11 mantissa bits but only 5 exponent bits, so every
+// operand tile is multiplied by a power of two (exact to apply, exact to undo in the epilogue) that maps a RIGOROUS
+// bound of its magnitude to 2^15.  Bounds come from row / column L1 norms of the weights (|PE| <= 1), so no value can
+// overflow whatever the weights are; the 30 binades of fp16 below the bound absorb the looseness of the bounds.
+// ------------------------------------------------------------------------------------------------
+struct NetScales {                       // one per (sample, net)
+  float sW1, sW2, sWd, sWa;              // weight images (a matrix and its transpose share the factor)
+  float sH1, sC, sG, sUM, sY, sQ;        // tiles written by pass 1: h1, c, g, u*m3, y, q*m1
+  float M1, Mc, l1W1, l1W12;             // bounds of |h1|, |c|; L1(W1), L1(W1) L1(W2)
+  float rowB;                            // max(1, L1(W1), L1(W1) L1(W2)): growth of the pass-2 tangent row over its chain
+  float cap;                             // largest sH1 * sW2 this (sample, net) can carry (plan_kernel takes the min over samples)
+  float sZP, sZH, sZC, sZD, sDV;         // Z-side tiles and the seed tile of the CURRENT chunk (zscale_kernel)
+  float pad_;
+};
+constexpr float S_PE = 1024.f;           // coordinate / data features lie in [-1, 1]
+constexpr float F16_TOP = 32768.f;       // bound -> 2^15 (fp16 max is 65504)
+
+__host__ __device__ __forceinline__ float pow2_floor(float x) {           // largest power of two <= x, clamped to [2^-40, 2^40]
+  if (!(x > 9.094947e-13f)) return 9.094947e-13f;                         // also catches NaN / 0 / negatives
+  if (x > 1.0995116e12f) return 1.0995116e12f;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__float_as_uint(x) & 0x7F800000u);
+#else
+  uint32_t u; memcpy(&u, &x, 4); u &= 0x7F800000u; float r; memcpy(&r, &u, 4); return r;
+#endif
+}
+__device__ __forceinline__ float scale_for(float bound) { return pow2_floor(F16_TOP / fmaxf(bound, 1e-30f)); }
 // element (r, 8*kc .. 8*kc+7) of a 128-row blob
 __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)kc * CORE_STRIDE + (uint32_t)r * 16; }
 
@@ -174,11 +225,11 @@ struct Producer {
 };
 
 // MMA side: one elected thread.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major, Nn rows).
-template <int PL>
+template <int PL, bool F16 = false>
 struct Issuer {
   Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t n = 0; long long t_full = 0;
   __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate) {
-    const uint32_t idesc = idesc_bf16(Nn, 0, 0);
+    const uint32_t idesc = idesc_16(F16, Nn, 0, 0);
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
       mbar_wait_t(&pp->full[s], ph, t_full);
@@ -278,7 +329,7 @@ __device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, 
   for (int i = 0; i < NVEC; ++i) svec[i * H + t] = __ldg(src[i] + t);       // t = 0..255
 }
 
-template <int PL>
+template <int PL, bool F16>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, Geo<PL>::CTAS_PER_SM) pass1_kernel(const Work w, const int sweep) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
@@ -330,7 +381,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     }
   } else if (warp == W_MMA && lane == 0) {
     // ---------------- MMA issuer ----------------
-    Issuer<PL> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+    Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
     uint32_t ab = 0, ae = 0;
     long long t_epi = 0, t_bulk = 0;
     const long long t_begin = clock64();
@@ -395,6 +446,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       epi_bar();                                                    // every warp is done with the previous net's vectors
       load_vectors(svec, w, b, k, tid);
       epi_bar();
+      // fp16 variant: accumulators carry (scale of A tile) x (scale of weight image); i* undo that, s* scale the next tile
+      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f;
+      if (F16) {
+        const NetScales t = w.sc[b * w.Kn + k];
+        i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / (t.sUM * t.sWa);
+        i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
+        sH1 = t.sH1; sC = t.sC; sG = t.sG; sUM = t.sUM; sY = t.sY;
+      }
       uint32_t m1w[4] = {0u, 0u, 0u, 0u};                            // ReLU mask of a1 for this thread's 128 columns
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
@@ -407,16 +466,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = v[j4 * 4 + e] + bb[e];
+            const float a = F16 ? fmaf(v[j4 * 4 + e], i1, bb[e]) : v[j4 * 4 + e] + bb[e];
             bits |= (a > 0.f ? 1u : 0u) << (j4 * 4 + e);
-            v[j4 * 4 + e] = fmaxf(a, 0.f);
+            v[j4 * 4 + e] = F16 ? fmaxf(a, 0.f) * sH1 : fmaxf(a, 0.f);
           }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          sts8<PL>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
+          sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
       }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe); t_comp += clock64() - t_mark;
@@ -434,14 +493,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float cc = v[j4 * 4 + e] + bb[e];
+            const float cc = F16 ? fmaf(v[j4 * 4 + e], i2, bb[e]) : v[j4 * 4 + e] + bb[e];
             if (e & 1) os1 = fmaf(ww[e], cc, os1); else os0 = fmaf(ww[e], cc, os0);
-            v[j4 * 4 + e] = cc;
+            v[j4 * 4 + e] = F16 ? cc * sC : cc;
           }
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          sts8<PL>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
+          sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
       }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe); t_comp += clock64() - t_mark;
@@ -461,17 +520,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
             const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a = v[qd * 8 + h2 * 4 + e] + bb[e];
+              const float a = F16 ? fmaf(v[qd * 8 + h2 * 4 + e], i3, bb[e]) : v[qd * 8 + h2 * 4 + e] + bb[e];
               const float gg = fmaxf(a, 0.f);
               if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
-              v[qd * 8 + h2 * 4 + e] = gg;
-              um[h2 * 4 + e] = a > 0.f ? uu[e] : 0.f;
+              v[qd * 8 + h2 * 4 + e] = F16 ? gg * sG : gg;
+              um[h2 * 4 + e] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;
             }
           }
           const uint32_t off = piece_off(r, cg * 4 + qd);
           if (sweep) {                                                // values-only calls keep nothing for a backward pass,
-            stg8<PL>(blob_h<PL>(nt, B_GG), BLOB_H, off, v + qd * 8);
-            sts8<PL>(act, BLOB_H, off, um);                           // and their buffer already belongs to the next PE tile
+            stg8<PL, F16>(blob_h<PL>(nt, B_GG), BLOB_H, off, v + qd * 8);
+            sts8<PL, F16>(act, BLOB_H, off, um);                           // and their buffer already belongs to the next PE tile
           }
         }
       }, (w.dbg_flags & 4) != 0);
@@ -491,11 +550,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
-          v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
+          if (F16) {
+            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], i4, wv.x) * sY; v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], i4, wv.y) * sY;
+            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], i4, wv.z) * sY; v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], i4, wv.w) * sY;
+          } else {
+            v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
+          }
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
-          sts8<PL>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
+          sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
       }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe); t_comp += clock64() - t_mark;
@@ -509,12 +573,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
         for (int i = 0; i < 4; ++i) bits = (cb == i) ? m1w[i] : bits;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
+        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint32_t off = piece_off(r, cg * 4 + qd);
-          if (sweep > 1) sts8<PL>(act, BLOB_H, off, v + qd * 8);
-          else stg8<PL>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
+          if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
+          else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
         }
       }, (w.dbg_flags & 4) != 0);
       epi_done(&pipe); t_comp += clock64() - t_mark;
@@ -541,7 +605,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         }
       }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, dz[c]);
+      for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, F16 ? dz[c] * i6 : dz[c]);
       epi_done(&pipe); t_comp += clock64() - t_mark;
       epi_bar();
       if (half == 0) {
@@ -573,18 +637,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 template <int PL> constexpr int smem_pass2() { return Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE + 3 * H * 4 + 16; }
 
 // 8 consecutive values of a stored tile: sum of its planes
-template <int PL>
+template <int PL, bool F16 = false>
 __device__ __forceinline__ void unpack_planes(const uint4 (&q)[PL], float* v) {
-  unpack8(q[0], v);
+  unpack8f<F16>(q[0], v);
   if (PL == 2) {
     float l[8];
-    unpack8(q[PL - 1], l);
+    unpack8f<F16>(q[PL - 1], l);
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] += l[e];
   }
 }
 
-template <int PL>
+template <int PL, bool F16>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, Geo<PL>::CTAS_PER_SM) pass2_kernel(const Work w, const int tangent) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
@@ -600,7 +664,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
   if (warp == W_PROD && lane == 0) {
     if (tangent) {
       Producer<PL> pr{&pipe, ring, cluster_ctarank()};
+      // the epilogues read this tile's h1 / c / g with plain loads: pull them into L2 one net ahead of their use
+      auto prefetch_net = [&](int k) {
+        const uint8_t* nt = net_tile<PL>(w, b, k, tl);
+        if (!(w.dbg_flags & 8)) bulk_prefetch_l2(nt, 3 * Geo<PL>::BH);          // B_H1, B_CC, B_GG are the first three blobs
+      };
+      prefetch_net(0);
       for (int k = 0; k < w.Kn; ++k) {
+        if (k + 1 < w.Kn) prefetch_net(k + 1);
         const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
         const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
         pr.stream(gen, 0, 12, STAGE_BYTES);                      // W1
@@ -610,7 +681,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     }
   } else if (warp == W_MMA && lane == 0) {
     if (tangent) {
-      Issuer<PL> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+      Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
       uint32_t ae = 0;
       long long t_epi = 0;
       const long long t_begin = clock64();
@@ -650,12 +721,32 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
         for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];
       }
-      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three bf16 terms, rest 0
+      // fp16 variant: sp = power-of-two scale of this point's tangent row (its seeds set the magnitude of xt, ht, ct);
+      // the Z-side tiles share one scale per (sample, net) because the weight-gradient contraction runs over points
+      float sp = 1.f, isp = 1.f, sZP = 1.f, sZH = 1.f, sZC = 1.f, sZD = 1.f, iH1 = 1.f, iC = 1.f, iG = 1.f, iW1 = 1.f, iW2 = 1.f, iWa = 1.f;
+      float sDV = 1.f;
+      if (F16) {
+        const NetScales t = w.sc[b * w.Kn + k];
+        const float Rp = 16.f * fmaxf(fabsf(dd[0]), fmaxf(fabsf(dd[1]), fabsf(dd[2])));
+        sp = Rp > 0.f ? scale_for(Rp * t.rowB) : 1.f;
+        isp = 1.f / sp;
+        sZP = t.sZP; sZH = t.sZH; sZC = t.sZC; sZD = t.sZD; sDV = t.sDV;
+        iH1 = 1.f / t.sH1; iC = 1.f / t.sC; iG = 1.f / t.sG; iW1 = 1.f / t.sW1; iW2 = 1.f / t.sW2; iWa = 1.f / t.sWa;
+      }
+      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three 16-bit terms, rest 0
       if (half == 0) {
-        const float hi = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
-        const float mid = __uint_as_float(__float_as_uint(dv - hi) & 0xFFFF0000u);
-        float a8[8] = {hi, mid, (dv - hi) - mid, 0.f, 0.f, 0.f, 0.f, 0.f};
-        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 0)), pack8(a8));
+        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (F16) {
+          const float x = dv * sDV;
+          a8[0] = __half2float(__float2half_rn(x));
+          a8[1] = __half2float(__float2half_rn(x - a8[0]));
+          a8[2] = (x - a8[0]) - a8[1];
+        } else {
+          a8[0] = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
+          a8[1] = __uint_as_float(__float_as_uint(dv - a8[0]) & 0xFFFF0000u);
+          a8[2] = (dv - a8[0]) - a8[1];
+        }
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 0)), pack8f<F16>(a8));
         __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 1)), make_uint4(0u, 0u, 0u, 0u));
       }
       // ---- prologue: xt -> activation buffer; zp, zd -> workspace (each half takes 4 of the 8 column groups) ----
@@ -676,17 +767,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           const int jp = DPE_PARTNER(j);
           xt[j] = dd[j % 3] * (DPE_SIGN(j) * w.band[J / 6]) * pe[jp];
           zp[j] = fmaf(dv, pe[j], xt[j]);
+          if (F16) { xt[j] *= sp; zp[j] *= sZP; }
         }
 #pragma unroll
         for (int qd = 0; qd < 3; ++qd) {
           const uint32_t off = piece_off(r, it * 3 + qd);
-          if (tangent) sts8<PL>(act, BLOB_H, off, xt + qd * 8);
-          stg8<PL>(blob_zp<PL>(nt), BLOB_C, off, zp + qd * 8);
+          if (tangent) sts8<PL, F16>(act, BLOB_H, off, xt + qd * 8);
+          stg8<PL, F16>(blob_zp<PL>(nt), BLOB_C, off, zp + qd * 8);
           float d6[8];
-          unpack_planes<PL>(p6[qd], d6);
+          unpack_planes<PL, F16>(p6[qd], d6);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) d6[e] *= dv;
-          stg8<PL>(blob_zd<PL>(nt), BLOB_C, off, d6);
+          for (int e = 0; e < 8; ++e) d6[e] *= F16 ? dv * (sZD / S_PE) : dv;
+          stg8<PL, F16>(blob_zd<PL>(nt), BLOB_C, off, d6);
         }
       }
       if (tangent) { epi_done(&pipe); t_comp += clock64() - t_mark; }
@@ -719,17 +811,22 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
             float s[8];
-            unpack_planes<PL>(cur[qd], s);
+            unpack_planes<PL, F16>(cur[qd], s);
+            const float is = st == 0 ? iH1 : (st == 1 ? iC : iG);       // stored tile -> true values
+            const float iw = st == 0 ? iW1 : (st == 1 ? iW2 : iWa);     // accumulator -> (tangent row x sp)
+            const float sz = st == 0 ? sZH : sZC;
+            float zs[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              float t = v[qd * 8 + e];
+              float t = F16 ? v[qd * 8 + e] * iw : v[qd * 8 + e];
               if (st != 1) t = s[e] > 0.f ? t : 0.f;                  // relu masks m1 (h1 > 0) / m3 (g > 0)
-              v[qd * 8 + e] = t;
-              z[qd * 8 + e] = fmaf(dv, s[e], t);
+              v[qd * 8 + e] = t;                                      // next A operand, still carrying sp
+              z[qd * 8 + e] = F16 ? fmaf(dv, s[e] * is, t * isp) : fmaf(dv, s[e], t);
+              zs[e] = F16 ? z[qd * 8 + e] * sz : z[qd * 8 + e];
             }
             const uint32_t off = piece_off(r, cg * 4 + qd);
-            if (st < 2) stg8<PL>(dst, BLOB_H, off, z + qd * 8);
-            if (tangent && st < 2) sts8<PL>(act, BLOB_H, off, v + qd * 8);
+            if (st < 2) stg8<PL, F16>(dst, BLOB_H, off, zs);
+            if (tangent && st < 2) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
           }
           if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
             const float cs = warp_colsum32(z, lane);
@@ -738,7 +835,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
                 float s[8];
-                unpack8(cur[qd][0], s);                                // sign of the hi plane = sign of the value
+                unpack8f<F16>(cur[qd][0], s);                          // sign of the hi plane = sign of the value
 #pragma unroll
                 for (int e = 0; e < 8; ++e) z[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
               }
@@ -801,13 +898,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
 struct WgradWork {
   int B, Kn, T, splits;
   const uint8_t* blobs;
+  const NetScales* sc;
   float *gW1, *gW2, *gWa, *gWd;
   float *gb1, *gb2, *ge, *gbd;
 };
 
 template <int PL> constexpr int smem_wgrad() { return PL * (BLOB_H / 2 + BLOB_H) + AUX_BYTES; }   // 102400 / 200704
 
-template <int PL>
+template <int PL, bool F16>
 __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const WgradWork w) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full, empty, acc_ready;
@@ -852,7 +950,7 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
         if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC, AUX_BYTES, &full);
       }
     } else if (warp == 5 && lane == 0) {
-      const uint32_t idesc = idesc_bf16(Nn, 1, 1), idesc_x = idesc_bf16(16, 1, 1);
+      const uint32_t idesc = idesc_16(F16, Nn, 1, 1), idesc_x = idesc_16(F16, 16, 1, 1);
       for (int t = t0; t < t1; ++t) {
         const uint32_t i = t - t0;
         mbar_wait(&full, i & 1);
@@ -889,15 +987,22 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
                  : layer == 2 ? w.gWa + (size_t)k * H * H
                  : w.gWd + (size_t)k * H * C;
       dst += (size_t)(mh * TP + tid) * Nn;
+      float un = 1.f, un_x = 1.f;                                      // fp16 variant: undo (J tile scale) x (Z tile / seed scale)
+      if (F16) {
+        const NetScales t = w.sc[gk];
+        const float sj = layer == 0 ? t.sQ : (layer == 2 ? t.sUM : t.sY);
+        const float sz = layer == 0 ? t.sZP : (layer == 1 ? t.sZH : (layer == 2 ? t.sZC : t.sZD));
+        un = 1.f / (sj * sz); un_x = 1.f / (sj * t.sDV);
+      }
       float v[32];
       for (int cb = 0; cb < Nn / 32; ++cb) {
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + cb * 32 + j, v[j]);
+        for (int j = 0; j < 32; ++j) atomicAdd(dst + cb * 32 + j, F16 ? v[j] * un : v[j]);
       }
       if (aux) {
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + C, v);
-        const float bsum = v[0] + v[1] + v[2];                         // the three bf16 terms of the seed
+        const float bsum = (v[0] + v[1] + v[2]) * un_x;                // the three 16-bit terms of the seed
         const int out = mh * TP + tid;
         if (layer == 0) {
           atomicAdd(w.gb1 + gk * H + out, bsum);
@@ -917,12 +1022,123 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // SIMT helpers of the tensor-core mode
 // ------------------------------------------------------------------------------------------------
+// ---- scaling plan of the fp16 variant -------------------------------------------------------------
+__device__ __forceinline__ float block_max256(float v, float* red) {      // 256 threads; every thread gets the result
+#pragma unroll
+  for (int w = 16; w; w >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, w));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float m = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  return m;
+}
+
+// One block per (sample, net): L1 norms / maxima of its matrices -> activation bounds and tile scales.
+__global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __restrict__ W1, const float* __restrict__ b1,
+                                                     const float* __restrict__ W2, const float* __restrict__ Wd,
+                                                     const float* __restrict__ Wa, const float* __restrict__ ba,
+                                                     const float* __restrict__ bsum, const float* __restrict__ uvec,
+                                                     const float* __restrict__ wo2, NetScales* __restrict__ tab) {
+  __shared__ float red[8];
+  const int bk = blockIdx.x, k = bk % Kn, j = threadIdx.x;
+  const float* w1 = W1 + ((size_t)bk * H + j) * C;
+  const float* w2 = W2 + (size_t)bk * H * H;
+  const float* wd = Wd + ((size_t)k * H + j) * C;
+  const float* wa = Wa + (size_t)k * H * H;
+  float r1 = 0.f, m1 = 0.f, rd = 0.f, md = 0.f;
+  for (int i = 0; i < C; ++i) {
+    const float a = fabsf(w1[i]), d = fabsf(wd[i]);
+    r1 += a; m1 = fmaxf(m1, a); rd += d; md = fmaxf(md, d);
+  }
+  float r2 = 0.f, c2 = 0.f, m2 = 0.f, ra = 0.f, ca = 0.f, ma = 0.f;
+  for (int i = 0; i < H; ++i) {
+    const float x2 = fabsf(w2[(size_t)j * H + i]), y2 = fabsf(w2[(size_t)i * H + j]);
+    const float xa = fabsf(wa[(size_t)j * H + i]), ya = fabsf(wa[(size_t)i * H + j]);
+    r2 += x2; c2 += y2; m2 = fmaxf(m2, x2); ra += xa; ca += ya; ma = fmaxf(ma, xa);
+  }
+  const float l1W1 = block_max256(r1, red), M1 = block_max256(r1 + fabsf(b1[(size_t)bk * H + j]), red);
+  const float l1W2 = block_max256(r2, red), l1Wd = block_max256(rd, red), l1Wa = block_max256(ra, red);
+  const float cW2 = block_max256(c2, red), cWa = block_max256(ca, red);
+  const float mW1 = block_max256(m1, red), mW2 = block_max256(m2, red), mWd = block_max256(md, red), mWa = block_max256(ma, red);
+  const float mBs = block_max256(fabsf(bsum[(size_t)bk * H + j]), red), mBa = block_max256(fabsf(ba[(size_t)k * H + j]), red);
+  const float Mu = block_max256(fabsf(uvec[(size_t)k * H + j]), red), mWo2 = block_max256(fabsf(wo2[(size_t)k * H + j]), red);
+  if (j == 0) {
+    NetScales t;
+    const float Mc = l1W2 * M1 + l1Wd + mBs, Mg = l1Wa * Mc + mBa;
+    const float My = Mu * cWa + mWo2, Mq = My * cW2;
+    t.sW1 = scale_for(mW1 * 32.f);                   // weights: maximum -> 2^10
+    t.sWa = scale_for(mWa * 32.f);
+    t.sWd = scale_for(mWd * 32.f);                   // preliminary: plan_kernel couples sWd, sH1 and sW2
+    t.sW2 = scale_for(mW2);                          // preliminary: the LARGEST admissible factor
+    t.sH1 = scale_for(M1); t.sC = scale_for(Mc); t.sG = scale_for(Mg);
+    t.sUM = scale_for(Mu); t.sY = scale_for(My); t.sQ = scale_for(Mq);
+    t.M1 = M1; t.Mc = Mc; t.l1W1 = l1W1; t.l1W12 = l1W1 * l1W2;
+    t.rowB = fmaxf(1.f, fmaxf(l1W1, l1W1 * l1W2));
+    t.cap = t.sH1 * t.sW2;
+    t.sZP = t.sZH = t.sZC = t.sZD = t.sDV = 1.f; t.pad_ = 0.f;
+    tab[bk] = t;
+  }
+}
+
+// G2 accumulates h1 W2^T and PE6 Wd^T in ONE accumulator: (sH1 sW2) must equal (S_PE sWd), and the Wd image is shared by
+// all samples.  Per net: T2 = min(S_PE * sWd, min over samples of their capacity); then sWd = T2 / S_PE, sW2 = T2 / sH1.
+__global__ void plan_kernel(int B, int Kn, NetScales* __restrict__ tab) {
+  const int k = threadIdx.x;
+  if (k >= Kn) return;
+  float T2 = S_PE * tab[k].sWd;
+  for (int b = 0; b < B; ++b) T2 = fminf(T2, tab[b * Kn + k].cap);
+  for (int b = 0; b < B; ++b) {
+    NetScales& t = tab[b * Kn + k];
+    t.sWd = T2 / S_PE;
+    t.sW2 = T2 / t.sH1;
+  }
+}
+
+// max |dov| and max |dod| per (sample, net) over the rows of this chunk -> seedmax[bk][2] (non-negative floats order like ints)
+__global__ void __launch_bounds__(256) seedmax_kernel(int Kn, size_t rows_per_sample, const float* __restrict__ dov,
+                                                      const float* __restrict__ dod, int* __restrict__ seedmax) {
+  const int b = blockIdx.y;
+  float mv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, md[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows_per_sample; r += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = (size_t)b * rows_per_sample + r;
+    for (int k = 0; k < Kn; ++k) {
+      mv[k] = fmaxf(mv[k], fabsf(dov[row * Kn + k]));
+#pragma unroll
+      for (int c = 0; c < 3; ++c) md[k] = fmaxf(md[k], fabsf(dod[(row * Kn + k) * 3 + c]));
+    }
+  }
+  for (int k = 0; k < Kn; ++k) {
+    float a = mv[k], d = md[k];
+#pragma unroll
+    for (int w = 16; w; w >>= 1) { a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, w)); d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, w)); }
+    if ((threadIdx.x & 31) == 0) {
+      if (a > 0.f && isfinite(a)) atomicMax(seedmax + ((size_t)b * Kn + k) * 2, __float_as_int(a));
+      if (d > 0.f && isfinite(d)) atomicMax(seedmax + ((size_t)b * Kn + k) * 2 + 1, __float_as_int(d));
+    }
+  }
+}
+
+// Z-side scales of this chunk from the seed maxima: zp = dov PE + xt, zh = dov h1 + ht, zc = dov c + ct, zd = dov PE6
+__global__ void zscale_kernel(int n, const int* __restrict__ seedmax, NetScales* __restrict__ tab) {
+  const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bk >= n) return;
+  NetScales& t = tab[bk];
+  const float DV = __int_as_float(seedmax[bk * 2]), RR = 16.f * __int_as_float(seedmax[bk * 2 + 1]);   // |dPE/dz| <= 2^4
+  t.sZP = scale_for(DV + RR);
+  t.sZH = scale_for(DV * t.M1 + RR * t.l1W1);
+  t.sZC = scale_for(DV * t.Mc + RR * t.l1W12);
+  t.sZD = scale_for(DV);
+  t.sDV = scale_for(DV);
+}
+
 // fp32 weight matrix [R_src x K_src] -> bf16 image in layout (*) ; transpose = image rows are source columns.
 // The image is a sequence of K = 16 chunks (two k-cores, rows*32 bytes per plane); with PL planes a chunk is
 // [hi plane | lo plane], so the producer still fetches one contiguous block per chunk.
-template <int PL>
+template <int PL, bool F16>
 __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
-                             size_t dst_stride, int rows, int kd, int transpose) {
+                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which) {
   const float* S = src + blockIdx.y * src_stride;
   uint8_t* D = dst + blockIdx.y * dst_stride;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;             // 16-byte piece index
@@ -931,15 +1147,21 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = transpose ? S[(size_t)(kc * 8 + e) * rows + r] : S[(size_t)r * kd + kc * 8 + e];
+  if (F16) {                                                         // entry blockIdx.y: (sample, net) for generated weights, (0, net) for static ones
+    const NetScales& t = tab[blockIdx.y];
+    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : t.sWa));
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= sc;
+  }
   uint4 pq[PL];
-  split8<PL>(v, pq);
+  split8<PL, F16>(v, pq);
   const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)(kc & 1) * rows * 16 + (size_t)r * 16;
 #pragma unroll
   for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * rows * 32) = pq[p];
 }
 
 // coordinate / data features of one tile: bf16 blobs (GEMM operands) and the fp32 transposed copy (epilogues)
-template <int PL>
+template <int PL, bool F16>
 __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Work w, const float* __restrict__ x,
                                                     const float* __restrict__ y, const float* __restrict__ t) {
   const size_t g = blockIdx.x;
@@ -972,8 +1194,12 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
     }
 #pragma unroll
     for (int j = 0; j < 24; ++j) pet[(size_t)(it * 24 + j) * TP] = buf[j];
+    if (F16) {
 #pragma unroll
-    for (int qd = 0; qd < 3; ++qd) sts8<PL>(pe, BLOB_C, piece_off(r, it * 3 + qd), buf + qd * 8);      // (plain global stores)
+      for (int j = 0; j < 24; ++j) buf[j] *= S_PE;
+    }
+#pragma unroll
+    for (int qd = 0; qd < 3; ++qd) sts8<PL, F16>(pe, BLOB_C, piece_off(r, it * 3 + qd), buf + qd * 8);      // (plain global stores)
   }
 #pragma unroll 1
   for (int it = 0; it < 8; ++it) {                                   // 2 frequencies x (6 sin, 6 cos)
@@ -984,12 +1210,12 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
       for (int c = 0; c < 6; ++c) {
         float s = 0.f, co = 0.f;
         if (valid) sincosf(d[c] * band, &s, &co);
-        buf[ff * 12 + c] = s;
-        buf[ff * 12 + 6 + c] = co;
+        buf[ff * 12 + c] = F16 ? s * S_PE : s;
+        buf[ff * 12 + 6 + c] = F16 ? co * S_PE : co;
       }
     }
 #pragma unroll
-    for (int qd = 0; qd < 3; ++qd) sts8<PL>(pe6, BLOB_C, piece_off(r, it * 3 + qd), buf + qd * 8);
+    for (int qd = 0; qd < 3; ++qd) sts8<PL, F16>(pe6, BLOB_C, piece_off(r, it * 3 + qd), buf + qd * 8);
   }
 }
 
@@ -1027,6 +1253,8 @@ struct Carve {
   uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
   float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo;
   long long* dbg;
+  NetScales* sc;
+  int* seedmax;
   size_t bytes;
 };
 
@@ -1056,6 +1284,8 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B, int pl) {
   c.sm3 = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sdo = reinterpret_cast<float*>(take((size_t)Kn * 4));
   c.dbg = reinterpret_cast<long long*>(take(16 * 8));
+  c.sc = reinterpret_cast<NetScales*>(take((size_t)B * Kn * sizeof(NetScales)));
+  c.seedmax = reinterpret_cast<int*>(take((size_t)B * Kn * 2 * sizeof(int)));
   c.bytes = off;
   return c;
 }
@@ -1068,28 +1298,28 @@ int default_chunk(int B, int planes) {
 
 size_t workspace_bytes(int chunk, int Kn, int B, int planes) { return carve(nullptr, chunk, Kn, B, planes).bytes; }
 
-template <int PL>
+template <int PL, bool F16>
 static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
-  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; };
+  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; };
   const Spec specs[] = {
-      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen},                          // W1  : rows = out, k = in
-      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen},                     // W1T : rows = in,  k = out
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen},
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen},
-      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta},
-      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta},
-      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta},
+      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0},                       // W1  : rows = out, k = in
+      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0},                  // W1T : rows = in,  k = out
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen, 1},
+      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta, 2},
+      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta, 3},
+      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta, 3},
   };
   for (const Spec& s : specs) {
     const int pieces = s.rows * s.kd / 8;
-    image_kernel<PL><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
-                                                                            s.rows, s.kd, s.tr);
+    image_kernel<PL, F16><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
+                                                                                 s.rows, s.kd, s.tr, c.sc, s.which);
     DPN_LAUNCH_OK();
   }
   return 0;
 }
 
-template <int PL>
+template <int PL, bool F16>
 static int run_planes(const Job& J, cudaStream_t st) {
   const int B = J.shape.B, N = J.shape.N, Kn = J.shape.K, chunk = J.chunk;
   if (J.pts->coord_pe) {
@@ -1099,9 +1329,9 @@ static int run_planes(const Job& J, cudaStream_t st) {
   static bool attr_done = false;
   const int smem_fused = tc::smem_fused<PL>(), smem_pass2 = tc::smem_pass2<PL>(), smem_wgrad = tc::smem_wgrad<PL>();
   if (!attr_done) {
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
-    DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
+    DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
     attr_done = true;
   }
   Carve c = carve(reinterpret_cast<uint8_t*>(J.workspace), chunk, Kn, B, PL);
@@ -1115,7 +1345,13 @@ static int run_planes(const Job& J, cudaStream_t st) {
   static const bool phase_debug = getenv("DPN_PHASE_DEBUG") != nullptr;
   if (phase_debug) DPN_CUDA_OK(cudaMemsetAsync(c.dbg, 0, 16 * 8, st));
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
-  if ((rc = make_images<PL>(Wt, c, B, Kn, st))) return rc;
+  if (F16) {                                                          // scaling plan before anything is converted to fp16
+    bounds_kernel<<<B * Kn, 256, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, c.sc);
+    DPN_LAUNCH_OK();
+    plan_kernel<<<1, 32, 0, st>>>(B, Kn, c.sc);
+    DPN_LAUNCH_OK();
+  }
+  if ((rc = make_images<PL, F16>(Wt, c, B, Kn, st))) return rc;
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
   if (want_bwd) {
     const DpnGrads& G = *J.grads;
@@ -1147,13 +1383,14 @@ static int run_planes(const Job& J, cudaStream_t st) {
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
     w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
+    w.sc = c.sc;
     w.phase_dbg = phase_debug ? c.dbg : nullptr;
     w.dbg_flags = getenv("DPN_DEBUG_FLAGS") ? atoi(getenv("DPN_DEBUG_FLAGS")) : 0;
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
-    encode_kernel<PL><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
+    encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
     DPN_LAUNCH_OK();
-    pass1_kernel<PL><<<tiles, FUSED_THREADS, smem_fused, st>>>(w, sweep);
+    pass1_kernel<PL, F16><<<tiles, FUSED_THREADS, smem_fused, st>>>(w, sweep);
     DPN_LAUNCH_OK();
     if (J.kind == JOB_DEC_FWD) {
       gather_o_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.o);
@@ -1179,10 +1416,17 @@ static int run_planes(const Job& J, cudaStream_t st) {
     }
     if (!want_bwd) continue;
     const DpnGrads& G = *J.grads;
-    pass2_kernel<PL><<<tiles, FUSED_THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
+    if (F16) {                                                        // Z-side scales of this chunk from the seeds' maxima
+      DPN_CUDA_OK(cudaMemsetAsync(c.seedmax, 0, (size_t)B * Kn * 2 * sizeof(int), st));
+      seedmax_kernel<<<dim3(64, B), 256, 0, st>>>(Kn, (size_t)T * TP, c.dov, c.dod, c.seedmax);
+      DPN_LAUNCH_OK();
+      zscale_kernel<<<(B * Kn + 63) / 64, 64, 0, st>>>(B * Kn, c.seedmax, c.sc);
+      DPN_LAUNCH_OK();
+    }
+    pass2_kernel<PL, F16><<<tiles, FUSED_THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
-    ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs;
+    ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd;
     const int items = B * Kn * 8;
@@ -1190,7 +1434,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     if (splits > T) splits = T;
     if (splits < 1) splits = 1;
     ww.splits = splits;
-    wgrad_kernel<PL><<<items * splits, 192, smem_wgrad, st>>>(ww);
+    wgrad_kernel<PL, F16><<<items * splits, 192, smem_wgrad, st>>>(ww);
     DPN_LAUNCH_OK();
   }
   if (phase_debug) {
@@ -1211,7 +1455,11 @@ static int run_planes(const Job& J, cudaStream_t st) {
   return 0;
 }
 
-int run(const Job& J, cudaStream_t st) { return J.shape.mode == DPN_MODE_BF16X3 ? run_planes<2>(J, st) : run_planes<1>(J, st); }
+int run(const Job& J, cudaStream_t st) {
+  if (J.shape.mode == DPN_MODE_F16X3) return run_planes<2, true>(J, st);
+  if (J.shape.mode == DPN_MODE_BF16X3) return run_planes<2, false>(J, st);
+  return run_planes<1, false>(J, st);
+}
 
 }  // namespace tc
 }  // namespace dpn

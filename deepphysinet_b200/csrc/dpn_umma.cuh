@@ -14,6 +14,7 @@
 // the K = points weight-gradient contraction (MN-major) without a transpose.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -130,6 +131,10 @@ __device__ __forceinline__ uint4 ldg_v4_hint(const void* p, uint64_t policy) {
   asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(policy));
   return v;
 }
+// Ask the memory system to bring [p, p + bytes) into L2 (no destination in the SM): hides DRAM latency of later ld.global
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 // generic-proxy writes to smem -> visible to the async proxy (tensor core / bulk copy)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -217,6 +222,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n, int a_mn_major, int b_m
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// Same for either 16-bit operand format of kind::f16: a_format / b_format = 0 (fp16) or 1 (bf16)
+__host__ __device__ constexpr uint32_t idesc_16(bool f16, int n, int a_mn_major, int b_mn_major, int m = 128) {
+  return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] * B[smem], one thread issues for the CTA
 __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -238,6 +249,11 @@ __host__ __device__ constexpr uint32_t tile_off(int rows, int r, int k) {   // b
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 v = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 

@@ -41,8 +41,10 @@ extern "C" {
 enum {
   DPN_MODE_FP32 = 0,  /* CUDA-core fp32 FMA everywhere: the 1e-4 parity mode                              */
   DPN_MODE_BF16 = 1,  /* tcgen05 kind::f16 (bf16 operands, fp32 TMEM accumulators); tolerance in DESIGN.md */
-  DPN_MODE_BF16X3 = 2 /* tcgen05, every operand split into bf16 hi + lo (16 mantissa bits), three MMAs per
+  DPN_MODE_BF16X3 = 2,/* tcgen05, every operand split into bf16 hi + lo (16 mantissa bits), three MMAs per
                          contraction (lo*hi + hi*lo + hi*hi); tolerance in DESIGN.md                        */
+  DPN_MODE_F16X3 = 3  /* same with fp16 hi + lo (22 mantissa bits) and exact power-of-two scaling of every
+                         operand tile from rigorous L1-norm bounds: fp32-class results on the tensor cores */
 };
 
 enum {
