@@ -179,11 +179,14 @@ class DecoderValuesFn(torch.autograd.Function):
         return (None,) * 8 + tuple(g.to(dt) for g, dt in zip(grads, ctx.dtypes))
 
 
-_DEFAULT_MODE = "bf16"
+_DEFAULT_MODE = "f16x3"
 
 
 def set_default_mode(mode: str):
-    """'bf16' (tcgen05 tensor cores, default) or 'fp32' (CUDA-core FMA; the 1e-4 parity mode)."""
+    """Arithmetic of the dense contractions (include/dpn_b200.h):
+    'f16x3'  tcgen05, scaled fp16 hi+lo operands, 3 MMAs per contraction - fp32-class accuracy (default)
+    'bf16x3' tcgen05, bf16 hi+lo operands - ~1e-3 class          'bf16' tcgen05, plain bf16 - fastest, ~5e-2 class
+    'fp32'   CUDA-core FMA - the reference arithmetic, slowest."""
     global _DEFAULT_MODE
     if mode not in N.MODES:
         raise ValueError("mode must be one of %s" % (tuple(N.MODES),))

@@ -159,7 +159,7 @@ def test_fp32_physics_net_forward_values_and_grad():
         assert H.rel(got.detach().cpu(), ref.detach()) < TOL_FP32
         (got * wts.float().cuda()).sum().backward()
     finally:
-        Fn.set_default_mode("bf16")
+        Fn.set_default_mode("f16x3")
     g64 = dict(net64.named_parameters())
     gtot = np.sqrt(sum(p.grad.norm().item() ** 2 for p in g64.values() if p.grad is not None))
     for k, p in net.named_parameters():
