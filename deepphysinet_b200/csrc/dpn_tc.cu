@@ -56,6 +56,15 @@ struct Geo {
   static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
   static constexpr size_t NET_TILE = (size_t)NBLOB_H * BH + (size_t)NBLOB_C * BC + AUX_BYTES;
   static constexpr int CTAS_PER_SM = PL == 1 ? 2 : 1;
+  // Epilogue warps: warps w, w+4, w+8, ... share the TMEM lanes 32 (w % 4) .. +31 and split the 256 columns into NQ groups.
+  // 8 warps everywhere: 16 warps (column quarters) were measured for the one-CTA-per-SM split modes and LOSE 11 % - the 96-register
+  // budget of 576 threads spills in the pass-2 epilogues (f16x3 call 24.3 -> 27.0 ms); the code below stays generic in EW.
+  static constexpr int EW = 8;
+  static constexpr int ET = EW * 32;                             // epilogue threads
+  static constexpr int NQ = EW / 4;                              // column groups
+  static constexpr int NB = 8 / NQ;                              // 32-column blocks per thread
+  static constexpr int W_PROD = EW, W_MMA = EW + 1;              // producer / MMA-issuer warps
+  static constexpr int THREADS = ET + 64;
 };
 enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, NVEC };   // epilogue vectors staged in shared memory per net
 
@@ -266,17 +275,18 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+template <int PL>
 __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], CLUSTER); }
     mbar_init(&pp->a_bulk, 1);
-    mbar_init(&pp->a_epi, 256);                 // every epilogue thread (8 warps) arrives
+    mbar_init(&pp->a_epi, Geo<PL>::ET);         // every epilogue thread arrives
     mbar_init(&pp->acc_ready, 1);
     mbar_init(&pp->act_free, 1);
     mbar_init(&pp->st_done, 1);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(&pp->tmem_base, 256);   // the MMA warp of the fused kernels owns the allocation
+  if (warp == Geo<PL>::W_MMA) tmem_alloc(&pp->tmem_base, 256);   // the MMA warp of the fused kernels owns the allocation
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -298,13 +308,9 @@ __device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my 
 // warps 0-3: epilogue (thread = point = TMEM lane), warp 4: bulk-copy producer, warp 5: MMA issuer.
 // Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | 5 epilogue vectors (b1, b2+bd+e, ba, u, 2wo) 5 KB.
 // ------------------------------------------------------------------------------------------------
-constexpr int EPI_WARPS = 8;                        // warps w and w+4 share TMEM lanes and split the 256 columns
-constexpr int EPI_THREADS = EPI_WARPS * 32;         // 256
-constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1;
-constexpr int FUSED_THREADS = EPI_THREADS + 64;     // 320
 template <int PL> constexpr int smem_fused() { return Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE + NVEC * H * 4 + TP * 4 * 4; }   // + per-row partial sums (o, dz[3])
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps only
+template <int PL> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(Geo<PL>::ET) : "memory"); }   // the epilogue warps only
 
 // NB consecutive 32-column blocks of this thread's TMEM lane: f(block, float (&v)[32])
 template <int NB, class F>
@@ -330,7 +336,7 @@ __device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, 
 }
 
 template <int PL, bool F16>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, Geo<PL>::CTAS_PER_SM) pass1_kernel(const Work w, const int sweep) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREADS, Geo<PL>::CTAS_PER_SM) pass1_kernel(const Work w, const int sweep) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
@@ -340,10 +346,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;                       // global tile index
-  pipe_init(&pipe, warp, tid);
+  pipe_init<PL>(&pipe, warp, tid);
   const uint32_t tmem = pipe.tmem_base;
 
-  if (warp == W_PROD && lane == 0) {
+  if (warp == Geo<PL>::W_PROD && lane == 0) {
     // ---------------- producer ----------------
     Producer<PL> pr{&pipe, ring, cluster_ctarank()};
     uint32_t af = 0, sd = 0;
@@ -379,7 +385,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         if (sweep > 1) pr.stream(iW1T, 0, 16, 6144);
       }
     }
-  } else if (warp == W_MMA && lane == 0) {
+  } else if (warp == Geo<PL>::W_MMA && lane == 0) {
     // ---------------- MMA issuer ----------------
     Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
     uint32_t ab = 0, ae = 0;
@@ -413,12 +419,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)t_epi);
       atomicAdd((unsigned long long*)w.phase_dbg + 3, (unsigned long long)t_bulk);
     }
-  } else if (warp < EPI_WARPS) {
-    // ---------------- epilogue: thread = (point r, column half) ----------------
-    const int half = warp >> 2;                                     // columns [128*half, 128*half+128)
+  } else if (warp < Geo<PL>::EW) {
+    // ---------------- epilogue: thread = (point r, column group) ----------------
+    constexpr int NB = Geo<PL>::NB;                                 // 32-column blocks per thread (4: column halves, 2: quarters)
+    const int half = warp >> 2;                                     // column group: columns [32 NB half, 32 NB (half + 1))
     const int r = (warp & 3) * 32 + lane;                           // row in tile = TMEM lane
-    const int c0 = half * 4;                                        // first 32-column block of this thread
-    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 128;
+    const int c0 = half * NB;                                       // first 32-column block of this thread
+    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * (NB * 32);
     const int p_local = tl * TP + r;
     const bool valid = p_local < w.P;
     const size_t q = (size_t)b * w.N + w.p0 + p_local;              // index into the caller's per-point arrays
@@ -432,7 +439,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     const uint64_t pol_stream = l2_policy_evict_first();              // activation tiles are written once, read much later
     const uint64_t pol_keep = l2_policy_evict_last();                 // the tile's coordinate features are re-read for every net
     auto drain = [&](uint8_t* blob, const bool to_producer) {
-      epi_bar();                                                    // every thread has written and fenced its part
+      epi_bar<PL>();                                                    // every thread has written and fenced its part
       if (tid == 0) {
         bulk_s2g_hint(blob, act, Geo<PL>::ACT, pol_stream);        // all planes: they are contiguous on both sides
         bulk_commit();
@@ -443,9 +450,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile<PL>(w, b, k, tl);
-      epi_bar();                                                    // every warp is done with the previous net's vectors
-      load_vectors(svec, w, b, k, tid);
-      epi_bar();
+      epi_bar<PL>();                                                    // every warp is done with the previous net's vectors
+      if (tid < H) load_vectors(svec, w, b, k, tid);
+      epi_bar<PL>();
       // fp16 variant: accumulators carry (scale of A tile) x (scale of weight image); i* undo that, s* scale the next tile
       float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f;
       if (F16) {
@@ -454,10 +461,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
         sH1 = t.sH1; sC = t.sC; sG = t.sG; sUM = t.sUM; sY = t.sY;
       }
-      uint32_t m1w[4] = {0u, 0u, 0u, 0u};                            // ReLU mask of a1 for this thread's 128 columns
+      uint32_t m1w[NB];                                              // ReLU mask of a1 for this thread's columns
+#pragma unroll
+      for (int i = 0; i < NB; ++i) m1w[i] = 0u;
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
         uint32_t bits = 0;
 #pragma unroll
@@ -472,7 +481,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
+        for (int i = 0; i < NB; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
@@ -481,10 +490,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       epi_done(&pipe); t_comp += clock64() - t_mark;
       if (sweep) drain(blob_h<PL>(nt, B_H1), true);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
-      if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
+      if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
       float os0 = 0.f, os1 = 0.f;
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -506,9 +515,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       epi_done(&pipe); t_comp += clock64() - t_mark;
       if (sweep) drain(blob_h<PL>(nt, B_CC), false);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
-      if (sweep) epi_bar();
+      if (sweep) epi_bar<PL>();
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -536,16 +545,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       }, (w.dbg_flags & 4) != 0);
       atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
       epi_done(&pipe); t_comp += clock64() - t_mark;
-      if (sweep) drain(blob_h<PL>(nt, B_UM), false); else epi_bar();
+      if (sweep) drain(blob_h<PL>(nt, B_UM), false); else epi_bar<PL>();
       if (half == 0) {
         if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
         rowsum[r * 4] = 0.f;
       }
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
-      if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
+      if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -565,13 +574,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       epi_done(&pipe); t_comp += clock64() - t_mark;
       drain(blob_h<PL>(nt, B_YT), sweep < 2);
       // ---- epilogue 5: qm = acc * m1 ----
-      if (sweep) epi_bar();                                         // the drain of the previous tile has released the buffer
+      if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<4>(tl_addr, [&](const int cb, float (&v)[32]) {
+      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
         const int cg = c0 + cb;
         uint32_t bits = 0u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bits = (cb == i) ? m1w[i] : bits;
+        for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
 #pragma unroll
@@ -587,7 +596,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
       mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
       float dz[3] = {0.f, 0.f, 0.f};
-      {
+      if (half < 2) {                                                // two 96-column groups; with 16 warps groups 2, 3 only wait
         const uint32_t a6 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 96;
         const float bsel = half ? 1.f : 0.f;
 #pragma unroll
@@ -604,10 +613,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           }
         }
       }
+      if (half < 2) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, F16 ? dz[c] * i6 : dz[c]);
+        for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, F16 ? dz[c] * i6 : dz[c]);
+      }
       epi_done(&pipe); t_comp += clock64() - t_mark;
-      epi_bar();
+      epi_bar<PL>();
       if (half == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -627,7 +638,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == W_MMA) tmem_dealloc(tmem, 256);
+  if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -649,7 +660,7 @@ __device__ __forceinline__ void unpack_planes(const uint4 (&q)[PL], float* v) {
 }
 
 template <int PL, bool F16>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS, Geo<PL>::CTAS_PER_SM) pass2_kernel(const Work w, const int tangent) {
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREADS, Geo<PL>::CTAS_PER_SM) pass2_kernel(const Work w, const int tangent) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ Pipe pipe;
   uint8_t* act = smem;
@@ -658,20 +669,15 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;
-  pipe_init(&pipe, warp, tid);
+  pipe_init<PL>(&pipe, warp, tid);
   const uint32_t tmem = pipe.tmem_base;
 
-  if (warp == W_PROD && lane == 0) {
+  if (warp == Geo<PL>::W_PROD && lane == 0) {
     if (tangent) {
       Producer<PL> pr{&pipe, ring, cluster_ctarank()};
-      // the epilogues read this tile's h1 / c / g with plain loads: pull them into L2 one net ahead of their use
-      auto prefetch_net = [&](int k) {
-        const uint8_t* nt = net_tile<PL>(w, b, k, tl);
-        if (!(w.dbg_flags & 8)) bulk_prefetch_l2(nt, 3 * Geo<PL>::BH);          // B_H1, B_CC, B_GG are the first three blobs
-      };
-      prefetch_net(0);
+      // (measured and dropped: cp.async.bulk.prefetch.L2 of this tile's h1 / c / g one net ahead makes pass 2 13 % SLOWER -
+      //  the epilogue loads are not latency-bound, the extra L2 traffic only competes with the streaming stores)
       for (int k = 0; k < w.Kn; ++k) {
-        if (k + 1 < w.Kn) prefetch_net(k + 1);
         const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
         const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
         pr.stream(gen, 0, 12, STAGE_BYTES);                      // W1
@@ -679,7 +685,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         pr.stream(sta + PL * IMG_HC, 0, 16, STAGE_BYTES);        // Wa
       }
     }
-  } else if (warp == W_MMA && lane == 0) {
+  } else if (warp == Geo<PL>::W_MMA && lane == 0) {
     if (tangent) {
       Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
       uint32_t ae = 0;
@@ -699,11 +705,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         atomicAdd((unsigned long long*)w.phase_dbg + 10, (unsigned long long)t_epi);
       }
     }
-  } else if (warp < EPI_WARPS) {
-    const int half = warp >> 2;
+  } else if (warp < Geo<PL>::EW) {
+    constexpr int NB = Geo<PL>::NB;
+    const int half = warp >> 2;                                     // column group (see pass 1)
     const int r = (warp & 3) * 32 + lane;
-    const int c0 = half * 4;
-    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 128;
+    const int c0 = half * NB;
+    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * (NB * 32);
     const size_t row = g * TP + r;
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     const uint8_t* pe6 = w.pe6_blob + g * Geo<PL>::BC;
@@ -711,8 +718,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
     long long t_acc = 0, t_comp = 0, t_mark = 0;
     const long long t_begin = clock64();
     const uint64_t pol_keep = l2_policy_evict_last();                 // the tile's coordinate features are re-read for every net
-    for (int i = tid; i < 3 * H + 4; i += EPI_THREADS) csum[i] = 0.f;
-    epi_bar();
+    for (int i = tid; i < 3 * H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
+    epi_bar<PL>();
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile<PL>(w, b, k, tl);
       const float dv = w.dov[row * w.Kn + k];
@@ -752,7 +759,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
       // ---- prologue: xt -> activation buffer; zp, zd -> workspace (each half takes 4 of the 8 column groups) ----
       t_mark = clock64();
 #pragma unroll 1
-      for (int it = half * 4; it < half * 4 + 4; ++it) {             // 24 columns = 4 frequencies = 3 pieces per iteration
+      for (int it = half * NB; it < half * NB + NB; ++it) {          // 24 columns = 4 frequencies = 3 pieces per iteration
         float pe[24], xt[24], zp[24];
         uint4 p6[3][PL];
 #pragma unroll
@@ -800,7 +807,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
             for (int p = 0; p < PL; ++p) cur[qd][p] = nxt[qd][p];
-          if (cb < 3) {
+          if (cb < NB - 1) {
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
@@ -845,10 +852,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
           }
         };
         if (tangent) {
-          tmem_blocks<4>(tl_addr, process);
+          tmem_blocks<NB>(tl_addr, process);
         } else {
 #pragma unroll 1
-          for (int cb = 0; cb < 4; ++cb) {
+          for (int cb = 0; cb < NB; ++cb) {
             float v0[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v0[j] = 0.f;
@@ -865,15 +872,15 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
         for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
         if (lane == 0) atomicAdd(csum + 3 * H, sd);
       }
-      epi_bar();
-      for (int i = tid; i < 3 * H; i += EPI_THREADS) {
+      epi_bar<PL>();
+      for (int i = tid; i < 3 * H; i += Geo<PL>::ET) {
         const int qn = i / H, j = i % H;
         float* dstv = qn == 0 ? w.vc : (qn == 1 ? w.vg : w.sm3);
         atomicAdd(dstv + (size_t)k * H + j, csum[i]);
         csum[i] = 0.f;
       }
       if (tid == 0) { atomicAdd(w.sdo + k, csum[3 * H]); csum[3 * H] = 0.f; }
-      epi_bar();
+      epi_bar<PL>();
     }
     if (w.phase_dbg && tid == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 12, (unsigned long long)(clock64() - t_begin));
@@ -885,7 +892,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(FUSED_THREADS,
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == W_MMA) tmem_dealloc(tmem, 256);
+  if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1390,7 +1397,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     const int tiles = B * T;
     encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
     DPN_LAUNCH_OK();
-    pass1_kernel<PL, F16><<<tiles, FUSED_THREADS, smem_fused, st>>>(w, sweep);
+    pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
     DPN_LAUNCH_OK();
     if (J.kind == JOB_DEC_FWD) {
       gather_o_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.o);
@@ -1423,7 +1430,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
       zscale_kernel<<<(B * Kn + 63) / 64, 64, 0, st>>>(B * Kn, c.seedmax, c.sc);
       DPN_LAUNCH_OK();
     }
-    pass2_kernel<PL, F16><<<tiles, FUSED_THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
+    pass2_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc;

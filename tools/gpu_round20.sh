@@ -1,0 +1,13 @@
+#!/bin/bash
+# profiles for the f16x3 default mode: launch list + ncu --set full of the three tcgen05 kernels + accuracy table
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=r01c
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-modes > gpurun_out/ncu_launch_stdout.txt 2>&1
+for k in pass1_kernel pass2_kernel wgrad_kernel; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o gpurun_out/prof_${TAG}_$k \
+      python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-modes > gpurun_out/ncu_${k}_stdout.txt 2>&1
+done
+timeout 600 python tools/mode_accuracy.py > gpurun_out/mode_accuracy_$TAG.txt 2>&1
+ls -la gpurun_out | tail -6
