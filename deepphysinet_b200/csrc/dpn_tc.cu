@@ -21,6 +21,7 @@
 // Every [128 x Kd] bf16 operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh, in shared memory and in
 // the workspace alike, so a tile written once by an epilogue is (a) the K-major A operand of the next GEMM and
 // (b) an MN-major operand of the weight-gradient contraction, and moves with plain 1-D bulk copies.
+#include <math.h>
 #include <stdlib.h>
 
 #include "dpn_tc.cuh"
@@ -36,7 +37,10 @@ constexpr int BLOB_H = TP * H * 2;            // 65536  [128 x 256] bf16
 constexpr int BLOB_C = TP * C * 2;            // 49152  [128 x 192] bf16
 constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of a 128-row blob
 constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a [256 x K] weight image
-constexpr int NSTAGE = 5;
+#ifndef DPN_NSTAGE
+#define DPN_NSTAGE 5
+#endif
+constexpr int NSTAGE = DPN_NSTAGE;
 constexpr int CLUSTER = 2;                     // CTAs (tiles of the same sample) sharing every weight chunk through one multicast L2 read
 constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
@@ -1437,9 +1441,17 @@ static int run_planes(const Job& J, cudaStream_t st) {
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd;
     const int items = B * Kn * 8;
-    int splits = (Geo<PL>::CTAS_PER_SM * 148 * 2 + items - 1) / items;
-    if (splits > T) splits = T;
-    if (splits < 1) splits = 1;
+    // point-splits per (sample, net, layer, out-half): fill whole waves of resident CTAs (148 SMs x CTAs per SM); every split
+    // adds one fp32 red.add pass over the gradient tile, so prefer the smallest count within 2 % of the best wave efficiency
+    int splits = 1;
+    {
+      const double slots = 148.0 * Geo<PL>::CTAS_PER_SM;
+      double best = 0.0;
+      for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
+        const double waves = items * sp / slots, eff = waves / ceil(waves);
+        if (eff > best + 0.02) { best = eff; splits = sp; }
+      }
+    }
     ww.splits = splits;
     wgrad_kernel<PL, F16><<<items * splits, 192, smem_wgrad, st>>>(ww);
     DPN_LAUNCH_OK();
