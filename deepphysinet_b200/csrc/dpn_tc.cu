@@ -37,10 +37,16 @@ constexpr int BLOB_H = TP * H * 2;            // 65536  [128 x 256] bf16
 constexpr int BLOB_C = TP * C * 2;            // 49152  [128 x 192] bf16
 constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of a 128-row blob
 constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a [256 x K] weight image
-#ifndef DPN_NSTAGE
-#define DPN_NSTAGE 5
+// CTA pair (cta_group::2, build with -DDPN_PAIR=1): the two CTAs of a cluster run ONE M = 256 MMA; each CTA stages only ITS half
+// of every weight chunk (N/2 rows), which halves the shared-memory ingress per SM and doubles the ring depth.  Parity-green in all
+// modes and the pair MMA itself runs at 128 cycles per TWO tiles (tools/umma2_probe.cu; 152 per tile for cta_group::1), but the
+// leader has to wait for the slower of two epilogues every round: measured f16x3 25.0 vs 24.3 ms, bf16 11.4 vs 10.9 ms per call.
+// Default 0 = cta_group::1, full chunks multicast to both CTAs.  The pair path pays off only with two tiles in flight per CTA.
+#ifndef DPN_PAIR
+#define DPN_PAIR 0
 #endif
-constexpr int NSTAGE = DPN_NSTAGE;
+constexpr bool PAIR = DPN_PAIR != 0;
+constexpr int NSTAGE = PAIR ? 10 : 5;
 constexpr int CLUSTER = 2;                     // CTAs (tiles of the same sample) sharing every weight chunk through one multicast L2 read
 constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
@@ -54,7 +60,7 @@ enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
 // in shared memory and in the workspace alike, so a tile still moves with one bulk copy.
 template <int PL>
 struct Geo {
-  static constexpr int STAGE = STAGE_BYTES * PL;                 // ring stage: [hi chunk | lo chunk]
+  static constexpr int STAGE = STAGE_BYTES * PL / (PAIR ? 2 : 1);   // ring stage: [hi chunk | lo chunk] (PAIR: this CTA's half of the rows)
   static constexpr int ACT = BLOB_H * PL;                        // activation buffer: plane p at p * BLOB_H
   static constexpr int BH = BLOB_H * PL, BC = BLOB_C * PL;       // workspace blobs: plane p at p * BLOB_H (p * BLOB_C)
   static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
@@ -204,6 +210,7 @@ __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)
 struct Pipe {            // shared-memory barriers of the fused kernels
   uint64_t full[NSTAGE], empty[NSTAGE];
   uint64_t a_bulk, a_epi, acc_ready, act_free;
+  uint64_t peer_full[NSTAGE], peer_epi, peer_bulk;   // leader only: mirrors of the peer CTA's full / a_epi / a_bulk (remote arrives)
   uint64_t st_done;        // the bulk store that drains the activation tile has finished reading it
   uint32_t tmem_base;
 };
@@ -221,6 +228,13 @@ struct Producer {
   uint64_t pol = l2_policy_evict_last();       // weight images: re-read by every tile of the sample, keep them in L2
   __device__ __forceinline__ void put(const uint8_t* src, uint32_t bytes) {
     const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
+    if (PAIR) {                                        // my half of the rows of this chunk (the image stores the halves back to back)
+      mbar_wait(&pp->empty[s], ph ^ 1);              // the pair MMA that read the previous occupant has completed
+      mbar_arrive_expect_tx(&pp->full[s], bytes / 2);
+      bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src + rank * (bytes / 2), bytes / 2, &pp->full[s], pol);
+      ++n;
+      return;
+    }
     mbar_wait(&pp->empty[s], ph ^ 1);                // every CTA of the cluster has consumed the previous occupant
     mbar_arrive_expect_tx(&pp->full[s], bytes);      // my copy of the chunk: my slice + the slices my peers multicast to me
     if (CLUSTER == 1) {
@@ -237,28 +251,63 @@ struct Producer {
   }
 };
 
-// MMA side: one elected thread.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major, Nn rows).
+// MMA side: one elected thread per CTA.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major).
+// PAIR: the leader CTA issues M = 256 MMAs for both tiles once BOTH CTAs' operands are in place; the peer CTA runs the same
+// sequence but, instead of issuing, forwards each of its local completions (weight stage landed, epilogue done, A tile landed)
+// to the leader's mirror barrier with a remote arrive.  Completions come back to both CTAs through multicast commits.
 template <int PL, bool F16 = false>
 struct Issuer {
-  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t n = 0; long long t_full = 0;
+  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t rank;
+  uint32_t n = 0; long long t_full = 0;
+  __device__ __forceinline__ bool leader() const { return !PAIR || rank == 0; }
+  __device__ __forceinline__ void sync_local(uint64_t* local, uint64_t* mirror, uint32_t parity, long long& t) {
+    mbar_wait_t(local, parity, t);
+    if (PAIR) {
+      if (rank == 0) { const long long t0 = clock64(); mbar_wait_cluster(mirror, parity); t += clock64() - t0; }
+      else mbar_arrive_remote(mirror, 0);
+    }
+    tc_fence_after();
+  }
+  __device__ __forceinline__ void wait_epi(uint32_t& ae, long long& t) {      // PAIR: both CTAs' epilogue warps arrive on the leader's barrier
+    if (leader()) { mbar_wait_t(&pp->a_epi, ae & 1, t); tc_fence_after(); }
+    ++ae;
+  }
+  __device__ __forceinline__ void wait_bulk(uint32_t& ab, long long& t) { sync_local(&pp->a_bulk, &pp->peer_bulk, ab & 1, t); ++ab; }
+  __device__ __forceinline__ void commit(uint64_t* bar) {
+    if (!leader()) return;
+    if (PAIR) mma_commit_pair(bar); else mma_commit(bar);
+  }
   __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate) {
-    const uint32_t idesc = idesc_16(F16, Nn, 0, 0);
+    const int Nb = PAIR ? Nn / 2 : Nn;                                  // rows of B staged in this CTA
+    const uint32_t idesc = idesc_16(F16, Nn, 0, 0, PAIR ? 256 : 128);
     for (int c = 0; c < nchunks; ++c) {
       const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
-      mbar_wait_t(&pp->full[s], ph, t_full);
-      tc_fence_after();
+      sync_local(&pp->full[s], &pp->peer_full[s], ph, t_full);
+      ++n;
+      if (!leader()) continue;
       const uint32_t a0 = act_addr + (uint32_t)(c * 2) * CORE_STRIDE, b0 = ring_addr + s * Geo<PL>::STAGE;
       const uint64_t ad = smem_desc(a0, CORE_STRIDE, 128);
-      const uint64_t bd = smem_desc(b0, Nn * 16, 128);
-      if (PL == 2) {                                   // small terms first: lo*hi + hi*lo + hi*hi into one accumulator
-        mma_bf16(tmem, smem_desc(a0 + BLOB_H, CORE_STRIDE, 128), bd, idesc, (accumulate || c > 0) ? 1u : 0u);
-        mma_bf16(tmem, ad, smem_desc(b0 + Nn * 32, Nn * 16, 128), idesc, 1u);
-        mma_bf16(tmem, ad, bd, idesc, 1u);
+      const uint64_t bd = smem_desc(b0, Nb * 16, 128);
+      const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
+      if (PAIR) {
+        if (PL == 2) {                                 // small terms first: lo*hi + hi*lo + hi*hi into one accumulator
+          mma_pair(tmem, smem_desc(a0 + BLOB_H, CORE_STRIDE, 128), bd, idesc, first);
+          mma_pair(tmem, ad, smem_desc(b0 + Nb * 32, Nb * 16, 128), idesc, 1u);
+          mma_pair(tmem, ad, bd, idesc, 1u);
+        } else {
+          mma_pair(tmem, ad, bd, idesc, first);
+        }
+        mma_commit_pair(&pp->empty[s]);
       } else {
-        mma_bf16(tmem, ad, bd, idesc, (accumulate || c > 0) ? 1u : 0u);
+        if (PL == 2) {
+          mma_bf16(tmem, smem_desc(a0 + BLOB_H, CORE_STRIDE, 128), bd, idesc, first);
+          mma_bf16(tmem, ad, smem_desc(b0 + Nb * 32, Nb * 16, 128), idesc, 1u);
+          mma_bf16(tmem, ad, bd, idesc, 1u);
+        } else {
+          mma_bf16(tmem, ad, bd, idesc, first);
+        }
+        if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
       }
-      if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
-      ++n;
     }
   }
 };
@@ -282,25 +331,37 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 template <int PL>
 __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
   if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], CLUSTER); }
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], PAIR ? 1 : CLUSTER); mbar_init(&pp->peer_full[s], 1); }
+    mbar_init(&pp->peer_epi, 1); mbar_init(&pp->peer_bulk, 1);
     mbar_init(&pp->a_bulk, 1);
-    mbar_init(&pp->a_epi, Geo<PL>::ET);         // every epilogue thread arrives
+    mbar_init(&pp->a_epi, PAIR ? 2 * Geo<PL>::EW : Geo<PL>::ET);   // every epilogue thread - PAIR: every epilogue warp of both CTAs - arrives
     mbar_init(&pp->acc_ready, 1);
     mbar_init(&pp->act_free, 1);
     mbar_init(&pp->st_done, 1);
     fence_barrier_init();
   }
-  if (warp == Geo<PL>::W_MMA) tmem_alloc(&pp->tmem_base, 256);   // the MMA warp of the fused kernels owns the allocation
+  if (warp == Geo<PL>::W_MMA) {                                  // the MMA warp of the fused kernels owns the allocation
+    if (PAIR) tmem_alloc_pair(&pp->tmem_base, 256); else tmem_alloc(&pp->tmem_base, 256);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   if (CLUSTER > 1) cluster_sync_all();              // peers' barriers exist before anything is multicast to them
+  // the leader passes ITS accumulator address to the pair MMA: both CTAs must have been given the same columns
+  if (PAIR && tid == 0 && cluster_ctarank() == 1 && ld_remote_u32(&pp->tmem_base, 0) != pp->tmem_base) __trap();
 }
 
 __device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my smem writes / TMEM reads are finished
   tc_fence_before();
   fence_proxy_async();
-  mbar_arrive(&pp->a_epi);
+  if (PAIR) {            // one arrival per warp, straight onto the LEADER's barrier (no relay hop for the peer CTA's tile)
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      if (cluster_ctarank() == 0) mbar_arrive(&pp->a_epi); else mbar_arrive_remote(&pp->a_epi, 0);
+    }
+  } else {
+    mbar_arrive(&pp->a_epi);
+  }
 }
 
 // sign / partner of d(PE_j)/dz: PE[6f+c] = sin, PE[6f+3+c] = cos  ->  dPE[6f+c] = +band cos, dPE[6f+3+c] = -band sin
@@ -319,6 +380,8 @@ template <int PL> __device__ __forceinline__ void epi_bar() { asm volatile("bar.
 // NB consecutive 32-column blocks of this thread's TMEM lane: f(block, float (&v)[32])
 template <int NB, class F>
 __device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f, const bool SKIP_TMEM_DBG = false) {
+  // (software-pipelined TMEM loads - dpn_umma.cuh:tmem_for_each_block - were measured again with 168 registers per thread in the
+  //  one-CTA-per-SM modes: f16x3 call 24.4 -> 26.9 ms; the plain load / wait / process sequence stays)
 #pragma unroll 1
   for (int cb = 0; cb < NB; ++cb) {
     float v[32];
@@ -391,31 +454,31 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
     }
   } else if (warp == Geo<PL>::W_MMA && lane == 0) {
     // ---------------- MMA issuer ----------------
-    Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+    Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank()};
     uint32_t ab = 0, ae = 0;
     long long t_epi = 0, t_bulk = 0;
     const long long t_begin = clock64();
     for (int k = 0; k < w.Kn; ++k) {
-      if (k > 0) { mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; }  // last epilogue of the previous net has drained TMEM
-      mbar_wait_t(&pipe.a_bulk, ab & 1, t_bulk); ++ab; tc_fence_after();
-      is.gemm(12, H, false); mma_commit(&pipe.acc_ready);           // G1
-      mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-      is.gemm(16, H, false); mma_commit(&pipe.act_free);            // G2a
-      mbar_wait_t(&pipe.a_bulk, ab & 1, t_bulk); ++ab; tc_fence_after();
-      is.gemm(12, H, true); mma_commit(&pipe.acc_ready);            // G2b
-      mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-      is.gemm(16, H, false); mma_commit(&pipe.acc_ready);           // G3
+      if (k > 0) is.wait_epi(ae, t_epi);                             // last epilogue of the previous net has drained TMEM
+      is.wait_bulk(ab, t_bulk);
+      is.gemm(12, H, false); is.commit(&pipe.acc_ready);           // G1
+      is.wait_epi(ae, t_epi);
+      is.gemm(16, H, false); is.commit(&pipe.act_free);            // G2a
+      is.wait_bulk(ab, t_bulk);
+      is.gemm(12, H, true); is.commit(&pipe.acc_ready);            // G2b
+      is.wait_epi(ae, t_epi);
+      is.gemm(16, H, false); is.commit(&pipe.acc_ready);           // G3
       if (sweep) {
-        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G4
-        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G5
+        is.wait_epi(ae, t_epi);
+        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G4
+        is.wait_epi(ae, t_epi);
+        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G5
         if (sweep > 1) {
-          mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-          is.gemm(16, C, false); mma_commit(&pipe.acc_ready);       // G6
+          is.wait_epi(ae, t_epi);
+          is.gemm(16, C, false); is.commit(&pipe.acc_ready);       // G6
         }
       }
-      mma_commit(&pipe.act_free);                                   // the activation buffer may take the next PE tile
+      is.commit(&pipe.act_free);                                   // the activation buffer may take the next PE tile
     }
     if (w.phase_dbg) {
       atomicAdd((unsigned long long*)w.phase_dbg + 0, (unsigned long long)(clock64() - t_begin));
@@ -642,7 +705,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 256);
+  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, 256); else tmem_dealloc(tmem, 256); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -691,17 +754,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
     }
   } else if (warp == Geo<PL>::W_MMA && lane == 0) {
     if (tangent) {
-      Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem};
+      Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank()};
       uint32_t ae = 0;
       long long t_epi = 0;
       const long long t_begin = clock64();
       for (int k = 0; k < w.Kn; ++k) {
-        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-        is.gemm(12, H, false); mma_commit(&pipe.acc_ready);         // G7
-        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G8
-        mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); ++ae; tc_fence_after();
-        is.gemm(16, H, false); mma_commit(&pipe.acc_ready);         // G9
+        is.wait_epi(ae, t_epi);
+        is.gemm(12, H, false); is.commit(&pipe.acc_ready);         // G7
+        is.wait_epi(ae, t_epi);
+        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G8
+        is.wait_epi(ae, t_epi);
+        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G9
       }
       if (w.phase_dbg) {
         atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
@@ -896,7 +959,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 256);
+  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, 256); else tmem_dealloc(tmem, 256); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1166,9 +1229,12 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   }
   uint4 pq[PL];
   split8<PL, F16>(v, pq);
-  const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)(kc & 1) * rows * 16 + (size_t)r * 16;
+  // chunk = [rows of CTA 0 | rows of CTA 1] (PAIR: each CTA of a pair stages its half of the rows), each part [hi plane | lo plane],
+  // each plane two k-cores of (part rows) x 16 bytes
+  const int prows = PAIR ? rows / 2 : rows, part = r / prows, rr = r % prows;
+  const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)part * PL * prows * 32 + (size_t)(kc & 1) * prows * 16 + (size_t)rr * 16;
 #pragma unroll
-  for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * rows * 32) = pq[p];
+  for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * prows * 32) = pq[p];
 }
 
 // coordinate / data features of one tile: bf16 blobs (GEMM operands) and the fp32 transposed copy (epilogues)
