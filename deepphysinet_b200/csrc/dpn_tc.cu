@@ -194,9 +194,9 @@ struct NetScales {                       // one per (sample, net)
 constexpr float S_PE = 1024.f;           // coordinate / data features lie in [-1, 1]
 constexpr float F16_TOP = 32768.f;       // bound -> 2^15 (fp16 max is 65504)
 
-__host__ __device__ __forceinline__ float pow2_floor(float x) {           // largest power of two <= x, clamped to [2^-40, 2^40]
-  if (!(x > 9.094947e-13f)) return 9.094947e-13f;                         // also catches NaN / 0 / negatives
-  if (x > 1.0995116e12f) return 1.0995116e12f;
+__host__ __device__ __forceinline__ float pow2_floor(float x) {           // largest power of two <= x, clamped to [2^-80, 2^80]
+  if (!(x > 8.2718061e-25f)) return 8.2718061e-25f;                       // 2^-80; also catches NaN / 0 / negatives
+  if (x > 1.2089258e24f) return 1.2089258e24f;                            // 2^80
 #ifdef __CUDA_ARCH__
   return __uint_as_float(__float_as_uint(x) & 0x7F800000u);
 #else
@@ -1066,7 +1066,7 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
         const NetScales t = w.sc[gk];
         const float sj = layer == 0 ? t.sQ : (layer == 2 ? t.sUM : t.sY);
         const float sz = layer == 0 ? t.sZP : (layer == 1 ? t.sZH : (layer == 2 ? t.sZC : t.sZD));
-        un = 1.f / (sj * sz); un_x = 1.f / (sj * t.sDV);
+        un = (1.f / sj) * (1.f / sz); un_x = (1.f / sj) * (1.f / t.sDV);      // separately: sj * sz may leave the fp32 range
       }
       float v[32];
       for (int cb = 0; cb < Nn / 32; ++cb) {

@@ -62,6 +62,18 @@ def test_f16x3_badly_scaled_weights(scale):
     assert rep["vals_rel"] < 1e-5 and rep["jac_rel"] < 1e-4 and rep["terms_rel"] < 1e-4 and rep["grad_rel_max"] < 1e-4, rep
 
 
+def test_f16x3_huge_loss_factors():
+    """Seeds 1e9 times larger than usual (loss factors x 1e9): the per-point and per-chunk Z-side scales follow them."""
+    from deepphysinet_b200 import testing as T
+    from deepphysinet_b200.config import PhysicsConsts
+    base = PhysicsConsts()
+    consts = PhysicsConsts(factor=tuple(f * 1e9 for f in base.factor))
+    W, pts = T.random_decoder_weights(B=1, N=200, seed=4, device="cuda")
+    rep = T.compare_with_oracle(W, pts, consts=consts, mode="f16x3")
+    print({k: v for k, v in rep.items() if k != "grad_rel"})
+    assert rep["jac_rel"] < 1e-4 and rep["terms_rel"] < 1e-4 and rep["grad_rel_max"] < 1e-4, rep
+
+
 def test_f16x3_chunking_is_invisible():
     from deepphysinet_b200 import functional as Fn, testing as T
     W, pts = T.random_decoder_weights(B=2, N=600, seed=3, device="cuda")

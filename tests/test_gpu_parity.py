@@ -1,9 +1,10 @@
 """GPU (-m gpu): the CUDA library, called through the C ABI, against the CPU oracle and against the
 golden vectors of the unmodified reference.
 
-Tolerances (BASELINE.json north_star): fp32 mode 1e-4 relative on loss terms, values, Jacobian and
-every weight-gradient tensor; the bf16 tensor-core mode is checked against its own stated tolerance
- in test_gpu_bf16.py.
+Tolerances (BASELINE.json north_star): 1e-4 relative on loss terms, values, Jacobian and every weight-gradient
+tensor for the fp32 mode (CUDA cores) and for the default tensor-core mode f16x3 (golden cases here, random weights in
+test_gpu_f16x3.py); the bf16x3 / bf16 tensor-core modes are checked against their own stated tolerances
+ in test_gpu_bf16x3.py / test_gpu_bf16.py.
 """
 import numpy as np
 import pytest
@@ -62,7 +63,7 @@ def test_fp32_chunking_is_invisible():
         assert H.rel(ga.cpu(), gb.cpu()) < 2e-5
 
 
-def _run_place_one_batch(name, dtype):
+def _run_place_one_batch(name, dtype, mode="fp32"):
     from deepphysinet_b200 import InterfacePhysics
     from deepphysinet_b200.config import DEFAULT_LOSS_FACTOR
     from oracle import make_golden as MG
@@ -73,7 +74,7 @@ def _run_place_one_batch(name, dtype):
                          dict(img_size=(Hh, Ww), dx=float(case["dx"]), dy=float(case["dx"]))).to(dtype)
     MG.scale_out_fc(m.physics_net, float(case["out_scale"]))
     m.with_clip = bool(case["with_clip"])
-    m.mode = "fp32"
+    m.mode = mode
     m = m.cuda()
     x, y, t, f, cd, field, fh = H.case_inputs(name, dtype)
     loss = m.place_one_batch(x, y, t, f, field, cd, fh, torch.nn.MSELoss(), DEFAULT_LOSS_FACTOR, 0, 0, "cuda:0")
@@ -95,13 +96,15 @@ def _grad_errors(case, m):
     return out
 
 
+@pytest.mark.parametrize("mode", ["fp32", "f16x3"])
 @pytest.mark.parametrize("name", H.CASES)
-def test_fp32_place_one_batch_matches_reference_golden(name):
+def test_place_one_batch_matches_reference_golden(name, mode):
     """Full drop-in surface: InterfacePhysics.place_one_batch (+ backward through hyper-network and encoder) on the
     GPU vs the fp64 run of the unmodified reference stored in tests/golden.  The PyTorch part (encoder, hyper-network)
     runs in fp64 here so that what is measured is the CUDA operator (fp32 mode), not cuDNN/cuBLAS round-off upstream of
-    it; test_fp32_place_one_batch_all_fp32 covers the all-fp32 configuration against the reference's own fp32 noise."""
-    case, m, loss = _run_place_one_batch(name, torch.float64)
+    it; test_fp32_place_one_batch_all_fp32 covers the all-fp32 configuration against the reference's own fp32 noise.
+    The default tensor-core mode (f16x3: scaled fp16 hi+lo operands) is held to the same bounds as the CUDA-core fp32 mode."""
+    case, m, loss = _run_place_one_batch(name, torch.float64, mode)
     np.testing.assert_allclose(loss.item(), case["total64"], rtol=TOL_FP32)
     np.testing.assert_allclose(m.last_terms[0].cpu().numpy(), case["terms64"], rtol=TOL_FP32)
     worst = ("", 0.0)
@@ -114,7 +117,7 @@ def test_fp32_place_one_batch_matches_reference_golden(name):
         if err / max(n64, 1e-300) > worst[1]:
             worst = (k, err / max(n64, 1e-300))
         assert err <= bound, (k, err, n64, ref_noise)
-    print(name, "worst grad rel err", worst)
+    print(name, mode, "worst grad rel err", worst)
 
 
 def test_fp32_place_one_batch_all_fp32():
