@@ -12,7 +12,7 @@ reference's *structure* (autograd double-backward), this file follows the produc
 
 It is exact (up to fp rounding) w.r.t. the reference because ReLU / clip masks are constants under
 PyTorch double-backward (threshold_backward), see SURVEY.md App. A.  `rnd` emulates the operand
-rounding of a tensor-core mode (identity for fp32/fp64, bf16 round-trip for the bf16 mode).
+rounding of a tensor-core mode (identity for fp32/fp64; bf16_round, bf16_split_round, f16_split_round for the three tcgen05 modes).
 """
 import torch
 
@@ -35,6 +35,17 @@ def bf16_split_round(a):
     the lo*lo product the kernels drop (2^-18 relative, below the representation error)."""
     hi = bf16_round(a)
     return hi + bf16_round(a - hi)
+
+
+def f16_split_round(a):
+    """Operand as the f16x3 mode sees it: scaled by a power of two that brings the tile's bound to 2^15 (here: its actual
+    maximum, the kernels use rigorous L1-norm bounds a few binades looser - fp16 has the exponent range to absorb that),
+    then hi = fp16(v) plus lo = fp16(v - hi) (22 mantissa bits)."""
+    m = a.abs().max().clamp_min(1e-300)
+    s = torch.exp2(torch.floor(torch.log2(32768.0 / m)))
+    v = a * s
+    hi = v.to(torch.float16).to(a.dtype)
+    return (hi + (v - hi).to(torch.float16).to(a.dtype)) / s
 
 
 def coord_features(x, y, t, dx, dy, lat_size, lon_size, t_span):

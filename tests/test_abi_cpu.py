@@ -44,11 +44,29 @@ def test_argument_validation_without_gpu():
     buf = C.create_string_buffer(256)
     L.dpn_last_error(buf, 256)
     assert b"bad shape" in buf.value
-    for mode in (0, 1):
+    for mode in N.MODES.values():
         ok = N.DpnShape(B=8, N=65536, K=6, mode=mode, n_norm=0, seed_scale=0.125, chunk=0)
         assert L.dpn_workspace_bytes(C.byref(ok), C.byref(need)) == 0 and need.value > 0
     # the 0.25 degree / B=8 / 65k configuration must fit comfortably in 180 GB
     assert need.value < 40 * 2 ** 30
+
+
+def test_mode_enum_matches_header():
+    """Every DPN_MODE_* of the header is reachable from Python under the documented name, and unknown modes are refused."""
+    N = _lib()
+    header = open(os.path.join(ROOT, "include", "dpn_b200.h")).read()
+    declared = {name.lower(): int(val) for name, val in re.findall(r"DPN_MODE_(\w+)\s*=\s*(\d+)", header)}
+    assert declared == N.MODES, (declared, N.MODES)
+    need = C.c_size_t(0)
+    bad = N.DpnShape(B=1, N=128, K=6, mode=max(N.MODES.values()) + 1, n_norm=0, seed_scale=1.0, chunk=0)
+    assert N.lib().dpn_workspace_bytes(C.byref(bad), C.byref(need)) != 0
+    # split-operand modes keep two planes per tile but halve the points in flight: same workspace class
+    sizes = {}
+    for name, mode in N.MODES.items():
+        shp = N.DpnShape(B=8, N=65536, K=6, mode=mode, n_norm=0, seed_scale=0.125, chunk=0)
+        assert N.lib().dpn_workspace_bytes(C.byref(shp), C.byref(need)) == 0
+        sizes[name] = need.value
+    assert 0.8 < sizes["f16x3"] / sizes["bf16"] < 1.25 and sizes["f16x3"] == sizes["bf16x3"], sizes
 
 
 def test_no_cpu_fallback():
