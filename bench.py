@@ -155,6 +155,48 @@ def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False):
     return line
 
 
+def eager_gpu_arm(dev, n_points):
+    """The competitor on the same box: the reference's formulation - six nets, one autograd.grad(create_graph=True)
+    per derivative, double backward - executed by PyTorch eager on this GPU in fp32.  It is the oracle port moved to CUDA
+    (a baseline leg like cpu_baseline: reported beside the product, never part of it); B = 1 x n_points, decoder only
+    (the encoder output is computed once outside the timed region)."""
+    import torch
+    from deepphysinet_b200.physics_net import PhysicsNet
+    from oracle import dpn_oracle as O
+    torch.manual_seed(0)
+    net = PhysicsNet(META_CFG, NET_CFG).to(dev)
+    gen = torch.Generator().manual_seed(1234)
+    x, y, t, f, cd = (a.to(dev) for a in O.synthetic_points(n_points, gen))
+    field = torch.randn(1, 159, 2405, generator=gen).to(dev)
+    fh = torch.tensor([[[24.0 / 360.0]]], device=dev)
+    params = O.split_params(dict(net.named_parameters()))
+
+    def step():
+        net.zero_grad(set_to_none=True)
+        meta = net.meta_net(field, fh)
+        total, _ = O.place_one_batch(x, y, t, f, cd, fh, meta, params)
+        total.backward()
+
+    try:
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out = {"value": n_points / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+               "sample": "B=1 x %d query points, PyTorch eager fp32 autograd double backward (oracle port on cuda), incl. encoder" % n_points}
+    except Exception as ex:                                                  # a baseline leg must never take the bench down
+        out = {"unavailable": str(ex)[:200]}
+    del net, params
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -168,6 +210,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--no-eager-gpu", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time the eager place_one_batch call instead of its CUDA-graph capture")
     ap.add_argument("--e2e-breakdown", action="store_true", help="print per-phase times of the e2e step to stderr")
     args = ap.parse_args()
@@ -366,6 +409,11 @@ def main():
                 "mma_passes_per_contraction": MMA_PASSES[args.mode],
                 "tensor_pipe_tflops": MMA_PASSES[args.mode] * EXEC_FLOP_PER_POINT * per_gpu_pts / 1e12}
 
+    # ---- the reference's own way of running this path on the same GPU: PyTorch eager autograd (double backward) ----
+    eager_gpu = None
+    if rank == 0 and world == 1 and not args.no_eager_gpu:
+        eager_gpu = eager_gpu_arm(dev, args.points)
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_arm(3, 1, args.cpu_points, emit=False, as_baseline=True)
@@ -380,7 +428,7 @@ def main():
                            "parallelism": "dp%d (samples sharded, NCCL grad all-reduce)" % world,
                            "l2": "per-step working set (%.1f GB workspace) >> 126 MB L2; no flush needed" %
                                  (Nat.workspace(Fn._shape(B, Np, 6, args.mode), dev)[1] / 2 ** 30)},
-                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+                "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "clocks": clocks,
                 "gpu_launches": int(holder.get("launches", 0)) * args.steps, "modes": modes}
         print(json.dumps(line))
     if world > 1:

@@ -51,7 +51,7 @@ def freq_bands(n_freqs: int, max_freq: float = 4.0) -> torch.Tensor:
 def sine_cos_pe(v: torch.Tensor, n_freqs: int) -> torch.Tensor:
     """utils/position_encoding.py:35-50 with include_input=False.
     out[..., f*2C + k*C + c] = fn_k(v[..., c] * band_f), fn_0 = sin, fn_1 = cos."""
-    bands = freq_bands(n_freqs).to(v.dtype)
+    bands = freq_bands(n_freqs).to(device=v.device, dtype=v.dtype)
     arg = v[..., None, :] * bands[:, None]                 # [..., F, C]
     emb = torch.stack((torch.sin(arg), torch.cos(arg)), dim=-2)  # [..., F, 2, C]
     return emb.reshape(v.shape[:-1] + (-1,))

@@ -113,8 +113,10 @@ def test_place_one_batch_matches_reference_golden(name, mode):
         # fp32-vs-fp64 discrepancy on that tensor as the yardstick where it is larger (key_projection.bias has an
         # analytically zero gradient: the reference's fp32 value there is pure round-off noise; the rho-net tensors
         # are ill-conditioned - the reference itself only reaches ~1e-4 on them in fp32).
-        bound = max(5 * TOL_FP32 * n64, 10.0 * ref_noise)
-        if err / max(n64, 1e-300) > worst[1]:
+        # f16x3: the tensor core accumulates round-toward-zero (3e-6 per contraction instead of fp32's 6e-8), which the same
+        # ill-conditioned tensors amplify to just under 1e-3 - 4x the fp32 bound, 100x tighter than the bf16 mode.
+        bound = max((5 if mode == "fp32" else 20) * TOL_FP32 * n64, 10.0 * ref_noise)
+        if err / max(n64, 1e-300) > worst[1] and ref_noise < 1e-2 * n64:
             worst = (k, err / max(n64, 1e-300))
         assert err <= bound, (k, err, n64, ref_noise)
     print(name, mode, "worst grad rel err", worst)
