@@ -51,7 +51,7 @@ constexpr int CLUSTER = 2;                     // CTAs (tiles of the same sample
 constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
-constexpr int GEN_IMG = 2 * IMG_HC + 2 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T
+constexpr int GEN_IMG = 2 * IMG_HC + 4 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T, P, PT  (P = Wa W2, see FOLD below)
 constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
 constexpr int NBLOB_H = 8, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX
 enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
@@ -66,6 +66,12 @@ struct Geo {
   static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
   static constexpr size_t NET_TILE = (size_t)NBLOB_H * BH + (size_t)NBLOB_C * BC + AUX_BYTES;
   static constexpr int CTAS_PER_SM = PL == 1 ? 2 : 1;
+  // FOLD (one CTA per SM, all 512 TMEM columns): two GEMMs that share their A operand run back to back into TWO accumulators and
+  // share ONE epilogue round.  Pass 1: y = um Wa (G4) and q = um (Wa W2) + 2wo W2 (G5 with the pre-multiplied P = Wa W2) both read
+  // the um tile; pass 2: ct = ht W2^T (G8) and gt = ht P^T (G9) both read the ht tile.  Same result, one MMA -> epilogue -> MMA
+  // serialisation less per net in each pass.
+  static constexpr bool FOLD = PL == 2;
+  static constexpr int TMEM_COLS = FOLD ? 512 : 256;
   // Epilogue warps: warps w, w+4, w+8, ... share the TMEM lanes 32 (w % 4) .. +31 and split the 256 columns into NQ groups.
   // 8 warps everywhere: 16 warps (column quarters) were measured for the one-CTA-per-SM split modes and LOSE 11 % - the 96-register
   // budget of 576 threads spills in the pass-2 epilogues (f16x3 call 24.3 -> 27.0 ms); the code below stays generic in EW.
@@ -76,7 +82,7 @@ struct Geo {
   static constexpr int W_PROD = EW, W_MMA = EW + 1;              // producer / MMA-issuer warps
   static constexpr int THREADS = ET + 64;
 };
-enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, NVEC };   // epilogue vectors staged in shared memory per net
+enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, V_C2, NVEC };   // epilogue vectors staged in shared memory per net
 
 struct NetScales;
 
@@ -92,6 +98,7 @@ struct Work {
   // epilogue vectors (fp32)
   const float *b1, *bsum;  // [B][Kn][H]
   const float *ba, *uvec, *wo2, *cst;   // [Kn][H], cst [Kn]
+  const float* c2;         // [B][Kn][H]  2wo W2 (FOLD)
   // per-point
   const float* coord_data; // [B*N][6]
   uint8_t* pe_blob;        // [B*T][PL][BLOB_C]
@@ -183,13 +190,12 @@ __device__ __forceinline__ void stg8(uint8_t* tile, uint32_t plane, uint32_t off
 // overflow whatever the weights are; the 30 binades of fp16 below the bound absorb the looseness of the bounds.
 // ------------------------------------------------------------------------------------------------
 struct NetScales {                       // one per (sample, net)
-  float sW1, sW2, sWd, sWa;              // weight images (a matrix and its transpose share the factor)
+  float sW1, sW2, sWd, sWa, sP;          // weight images (a matrix and its transpose share the factor); P = Wa W2
   float sH1, sC, sG, sUM, sY, sQ;        // tiles written by pass 1: h1, c, g, u*m3, y, q*m1
   float M1, Mc, l1W1, l1W12;             // bounds of |h1|, |c|; L1(W1), L1(W1) L1(W2)
   float rowB;                            // max(1, L1(W1), L1(W1) L1(W2)): growth of the pass-2 tangent row over its chain
   float cap;                             // largest sH1 * sW2 this (sample, net) can carry (plan_kernel takes the min over samples)
   float sZP, sZH, sZC, sZD, sDV;         // Z-side tiles and the seed tile of the CURRENT chunk (zscale_kernel)
-  float pad_;
 };
 constexpr float S_PE = 1024.f;           // coordinate / data features lie in [-1, 1]
 constexpr float F16_TOP = 32768.f;       // bound -> 2^15 (fp16 max is 65504)
@@ -277,7 +283,8 @@ struct Issuer {
     if (!leader()) return;
     if (PAIR) mma_commit_pair(bar); else mma_commit(bar);
   }
-  __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate) {
+  __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate, uint32_t col = 0) {   // accumulator = TMEM columns [col, col + Nn)
+    const uint32_t tmem = this->tmem + col;
     const int Nb = PAIR ? Nn / 2 : Nn;                                  // rows of B staged in this CTA
     const uint32_t idesc = idesc_16(F16, Nn, 0, 0, PAIR ? 256 : 128);
     for (int c = 0; c < nchunks; ++c) {
@@ -341,7 +348,7 @@ __device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
     fence_barrier_init();
   }
   if (warp == Geo<PL>::W_MMA) {                                  // the MMA warp of the fused kernels owns the allocation
-    if (PAIR) tmem_alloc_pair(&pp->tmem_base, 256); else tmem_alloc(&pp->tmem_base, 256);
+    if (PAIR) tmem_alloc_pair(&pp->tmem_base, Geo<PL>::TMEM_COLS); else tmem_alloc(&pp->tmem_base, Geo<PL>::TMEM_COLS);
   }
   tc_fence_before();
   __syncthreads();
@@ -397,7 +404,7 @@ __device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f, const bool SK
 
 __device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, int k, int t) {
   const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
-  const float* src[NVEC] = {w.b1 + vb, w.bsum + vb, w.ba + vk, w.uvec + vk, w.wo2 + vk};
+  const float* src[NVEC] = {w.b1 + vb, w.bsum + vb, w.ba + vk, w.uvec + vk, w.wo2 + vk, w.c2 + vb};
 #pragma unroll
   for (int i = 0; i < NVEC; ++i) svec[i * H + t] = __ldg(src[i] + t);       // t = 0..255
 }
@@ -431,6 +438,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
       const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
       const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
       const uint8_t *iW1 = gen, *iW1T = gen + PL * IMG_HC, *iW2 = gen + PL * 2 * IMG_HC, *iW2T = gen + PL * (2 * IMG_HC + IMG_HH);
+      const uint8_t* iPT = gen + PL * (2 * IMG_HC + 3 * IMG_HH);
       const uint8_t *iWd = sta, *iWa = sta + PL * IMG_HC, *iWaT = sta + PL * (IMG_HC + IMG_HH);
       pr.stream(iW1, 0, 4, STAGE_BYTES);              // these do not depend on the activation buffer
       if (k > 0) {
@@ -448,7 +456,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
       pr.stream(iWa, 0, 16, STAGE_BYTES);
       if (sweep) {
         pr.stream(iWaT, 0, 16, STAGE_BYTES);
-        pr.stream(iW2T, 0, 16, STAGE_BYTES);
+        pr.stream(Geo<PL>::FOLD ? iPT : iW2T, 0, 16, STAGE_BYTES);    // FOLD: q = um (Wa W2) + 2wo W2 straight from the um tile
         if (sweep > 1) pr.stream(iW1T, 0, 16, 6144);
       }
     }
@@ -470,9 +478,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
       is.gemm(16, H, false); is.commit(&pipe.acc_ready);           // G3
       if (sweep) {
         is.wait_epi(ae, t_epi);
-        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G4
-        is.wait_epi(ae, t_epi);
-        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G5
+        if (Geo<PL>::FOLD) {
+          is.gemm(16, H, false);                                     // G4 -> columns [0, 256)
+          is.gemm(16, H, false, 256); is.commit(&pipe.acc_ready);    // G5 (folded) -> columns [256, 512): one epilogue round for both
+        } else {
+          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G4
+          is.wait_epi(ae, t_epi);
+          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G5
+        }
         if (sweep > 1) {
           is.wait_epi(ae, t_epi);
           is.gemm(16, C, false); is.commit(&pipe.acc_ready);       // G6
@@ -521,11 +534,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
       if (tid < H) load_vectors(svec, w, b, k, tid);
       epi_bar<PL>();
       // fp16 variant: accumulators carry (scale of A tile) x (scale of weight image); i* undo that, s* scale the next tile
-      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f;
+      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f, sQ = 1.f;
       if (F16) {
         const NetScales t = w.sc[b * w.Kn + k];
         i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / (t.sUM * t.sWa);
-        i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
+        i5 = Geo<PL>::FOLD ? 1.f / (t.sUM * t.sP) : t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
+        sQ = t.sQ;
         sH1 = t.sH1; sC = t.sC; sG = t.sG; sUM = t.sUM; sY = t.sY;
       }
       uint32_t m1w[NB];                                              // ReLU mask of a1 for this thread's columns
@@ -612,52 +626,95 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
       }, (w.dbg_flags & 4) != 0);
       atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
       epi_done(&pipe); t_comp += clock64() - t_mark;
-      if (sweep) drain(blob_h<PL>(nt, B_UM), false); else epi_bar<PL>();
+      if (sweep) drain(blob_h<PL>(nt, B_UM), Geo<PL>::FOLD && sweep < 2); else epi_bar<PL>();
       if (half == 0) {
         if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
         rowsum[r * 4] = 0.f;
       }
       if (!sweep) continue;
-      // ---- epilogue 4: y = acc + 2wo ----
-      if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-        const int cg = c0 + cb;
+      if (Geo<PL>::FOLD) {
+        // ---- epilogues 4 + 5 in one round: y = acc0 + 2wo -> workspace ;  qm = (acc1 + 2wo W2) * m1 -> next A tile ----
+        epi_bar<PL>();                                              // the drain of the um tile has released the buffer
+        mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
+#pragma unroll 1
+        for (int cb = 0; cb < NB; ++cb) {
+          const int cg = c0 + cb;
+          float v[32];
+          tmem_ld32(tl_addr + cb * 32, v);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
-          if (F16) {
-            v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], i4, wv.x) * sY; v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], i4, wv.y) * sY;
-            v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], i4, wv.z) * sY; v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], i4, wv.w) * sY;
-          } else {
-            v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
+            const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = F16 ? fmaf(v[j4 * 4 + e], i4, ww[e]) * sY : v[j4 * 4 + e] + ww[e];
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) stg8<PL, F16>(blob_h<PL>(nt, B_YT), BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
+          tmem_ld32(tl_addr + 256 + cb * 32, v);
+          uint32_t bits = 0u;
+#pragma unroll
+          for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 cv = *reinterpret_cast<const float4*>(svec + V_C2 * H + cg * 32 + j4 * 4);
+            const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = j4 * 4 + e;
+              const float qv = F16 ? fmaf(v[j], i5, cc[e]) * sQ : v[j] + cc[e];
+              v[j] = ((bits >> j) & 1u) ? qv : 0.f;
+            }
+          }
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const uint32_t off = piece_off(r, cg * 4 + qd);
+            if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
+            else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);
           }
         }
+        epi_done(&pipe); t_comp += clock64() - t_mark;
+      } else {
+      // ---- epilogue 4: y = acc + 2wo ----
+        if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
+        mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
+        tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
+          const int cg = c0 + cb;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
-        }
-      }, (w.dbg_flags & 4) != 0);
-      epi_done(&pipe); t_comp += clock64() - t_mark;
-      drain(blob_h<PL>(nt, B_YT), sweep < 2);
-      // ---- epilogue 5: qm = acc * m1 ----
-      if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-        const int cg = c0 + cb;
-        uint32_t bits = 0u;
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
+            if (F16) {
+              v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], i4, wv.x) * sY; v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], i4, wv.y) * sY;
+              v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], i4, wv.z) * sY; v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], i4, wv.w) * sY;
+            } else {
+              v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
+            }
+          }
 #pragma unroll
-        for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
+          for (int qd = 0; qd < 4; ++qd) {
+            sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
+          }
+        }, (w.dbg_flags & 4) != 0);
+        epi_done(&pipe); t_comp += clock64() - t_mark;
+        drain(blob_h<PL>(nt, B_YT), sweep < 2);
+        // ---- epilogue 5: qm = acc * m1 ----
+        if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
+        mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
+        tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
+          const int cg = c0 + cb;
+          uint32_t bits = 0u;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
+          for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          const uint32_t off = piece_off(r, cg * 4 + qd);
-          if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
-          else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
-        }
-      }, (w.dbg_flags & 4) != 0);
-      epi_done(&pipe); t_comp += clock64() - t_mark;
+          for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            const uint32_t off = piece_off(r, cg * 4 + qd);
+            if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
+            else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
+          }
+        }, (w.dbg_flags & 4) != 0);
+        epi_done(&pipe); t_comp += clock64() - t_mark;
+      }
       if (sweep < 2) continue;
       drain(blob_h<PL>(nt, B_QM), true);
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
@@ -705,7 +762,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, 256); else tmem_dealloc(tmem, 256); }
+  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, Geo<PL>::TMEM_COLS); else tmem_dealloc(tmem, Geo<PL>::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -749,7 +806,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
         pr.stream(gen, 0, 12, STAGE_BYTES);                      // W1
         pr.stream(gen + PL * 2 * IMG_HC, 0, 16, STAGE_BYTES);    // W2
-        pr.stream(sta + PL * IMG_HC, 0, 16, STAGE_BYTES);        // Wa
+        if (Geo<PL>::FOLD) pr.stream(gen + PL * (2 * IMG_HC + 2 * IMG_HH), 0, 16, STAGE_BYTES);   // P = Wa W2: gt = ht P^T from the ht tile
+        else pr.stream(sta + PL * IMG_HC, 0, 16, STAGE_BYTES);   // Wa
       }
     }
   } else if (warp == Geo<PL>::W_MMA && lane == 0) {
@@ -762,9 +820,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         is.wait_epi(ae, t_epi);
         is.gemm(12, H, false); is.commit(&pipe.acc_ready);         // G7
         is.wait_epi(ae, t_epi);
-        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G8
-        is.wait_epi(ae, t_epi);
-        is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G9
+        if (Geo<PL>::FOLD) {
+          is.gemm(16, H, false);                                     // G8 -> columns [0, 256)
+          is.gemm(16, H, false, 256); is.commit(&pipe.acc_ready);    // G9 (folded) -> columns [256, 512): both read the ht tile
+        } else {
+          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G8
+          is.wait_epi(ae, t_epi);
+          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G9
+        }
       }
       if (w.phase_dbg) {
         atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
@@ -805,7 +868,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         sp = Rp > 0.f ? scale_for(Rp * t.rowB) : 1.f;
         isp = 1.f / sp;
         sZP = t.sZP; sZH = t.sZH; sZC = t.sZC; sZD = t.sZD; sDV = t.sDV;
-        iH1 = 1.f / t.sH1; iC = 1.f / t.sC; iG = 1.f / t.sG; iW1 = 1.f / t.sW1; iW2 = 1.f / t.sW2; iWa = 1.f / t.sWa;
+        iH1 = 1.f / t.sH1; iC = 1.f / t.sC; iG = 1.f / t.sG; iW1 = 1.f / t.sW1; iW2 = 1.f / t.sW2;
+        iWa = 1.f / (Geo<PL>::FOLD ? t.sP : t.sWa);                  // FOLD: G9 contracts ht with P = Wa W2
       }
       // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three 16-bit terms, rest 0
       if (half == 0) {
@@ -866,7 +930,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
           for (int p = 0; p < PL; ++p) nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + piece_off(r, c0 * 4 + qd)));
-        if (tangent) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64(); }
+        // FOLD: G8 and G9 were issued together; the st = 2 phase finds its accumulator (columns 256..511) already complete
+        if (tangent && !(Geo<PL>::FOLD && st == 2)) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
+        t_mark = clock64();
         auto process = [&](const int cb, float (&v)[32]) {
           const int cg = c0 + cb;
           uint4 cur[4][PL];
@@ -900,7 +966,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
             }
             const uint32_t off = piece_off(r, cg * 4 + qd);
             if (st < 2) stg8<PL, F16>(dst, BLOB_H, off, zs);
-            if (tangent && st < 2) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
+            if (tangent && (st == 0 || (st == 1 && !Geo<PL>::FOLD))) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);   // FOLD: ct is no A operand
           }
           if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
             const float cs = warp_colsum32(z, lane);
@@ -919,7 +985,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
           }
         };
         if (tangent) {
-          tmem_blocks<NB>(tl_addr, process);
+          tmem_blocks<NB>(tl_addr + ((Geo<PL>::FOLD && st == 2) ? 256u : 0u), process);
         } else {
 #pragma unroll 1
           for (int cb = 0; cb < NB; ++cb) {
@@ -929,7 +995,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
             process(cb, v0);
           }
         }
-        if (tangent && st < 2) epi_done(&pipe);
+        if (tangent && (st == 0 || (st == 1 && !Geo<PL>::FOLD))) epi_done(&pipe);
         t_comp += clock64() - t_mark;
       }
       // ---- flush this net's column sums ----
@@ -959,7 +1025,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   tc_fence_before();
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, 256); else tmem_dealloc(tmem, 256); }
+  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, Geo<PL>::TMEM_COLS); else tmem_dealloc(tmem, Geo<PL>::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1096,6 +1162,43 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // SIMT helpers of the tensor-core mode
 // ------------------------------------------------------------------------------------------------
+// ---- FOLD: P = Wa W2 and c2 = 2wo W2 per (sample, net), fp32 on the CUDA cores (0.8 GMAC per call) ---------------------------
+// y = um Wa + 2wo and q = y W2 are consecutive linear maps of the same tile, so q = um P + c2: G4 and G5 can share one round.
+__global__ void __launch_bounds__(256) pfold_kernel(int Kn, const float* __restrict__ Wa, const float* __restrict__ W2,
+                                                    float* __restrict__ P) {
+  __shared__ float sA[32][33], sB[32][33];
+  const int bk = blockIdx.z, k = bk % Kn;
+  const float* A = Wa + (size_t)k * H * H;                     // [j][i]
+  const float* Bm = W2 + (size_t)bk * H * H;                   // [i][l]
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads, 4 rows each
+  const int j0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int i0 = 0; i0 < H; i0 += 32) {
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      sA[ty * 4 + rr][tx] = A[(size_t)(j0 + ty * 4 + rr) * H + i0 + tx];
+      sB[ty * 4 + rr][tx] = Bm[(size_t)(i0 + ty * 4 + rr) * H + l0 + tx];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float bv = sB[i][tx];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) acc[rr] = fmaf(sA[ty * 4 + rr][i], bv, acc[rr]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) P[((size_t)bk * H + j0 + ty * 4 + rr) * H + l0 + tx] = acc[rr];
+}
+__global__ void __launch_bounds__(256) c2_kernel(int Kn, const float* __restrict__ wo2, const float* __restrict__ W2, float* __restrict__ c2) {
+  const int bk = blockIdx.x, k = bk % Kn, l = threadIdx.x;
+  const float* Bm = W2 + (size_t)bk * H * H;
+  float s = 0.f;
+  for (int i = 0; i < H; ++i) s = fmaf(wo2[(size_t)k * H + i], Bm[(size_t)i * H + l], s);
+  c2[(size_t)bk * H + l] = s;
+}
+
 // ---- scaling plan of the fp16 variant -------------------------------------------------------------
 __device__ __forceinline__ float block_max256(float v, float* red) {      // 256 threads; every thread gets the result
 #pragma unroll
@@ -1114,7 +1217,8 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
                                                      const float* __restrict__ W2, const float* __restrict__ Wd,
                                                      const float* __restrict__ Wa, const float* __restrict__ ba,
                                                      const float* __restrict__ bsum, const float* __restrict__ uvec,
-                                                     const float* __restrict__ wo2, NetScales* __restrict__ tab) {
+                                                     const float* __restrict__ wo2, const float* __restrict__ P,
+                                                     NetScales* __restrict__ tab) {
   __shared__ float red[8];
   const int bk = blockIdx.x, k = bk % Kn, j = threadIdx.x;
   const float* w1 = W1 + ((size_t)bk * H + j) * C;
@@ -1126,8 +1230,9 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
     const float a = fabsf(w1[i]), d = fabsf(wd[i]);
     r1 += a; m1 = fmaxf(m1, a); rd += d; md = fmaxf(md, d);
   }
-  float r2 = 0.f, c2 = 0.f, m2 = 0.f, ra = 0.f, ca = 0.f, ma = 0.f;
+  float r2 = 0.f, c2 = 0.f, m2 = 0.f, ra = 0.f, ca = 0.f, ma = 0.f, mp = 0.f;
   for (int i = 0; i < H; ++i) {
+    mp = fmaxf(mp, fabsf(P[((size_t)bk * H + j) * H + i]));
     const float x2 = fabsf(w2[(size_t)j * H + i]), y2 = fabsf(w2[(size_t)i * H + j]);
     const float xa = fabsf(wa[(size_t)j * H + i]), ya = fabsf(wa[(size_t)i * H + j]);
     r2 += x2; c2 += y2; m2 = fmaxf(m2, x2); ra += xa; ca += ya; ma = fmaxf(ma, xa);
@@ -1136,6 +1241,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
   const float l1W2 = block_max256(r2, red), l1Wd = block_max256(rd, red), l1Wa = block_max256(ra, red);
   const float cW2 = block_max256(c2, red), cWa = block_max256(ca, red);
   const float mW1 = block_max256(m1, red), mW2 = block_max256(m2, red), mWd = block_max256(md, red), mWa = block_max256(ma, red);
+  const float mP = block_max256(mp, red);
   const float mBs = block_max256(fabsf(bsum[(size_t)bk * H + j]), red), mBa = block_max256(fabsf(ba[(size_t)k * H + j]), red);
   const float Mu = block_max256(fabsf(uvec[(size_t)k * H + j]), red), mWo2 = block_max256(fabsf(wo2[(size_t)k * H + j]), red);
   if (j == 0) {
@@ -1144,6 +1250,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
     const float My = Mu * cWa + mWo2, Mq = My * cW2;
     t.sW1 = scale_for(mW1 * 32.f);                   // weights: maximum -> 2^10
     t.sWa = scale_for(mWa * 32.f);
+    t.sP = scale_for(mP * 32.f);
     t.sWd = scale_for(mWd * 32.f);                   // preliminary: plan_kernel couples sWd, sH1 and sW2
     t.sW2 = scale_for(mW2);                          // preliminary: the LARGEST admissible factor
     t.sH1 = scale_for(M1); t.sC = scale_for(Mc); t.sG = scale_for(Mg);
@@ -1151,7 +1258,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
     t.M1 = M1; t.Mc = Mc; t.l1W1 = l1W1; t.l1W12 = l1W1 * l1W2;
     t.rowB = fmaxf(1.f, fmaxf(l1W1, l1W1 * l1W2));
     t.cap = t.sH1 * t.sW2;
-    t.sZP = t.sZH = t.sZC = t.sZD = t.sDV = 1.f; t.pad_ = 0.f;
+    t.sZP = t.sZH = t.sZC = t.sZD = t.sDV = 1.f;
     tab[bk] = t;
   }
 }
@@ -1223,7 +1330,7 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   for (int e = 0; e < 8; ++e) v[e] = transpose ? S[(size_t)(kc * 8 + e) * rows + r] : S[(size_t)r * kd + kc * 8 + e];
   if (F16) {                                                         // entry blockIdx.y: (sample, net) for generated weights, (0, net) for static ones
     const NetScales& t = tab[blockIdx.y];
-    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : t.sWa));
+    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : (which == 3 ? t.sWa : t.sP)));
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] *= sc;
   }
@@ -1328,7 +1435,7 @@ __global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
 // ------------------------------------------------------------------------------------------------
 struct Carve {
   uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
-  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo;
+  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo, *P, *c2;
   long long* dbg;
   NetScales* sc;
   int* seedmax;
@@ -1360,6 +1467,8 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B, int pl) {
   c.vg = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sm3 = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sdo = reinterpret_cast<float*>(take((size_t)Kn * 4));
+  c.P = reinterpret_cast<float*>(take((size_t)B * Kn * H * H * 4));
+  c.c2 = reinterpret_cast<float*>(take((size_t)B * Kn * H * 4));
   c.dbg = reinterpret_cast<long long*>(take(16 * 8));
   c.sc = reinterpret_cast<NetScales*>(take((size_t)B * Kn * sizeof(NetScales)));
   c.seedmax = reinterpret_cast<int*>(take((size_t)B * Kn * 2 * sizeof(int)));
@@ -1383,11 +1492,14 @@ static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cuda
       {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0},                  // W1T : rows = in,  k = out
       {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1},
       {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen, 1},
+      {c.P, (size_t)H * H, 2 * IMG_HC + 2 * IMG_HH, GEN_IMG, H, H, 0, PL == 2 ? B * Kn : 0, c.img_gen, 4},   // P  : rows = a3 index, k = a1 index (pass 2, G9)
+      {c.P, (size_t)H * H, 2 * IMG_HC + 3 * IMG_HH, GEN_IMG, H, H, 1, PL == 2 ? B * Kn : 0, c.img_gen, 4},   // PT : rows = a1 index, k = a3 index (pass 1, G5)
       {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta, 2},
       {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta, 3},
       {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta, 3},
   };
   for (const Spec& s : specs) {
+    if (s.batches == 0) continue;
     const int pieces = s.rows * s.kd / 8;
     image_kernel<PL, F16><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
                                                                                  s.rows, s.kd, s.tr, c.sc, s.which);
@@ -1422,8 +1534,14 @@ static int run_planes(const Job& J, cudaStream_t st) {
   static const bool phase_debug = getenv("DPN_PHASE_DEBUG") != nullptr;
   if (phase_debug) DPN_CUDA_OK(cudaMemsetAsync(c.dbg, 0, 16 * 8, st));
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
+  if (Geo<PL>::FOLD) {
+    pfold_kernel<<<dim3(H / 32, H / 32, B * Kn), 256, 0, st>>>(Kn, Wt.Wa, Wt.W2, c.P);
+    DPN_LAUNCH_OK();
+    c2_kernel<<<B * Kn, 256, 0, st>>>(Kn, c.wo2, Wt.W2, c.c2);
+    DPN_LAUNCH_OK();
+  }
   if (F16) {                                                          // scaling plan before anything is converted to fp16
-    bounds_kernel<<<B * Kn, 256, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, c.sc);
+    bounds_kernel<<<B * Kn, 256, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, c.P, c.sc);
     DPN_LAUNCH_OK();
     plan_kernel<<<1, 32, 0, st>>>(B, Kn, c.sc);
     DPN_LAUNCH_OK();
@@ -1455,7 +1573,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     memset(&w, 0, sizeof(w));
     w.B = B; w.Kn = Kn; w.T = T; w.P = P; w.N = N; w.p0 = p0;
     w.img_gen = c.img_gen; w.img_sta = c.img_sta;
-    w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst;
+    w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst; w.c2 = c.c2;
     w.coord_data = J.pts->coord_data;
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
