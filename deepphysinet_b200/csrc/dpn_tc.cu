@@ -47,7 +47,10 @@ constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a
 #endif
 constexpr bool PAIR = DPN_PAIR != 0;
 constexpr int NSTAGE = PAIR ? 10 : 5;
-constexpr int CLUSTER = 2;                     // CTAs (tiles of the same sample) sharing every weight chunk through one multicast L2 read
+#ifndef DPN_CLUSTER
+#define DPN_CLUSTER 2
+#endif
+constexpr int CLUSTER = DPN_CLUSTER;                     // CTAs (tiles of the same sample) sharing every weight chunk through one multicast L2 read
 constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
