@@ -1518,13 +1518,18 @@ static int run_planes(const Job& J, cudaStream_t st) {
     set_error("the tensor-core modes derive the coordinate encoding from x,y,t; pre-encoded coord_pe is served by the fp32 kernels");
     return DPN_E_UNSUPPORTED;
   }
-  static bool attr_done = false;
   const int smem_fused = tc::smem_fused<PL>(), smem_pass2 = tc::smem_pass2<PL>(), smem_wgrad = tc::smem_wgrad<PL>();
-  if (!attr_done) {
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
-    DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
-    DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
-    attr_done = true;
+  {
+    // function attributes are per device: set them once for every device this process drives (bit d of the mask)
+    static unsigned long long attr_done_mask = 0ull;
+    int dev = 0;
+    DPN_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !((attr_done_mask >> dev) & 1ull)) {
+      DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+      DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
+      DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
+      if (dev >= 0 && dev < 64) attr_done_mask |= 1ull << dev;
+    }
   }
   Carve c = carve(reinterpret_cast<uint8_t*>(J.workspace), chunk, Kn, B, PL);
   const DpnWeights& Wt = *J.w;

@@ -173,3 +173,25 @@ def test_fp32_physics_net_forward_values_and_grad():
             continue
         err = (p.grad.double().cpu() - r).norm().item()
         assert err < 5 * TOL_FP32 * max(r.norm().item(), 1e-6 * gtot), (k, err, r.norm().item())
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("f16x3", 5e-5)])
+def test_point_sharding_adds_up(mode, tol):
+    """SURVEY 8(e) level 2: one sample's query points split over two "ranks", each call normalised by the TOTAL point count
+    (n_norm): partial loss terms and partial weight gradients add up to the unsharded result (what the all-reduce sums)."""
+    from deepphysinet_b200 import testing as T
+    from deepphysinet_b200 import parallel as P
+    W, pts = T.random_decoder_weights(B=2, N=500, seed=13, device="cuda")
+    full = T.run_library(W, pts, mode=mode, want_fields=False)
+    terms = torch.zeros_like(full["terms"])
+    grads = [torch.zeros_like(g) for g in full["grads"]]
+    for rank in range(2):
+        lo, hi = P.shard_range(500, rank, 2)
+        part = {k: v[:, lo:hi].contiguous() for k, v in pts.items()}
+        out = T.run_library(W, part, mode=mode, want_fields=False, n_norm=500)
+        terms += out["terms"]
+        for g, go in zip(grads, out["grads"]):
+            g += go
+    assert torch.allclose(terms, full["terms"], rtol=tol)
+    for n, g, gf in zip(W._fields, grads, full["grads"]):
+        assert H.rel(g.cpu(), gf.cpu()) < tol, n
