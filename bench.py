@@ -229,6 +229,9 @@ def main():
     from deepphysinet_b200 import InterfacePhysics, functional as Fn, parallel as P, _native as Nat
     from deepphysinet_b200.config import DEFAULT_LOSS_FACTOR, DEFAULT_OBS_NORM
 
+    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION: keep stdout for the one JSON line of the contract
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, local_rank, world = P.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
