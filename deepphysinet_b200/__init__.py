@@ -10,5 +10,6 @@ from .config import PhysicsConsts  # noqa: F401
 from .functional import DecoderWeights, decoder_values, pde_residual, set_default_mode  # noqa: F401
 from .interface import InterfacePhysics  # noqa: F401
 from .physics_net import PhysicsNet, VariableNet  # noqa: F401
+from .trainer import TrainStep  # noqa: F401
 
 __version__ = "0.1.0"
