@@ -363,7 +363,7 @@ def main():
         ms_e = timed(step_fn, e_steps, max(5, args.warmup))
         h2d = sum(a.numel() * a.element_size() for a in (hx, hy, ht, hf, hcd, hfield, hfh))
         e2e = {"value": pts_step / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-               "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e, "steps": e_steps, "api": api}
+               "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e, "steps_per_s": 1e3 / ms_e, "steps": e_steps, "api": api}
         if step_fn is not e2e_step:
             ms_eager = timed(e2e_step, e_steps, 3)
             e2e["eager_ms_per_step"] = ms_eager
