@@ -195,3 +195,25 @@ def test_point_sharding_adds_up(mode, tol):
     assert torch.allclose(terms, full["terms"], rtol=tol)
     for n, g, gf in zip(W._fields, grads, full["grads"]):
         assert H.rel(g.cpu(), gf.cpu()) < tol, n
+
+
+@pytest.mark.parametrize("mode", ["fp32", "f16x3", "bf16"])
+def test_relu_preactivation_exactly_zero(mode):
+    """SURVEY section 4 edge case: units whose pre-activation is EXACTLY zero (zero weight row and zero bias) - PyTorch's
+    threshold_backward gives them derivative 0, and so must the frozen masks m1 = [a1 > 0], m3 = [a3 > 0] of the kernels."""
+    from deepphysinet_b200 import functional as Fn, testing as T
+    W, pts = T.random_decoder_weights(B=1, N=200, seed=31, device="cuda")
+    W1, b1, Wa, ba = W.W1.clone(), W.b1.clone(), W.Wa.clone(), W.ba.clone()
+    W1[:, :, 5:40] = 0.0; b1[:, :, 5:40] = 0.0           # a1 == 0 for 35 hidden units of every net
+    Wa[:, 100:130] = 0.0; ba[:, 100:130] = 0.0           # a3 == 0 for 30 units
+    W = W._replace(W1=W1, b1=b1, Wa=Wa, ba=ba)
+    rep = T.compare_with_oracle(W, pts, mode=mode)
+    # f16x3: typical 3e-6; 2e-3 leaves room for one threshold tie of a NON-zero unit (test_gpu_f16x3.py docstring) - what this
+    # test pins are the exactly-zero units: their gradients below must vanish identically
+    tol = {"fp32": 1e-4, "f16x3": 2e-3, "bf16": 0.2}[mode]
+    assert rep["terms_rel"] < tol and rep["jac_rel"] < tol and rep["grad_rel_max"] < tol, rep
+    got = T.run_library(W, pts, mode=mode)
+    names = Fn.DecoderWeights._fields
+    g = dict(zip(names, got["grads"]))
+    assert g["W1"][:, :, 5:40].abs().max().item() == 0.0 and g["b1"][:, :, 5:40].abs().max().item() == 0.0
+    assert g["ba"][:, 100:130].abs().max().item() == 0.0
