@@ -39,6 +39,19 @@ for logn in (20, 22, 24):
     del W, pts, leaves
     torch.cuda.empty_cache()
 
+# N2: the on-GPU trilinear sampler + Coriolis ("feature gather"): 12 B/point in (x, y, t), 28 B/point out (coord_data, f);
+# the coarse field stack (5 x 37 x 65 x 6 floats = 289 KB per sample) stays in L2
+for Bs, Ns in ((8, 65536), (1, 1 << 24)):
+    g = torch.Generator().manual_seed(2)
+    coarse_s = (0.5 * torch.randn(Bs, 5, 37, 65, 6, generator=g)).to(dev)
+    xs = (torch.rand(Bs, Ns, generator=g) * 256 * 27000.0).to(dev)
+    ys = (torch.rand(Bs, Ns, generator=g) * 144 * 27000.0).to(dev)
+    ts = (torch.randint(0, 25, (Bs, Ns), generator=g).float() * 3600.0).to(dev)
+    ms = timed(lambda: Fn.sample_field(coarse_s, xs, ys, ts), 10)
+    print("N2 sampler  B=%d N=%d  %7.3f ms  %7.1f M points/s  %6.0f GB/s of the 40 B/point it must move (measured copy peak 6536)"
+          % (Bs, Ns, ms, Bs * Ns / ms / 1e3, 40.0 * Bs * Ns / ms / 1e6))
+    del coarse_s, xs, ys, ts
+
 obs = {k: dict(v, norm_type="mean_norm", use_norm=True) for k, v in DEFAULT_OBS_NORM.items()}
 torch.manual_seed(0)
 model = InterfacePhysics(BN.META_CFG, BN.NET_CFG, obs, None, dict(img_size=(145, 257), dx=27000, dy=27000)).to(dev)
