@@ -104,7 +104,7 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False):
+def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_gpus=1):
     """The reference's CPU path: oracle port (oracle/dpn_oracle.py, an autograd restatement of
     InterfacePhysics.place_one_batch pinned to the reference's golden vectors) + the PyTorch encoder, all host
     threads, one sample of n_points query points per step, backward included."""
@@ -141,7 +141,7 @@ def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False):
                            % (n_points, steps, warmup))
     mean = sum(times) / len(times)
     val = n_points / mean
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 0, "steps": steps, "warmup": warmup,
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "configs[1] 0.25deg grid (145x257), batch 8 x 65536 query points - bounded CPU sample per step",
@@ -219,7 +219,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         if rank == 0:
-            cpu_reference_arm(args.steps, args.warmup, args.cpu_points)
+            cpu_reference_arm(args.steps, args.warmup, args.cpu_points, n_gpus=args.gpus)
         return
 
     import torch
