@@ -91,7 +91,7 @@ def test_f16x3_chunking_is_invisible():
 
 def test_f16x3_weight_gradients_at_scale():
     """The tensor core accumulates round-toward-zero; a weight-gradient tile that collects many point tiles in one TMEM
-    accumulator drifts (65 536 points, 64 tiles per CTA: 1e-4 against an fp64 oracle).  The library flushes every 16 tiles to the
+    accumulator drifts (65 536 points, 64 tiles per CTA: 1e-4 against an fp64 oracle).  The library flushes every 32 tiles to the
     fp32 red.add sums; pinned here against the CUDA-core fp32 mode (itself 3e-6 on these tensors, tools/largeN_agreement.py)."""
     from deepphysinet_b200 import functional as Fn, testing as T
     W, pts = T.random_decoder_weights(B=1, N=32768, seed=2, device="cuda")
