@@ -101,3 +101,36 @@ def test_f16x3_weight_gradients_at_scale():
     print(rel)
     assert rel["W2"] < 3e-5 and rel["Wd"] < 3e-5, rel
     assert max(rel.values()) < 2e-4, rel
+
+
+def test_f16x3_full_size_properties():
+    """At the size the headline is quoted on (65 536 query points per sample) the oracle is too slow; check properties that do not
+    depend on it: (i) permuting the query points changes nothing but the summation order, (ii) two point-shards normalised by the
+    total count (n_norm) add up to the unsharded call, (iii) loss terms and gradients are linear in the loss factors."""
+    from dataclasses import replace
+    from deepphysinet_b200 import functional as Fn, testing as T
+    from deepphysinet_b200.config import PhysicsConsts
+    N = 65536
+    W, pts = T.random_decoder_weights(B=2, N=N, seed=6, device="cuda")
+    full = T.run_library(W, pts, mode="f16x3", want_fields=False)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    perm = torch.randperm(N, generator=g, device="cuda")
+    shuf = T.run_library(W, {k: v[:, perm].contiguous() for k, v in pts.items()}, mode="f16x3", want_fields=False)
+    assert torch.allclose(shuf["terms"], full["terms"], rtol=1e-9)             # fp64 sums
+    for n, a, b in zip(Fn.DecoderWeights._fields, shuf["grads"], full["grads"]):
+        assert H.rel(a, b) < 5e-5, (n, H.rel(a, b))
+    terms = torch.zeros_like(full["terms"])
+    grads = [torch.zeros_like(x) for x in full["grads"]]
+    for lo, hi in ((0, 40000), (40000, N)):                                     # ragged shards
+        out = T.run_library(W, {k: v[:, lo:hi].contiguous() for k, v in pts.items()}, mode="f16x3", want_fields=False, n_norm=N)
+        terms += out["terms"]
+        for acc, go in zip(grads, out["grads"]):
+            acc += go
+    assert torch.allclose(terms, full["terms"], rtol=1e-9)
+    for n, a, b in zip(Fn.DecoderWeights._fields, grads, full["grads"]):
+        assert H.rel(a, b) < 5e-5, (n, H.rel(a, b))
+    base = PhysicsConsts()
+    scaled = T.run_library(W, pts, consts=replace(base, factor=tuple(4.0 * f for f in base.factor)), mode="f16x3", want_fields=False)
+    assert torch.allclose(scaled["terms"], 4.0 * full["terms"], rtol=1e-12)
+    for n, a, b in zip(Fn.DecoderWeights._fields, scaled["grads"], full["grads"]):
+        assert H.rel(a, 4.0 * b) < 2e-6, (n, H.rel(a, 4.0 * b))                   # power-of-two factor: exact up to the red.add order
