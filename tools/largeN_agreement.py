@@ -26,6 +26,9 @@ ref_g = [l.grad for l in leaves]
 ref_terms = torch.stack([a.detach() for a in terms])
 del tot, terms
 torch.cuda.empty_cache()
+if os.environ.get("DPN_CHUNK"):                     # experiment: smaller internal passes = more local Z-side scales in f16x3
+    orig = Fn._shape
+    Fn._shape = lambda *a, **kw: orig(*a, **{**kw, "chunk": int(os.environ["DPN_CHUNK"])})
 for mode in modes:
     got = T.run_library(W, pts, mode=mode, want_fields=True)
     rel = {n: T._rel(g, r) for n, g, r in zip(names, got["grads"], ref_g)}
