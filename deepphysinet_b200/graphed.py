@@ -20,6 +20,10 @@ class GraphedPlaceOneBatch:
                 raise ValueError("GraphedPlaceOneBatch replays host->device copies: inputs must be pinned host tensors")
         self.criterion, self.loss_factor, self.rank = criterion, loss_factor, rank
         params = [p for p in model.physics_net.parameters() if p.requires_grad]
+        # warm-up and capture run on side streams on purpose; the AccumulateGrad nodes of the warm-up are dropped with zero_grad below
+        quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if quiet is not None:
+            quiet(False)
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):                      # warm-up on a side stream (allocator, workspace, func attributes)
