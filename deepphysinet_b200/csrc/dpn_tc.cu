@@ -46,7 +46,14 @@ constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a
 #define DPN_PAIR 0
 #endif
 constexpr bool PAIR = DPN_PAIR != 0;
-constexpr int NSTAGE = PAIR ? 10 : 5;
+#ifndef DPN_REUSE_A
+#define DPN_REUSE_A 1
+#endif
+constexpr bool REUSE_A = DPN_REUSE_A != 0;               // split modes: consecutive MMAs on the same A tile share one shared-memory fetch
+#ifndef DPN_NSTAGE
+#define DPN_NSTAGE (DPN_PAIR ? 10 : 5)
+#endif
+constexpr int NSTAGE = DPN_NSTAGE;                       // ring depth (>= 4: the producer streams four chunks ahead of an activation tile)
 #ifndef DPN_CLUSTER
 #define DPN_CLUSTER 2
 #endif
@@ -230,29 +237,29 @@ __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long
   acc += clock64() - t0;
 }
 
-// Producer side of the weight ring: one elected thread.
+// Producer side of the weight ring.  The WHOLE warp runs the loop (uniform control flow, see dpn_umma.cuh:elect_one); one elected
+// lane issues the copies.
 template <int PL>
 struct Producer {
-  Pipe* pp; uint8_t* ring; uint32_t rank; uint32_t n = 0;
+  Pipe* pp; uint8_t* ring; uint32_t rank; uint32_t s = 0, ph = 0;
   uint64_t pol = l2_policy_evict_last();       // weight images: re-read by every tile of the sample, keep them in L2
   __device__ __forceinline__ void put(const uint8_t* src, uint32_t bytes) {
-    const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
-    if (PAIR) {                                        // my half of the rows of this chunk (the image stores the halves back to back)
-      mbar_wait(&pp->empty[s], ph ^ 1);              // the pair MMA that read the previous occupant has completed
-      mbar_arrive_expect_tx(&pp->full[s], bytes / 2);
-      bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src + rank * (bytes / 2), bytes / 2, &pp->full[s], pol);
-      ++n;
-      return;
+    mbar_wait(&pp->empty[s], ph ^ 1);                // every consumer (PAIR: the pair MMA; else every CTA of the cluster) is done with the previous occupant
+    if (elect_one()) {
+      if (PAIR) {                                      // my half of the rows of this chunk (the image stores the halves back to back)
+        mbar_arrive_expect_tx(&pp->full[s], bytes / 2);
+        bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src + rank * (bytes / 2), bytes / 2, &pp->full[s], pol);
+      } else {
+        mbar_arrive_expect_tx(&pp->full[s], bytes);    // my copy of the chunk: my slice + the slices my peers multicast to me
+        if (CLUSTER == 1) {
+          bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src, bytes, &pp->full[s], pol);
+        } else {
+          const uint32_t slice = bytes / CLUSTER;
+          bulk_g2s_mc_hint(ring + s * Geo<PL>::STAGE + rank * slice, src + rank * slice, slice, &pp->full[s], (uint16_t)((1u << CLUSTER) - 1), pol);
+        }
+      }
     }
-    mbar_wait(&pp->empty[s], ph ^ 1);                // every CTA of the cluster has consumed the previous occupant
-    mbar_arrive_expect_tx(&pp->full[s], bytes);      // my copy of the chunk: my slice + the slices my peers multicast to me
-    if (CLUSTER == 1) {
-      bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src, bytes, &pp->full[s], pol);
-    } else {
-      const uint32_t slice = bytes / CLUSTER;
-      bulk_g2s_mc_hint(ring + s * Geo<PL>::STAGE + rank * slice, src + rank * slice, slice, &pp->full[s], (uint16_t)((1u << CLUSTER) - 1), pol);
-    }
-    ++n;
+    if (++s == NSTAGE) { s = 0; ph ^= 1; }
   }
   // chunks [first, last) of a weight image whose K = 16 chunks are `bytes` per plane
   __device__ __forceinline__ void stream(const uint8_t* img, int first, int last, uint32_t bytes) {
@@ -260,64 +267,72 @@ struct Producer {
   }
 };
 
-// MMA side: one elected thread per CTA.  A = the activation buffer (K-major, 128 rows), B = ring stages (K-major).
+// MMA side: the whole warp runs the loop, one elected lane issues.  A = the activation buffer (K-major, 128 rows), B = ring stages
+// (K-major).  Descriptors are built once per GEMM; a chunk only adds its byte offset (>> 4) to the 14-bit address field.
 // PAIR: the leader CTA issues M = 256 MMAs for both tiles once BOTH CTAs' operands are in place; the peer CTA runs the same
 // sequence but, instead of issuing, forwards each of its local completions (weight stage landed, epilogue done, A tile landed)
 // to the leader's mirror barrier with a remote arrive.  Completions come back to both CTAs through multicast commits.
 template <int PL, bool F16 = false>
 struct Issuer {
-  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t rank;
-  uint32_t n = 0; long long t_full = 0;
+  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t rank; bool timed;
+  uint32_t s = 0, ph = 0; long long t_full = 0;
   __device__ __forceinline__ bool leader() const { return !PAIR || rank == 0; }
+  __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, long long& t) {
+    if (timed) mbar_wait_t(bar, parity, t); else mbar_wait(bar, parity);
+  }
   __device__ __forceinline__ void sync_local(uint64_t* local, uint64_t* mirror, uint32_t parity, long long& t) {
-    mbar_wait_t(local, parity, t);
+    wait(local, parity, t);
     if (PAIR) {
       if (rank == 0) { const long long t0 = clock64(); mbar_wait_cluster(mirror, parity); t += clock64() - t0; }
-      else mbar_arrive_remote(mirror, 0);
+      else if (elect_one()) mbar_arrive_remote(mirror, 0);
     }
     tc_fence_after();
   }
   __device__ __forceinline__ void wait_epi(uint32_t& ae, long long& t) {      // PAIR: both CTAs' epilogue warps arrive on the leader's barrier
-    if (leader()) { mbar_wait_t(&pp->a_epi, ae & 1, t); tc_fence_after(); }
+    if (leader()) { wait(&pp->a_epi, ae & 1, t); tc_fence_after(); }
     ++ae;
   }
   __device__ __forceinline__ void wait_bulk(uint32_t& ab, long long& t) { sync_local(&pp->a_bulk, &pp->peer_bulk, ab & 1, t); ++ab; }
   __device__ __forceinline__ void commit(uint64_t* bar) {
     if (!leader()) return;
-    if (PAIR) mma_commit_pair(bar); else mma_commit(bar);
+    if (elect_one()) { if (PAIR) mma_commit_pair(bar); else mma_commit(bar); }
   }
   __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate, uint32_t col = 0) {   // accumulator = TMEM columns [col, col + Nn)
     const uint32_t tmem = this->tmem + col;
     const int Nb = PAIR ? Nn / 2 : Nn;                                  // rows of B staged in this CTA
     const uint32_t idesc = idesc_16(F16, Nn, 0, 0, PAIR ? 256 : 128);
+    const uint64_t a_base = smem_desc(act_addr, CORE_STRIDE, 128);
+    const uint64_t b_base = smem_desc(ring_addr, Nb * 16, 128);
+    const uint32_t b_lo = (uint32_t)(Nb * 32) >> 4;                     // lo plane of a stage / of the activation tile, in descriptor units
+    constexpr uint32_t a_lo = BLOB_H >> 4, a_step = (2 * CORE_STRIDE) >> 4, b_step = Geo<PL>::STAGE >> 4;
     for (int c = 0; c < nchunks; ++c) {
-      const uint32_t s = n % NSTAGE, ph = (n / NSTAGE) & 1;
       sync_local(&pp->full[s], &pp->peer_full[s], ph, t_full);
-      ++n;
-      if (!leader()) continue;
-      const uint32_t a0 = act_addr + (uint32_t)(c * 2) * CORE_STRIDE, b0 = ring_addr + s * Geo<PL>::STAGE;
-      const uint64_t ad = smem_desc(a0, CORE_STRIDE, 128);
-      const uint64_t bd = smem_desc(b0, Nb * 16, 128);
-      const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
-      if (PAIR) {
-        if (PL == 2) {                                 // small terms first: lo*hi + hi*lo + hi*hi into one accumulator
-          mma_pair(tmem, smem_desc(a0 + BLOB_H, CORE_STRIDE, 128), bd, idesc, first);
-          mma_pair(tmem, ad, smem_desc(b0 + Nb * 32, Nb * 16, 128), idesc, 1u);
-          mma_pair(tmem, ad, bd, idesc, 1u);
-        } else {
-          mma_pair(tmem, ad, bd, idesc, first);
+      if (leader()) {
+        const uint64_t ad = a_base + (uint32_t)c * a_step, bd = b_base + s * b_step;
+        const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
+        if (elect_one()) {
+          if (PAIR) {
+            if (PL == 2) {                                 // small terms first: lo*hi + hi*lo + hi*hi into one accumulator
+              mma_pair(tmem, ad + a_lo, bd, idesc, first);
+              mma_pair(tmem, ad, bd + b_lo, idesc, 1u);
+              mma_pair(tmem, ad, bd, idesc, 1u);
+            } else {
+              mma_pair(tmem, ad, bd, idesc, first);
+            }
+            mma_commit_pair(&pp->empty[s]);
+          } else {
+            if (PL == 2) {                                 // A_hi is fetched once for its two MMAs (collector buffer)
+              mma_bf16(tmem, ad + a_lo, bd, idesc, first);
+              mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bd + b_lo, idesc, 1u);
+              mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem, ad, bd, idesc, 1u);
+            } else {
+              mma_bf16(tmem, ad, bd, idesc, first);
+            }
+            if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
+          }
         }
-        mma_commit_pair(&pp->empty[s]);
-      } else {
-        if (PL == 2) {
-          mma_bf16(tmem, smem_desc(a0 + BLOB_H, CORE_STRIDE, 128), bd, idesc, first);
-          mma_bf16(tmem, ad, smem_desc(b0 + Nb * 32, Nb * 16, 128), idesc, 1u);
-          mma_bf16(tmem, ad, bd, idesc, 1u);
-        } else {
-          mma_bf16(tmem, ad, bd, idesc, first);
-        }
-        if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
       }
+      if (++s == NSTAGE) { s = 0; ph ^= 1; }
     }
   }
 };
@@ -420,22 +435,25 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   uint8_t* ring = smem + Geo<PL>::ACT;
   float* svec = reinterpret_cast<float*>(smem + Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE);
   float* rowsum = svec + NVEC * H;                                // [TP][4]: o partial, dz[3]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform by construction: the role branches below stay uniform
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;                       // global tile index
   pipe_init<PL>(&pipe, warp, tid);
   const uint32_t tmem = pipe.tmem_base;
 
-  if (warp == Geo<PL>::W_PROD && lane == 0) {
-    // ---------------- producer ----------------
+  if (warp == Geo<PL>::W_PROD) {
+    // ---------------- producer (whole warp, one elected lane issues) ----------------
     Producer<PL> pr{&pipe, ring, cluster_ctarank()};
     uint32_t af = 0, sd = 0;
     const uint8_t* pe_src = w.pe_blob + g * Geo<PL>::BC;
     const uint8_t* pe6_src = w.pe6_blob + g * Geo<PL>::BC;
     auto load_a_tile = [&](const uint8_t* src) {                  // [128 x 192] tile, plane p -> act + p * BLOB_H
-      mbar_arrive_expect_tx(&pipe.a_bulk, PL * BLOB_C);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&pipe.a_bulk, PL * BLOB_C);
 #pragma unroll
-      for (int p = 0; p < PL; ++p) bulk_g2s_hint(act + p * BLOB_H, src + p * BLOB_C, BLOB_C, &pipe.a_bulk, pr.pol);
+        for (int p = 0; p < PL; ++p) bulk_g2s_hint(act + p * BLOB_H, src + p * BLOB_C, BLOB_C, &pipe.a_bulk, pr.pol);
+      }
     };
     for (int k = 0; k < w.Kn; ++k) {
       const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
@@ -463,9 +481,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         if (sweep > 1) pr.stream(iW1T, 0, 16, 6144);
       }
     }
-  } else if (warp == Geo<PL>::W_MMA && lane == 0) {
-    // ---------------- MMA issuer ----------------
-    Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank()};
+  } else if (warp == Geo<PL>::W_MMA) {
+    // ---------------- MMA issuer (whole warp, one elected lane issues) ----------------
+    Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank(), w.phase_dbg != nullptr};
     uint32_t ab = 0, ae = 0;
     long long t_epi = 0, t_bulk = 0;
     const long long t_begin = clock64();
@@ -496,7 +514,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
       }
       is.commit(&pipe.act_free);                                   // the activation buffer may take the next PE tile
     }
-    if (w.phase_dbg) {
+    if (w.phase_dbg && lane == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 0, (unsigned long long)(clock64() - t_begin));
       atomicAdd((unsigned long long*)w.phase_dbg + 1, (unsigned long long)is.t_full);
       atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)t_epi);
@@ -793,13 +811,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   uint8_t* act = smem;
   uint8_t* ring = smem + Geo<PL>::ACT;
   float* csum = reinterpret_cast<float*>(smem + Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE);   // [3][H] + sdo
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform by construction: the role branches below stay uniform
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;
   pipe_init<PL>(&pipe, warp, tid);
   const uint32_t tmem = pipe.tmem_base;
 
-  if (warp == Geo<PL>::W_PROD && lane == 0) {
+  if (warp == Geo<PL>::W_PROD) {
     if (tangent) {
       Producer<PL> pr{&pipe, ring, cluster_ctarank()};
       // (measured and dropped: cp.async.bulk.prefetch.L2 of this tile's h1 / c / g one net ahead makes pass 2 13 % SLOWER -
@@ -813,9 +832,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         else pr.stream(sta + PL * IMG_HC, 0, 16, STAGE_BYTES);   // Wa
       }
     }
-  } else if (warp == Geo<PL>::W_MMA && lane == 0) {
+  } else if (warp == Geo<PL>::W_MMA) {
     if (tangent) {
-      Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank()};
+      Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank(), w.phase_dbg != nullptr};
       uint32_t ae = 0;
       long long t_epi = 0;
       const long long t_begin = clock64();
@@ -832,7 +851,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
           is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G9
         }
       }
-      if (w.phase_dbg) {
+      if (w.phase_dbg && lane == 0) {
         atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
         atomicAdd((unsigned long long*)w.phase_dbg + 9, (unsigned long long)is.t_full);
         atomicAdd((unsigned long long*)w.phase_dbg + 10, (unsigned long long)t_epi);
@@ -1056,7 +1075,8 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
   uint8_t* sJ = smem;                          // PL x 32 KB: 128 points x 128 out (half), plane p at p * 32 KB
   uint8_t* sZ = smem + PL * (BLOB_H / 2);      // PL x up to 64 KB, plane p at p * zbytes
   uint8_t* sX = smem + PL * (BLOB_H / 2 + BLOB_H);   // 4 KB seed tile
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform: the loader / issuer warps run with all lanes, one elected lane issues
   int item = blockIdx.x;
   const int split = item % w.splits; item /= w.splits;
   const int mh = item & 1; item >>= 1;
@@ -1077,7 +1097,7 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
   tc_fence_after();
   const uint32_t tmem = tmem_s;
   if (t1 > t0) {
-    if (warp == 4 && lane == 0) {
+    if (warp == 4) {
       for (int t = t0; t < t1; ++t) {
         const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
         const uint8_t* zsrc = layer == 0 ? nt + (size_t)NBLOB_H * Geo<PL>::BH
@@ -1085,42 +1105,57 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
                             : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * Geo<PL>::BH;
         const uint32_t i = t - t0;
         mbar_wait(&empty, (i & 1) ^ 1);
-        mbar_arrive_expect_tx(&full, PL * (BLOB_H / 2 + zbytes) + (aux ? AUX_BYTES : 0));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full, PL * (BLOB_H / 2 + zbytes) + (aux ? AUX_BYTES : 0));
 #pragma unroll
-        for (int p = 0; p < PL; ++p)
-          bulk_g2s(sJ + p * (BLOB_H / 2), nt + (size_t)jsel * Geo<PL>::BH + (size_t)p * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
-        bulk_g2s(sZ, zsrc, PL * zbytes, &full);                        // the planes of a tile are contiguous
-        if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC, AUX_BYTES, &full);
+          for (int p = 0; p < PL; ++p)
+            bulk_g2s(sJ + p * (BLOB_H / 2), nt + (size_t)jsel * Geo<PL>::BH + (size_t)p * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
+          bulk_g2s(sZ, zsrc, PL * zbytes, &full);                        // the planes of a tile are contiguous
+          if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC, AUX_BYTES, &full);
+        }
       }
-    } else if (warp == 5 && lane == 0) {
+    } else if (warp == 5) {
       const uint32_t idesc = idesc_16(F16, Nn, 1, 1), idesc_x = idesc_16(F16, 16, 1, 1);
+      // descriptors once; a K = 16-point step adds 256 bytes (>> 4) to the address field
+      const uint64_t a_hi = smem_desc(smem_u32(sJ), 128, CORE_STRIDE), b_hi = smem_desc(smem_u32(sZ), 128, CORE_STRIDE);
+      const uint64_t x_d = smem_desc(smem_u32(sX), 128, CORE_STRIDE);
+      const uint32_t a_lo = (BLOB_H / 2) >> 4, b_lo = zbytes >> 4;
       for (int t = t0; t < t1; ++t) {
         const uint32_t i = t - t0;
         mbar_wait(&full, i & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                              // 16 points per MMA
-          const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-          const uint64_t ad = smem_desc(smem_u32(sJ) + ks * 256, 128, CORE_STRIDE);
-          const uint64_t bd = smem_desc(smem_u32(sZ) + ks * 256, 128, CORE_STRIDE);
-          if (PL == 2) {
-            const uint64_t al = smem_desc(smem_u32(sJ) + BLOB_H / 2 + ks * 256, 128, CORE_STRIDE);
-            const uint64_t bl = smem_desc(smem_u32(sZ) + zbytes + ks * 256, 128, CORE_STRIDE);
-            mma_bf16(tmem, al, bd, idesc, first);
-            mma_bf16(tmem, ad, bl, idesc, 1u);
-            mma_bf16(tmem, ad, bd, idesc, 1u);
-          } else {
-            mma_bf16(tmem, ad, bd, idesc, first);
+          for (int ks = 0; ks < 8; ++ks) {                              // 16 points per MMA
+            const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t ad = a_hi + ks * 16, bd = b_hi + ks * 16;
+            const uint64_t xd = x_d + ks * 16;
+            if (PL == 2 && REUSE_A) {                      // every J plane is fetched once per step for all MMAs that read it
+              if (aux) {
+                mma_f16_c<A_FILL>(tmem, ad + a_lo, bd, idesc, first);
+                mma_f16_c<A_LAST>(tmem + C, ad + a_lo, xd, idesc_x, first);
+                mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
+                mma_f16_c<A_USE>(tmem, ad, bd, idesc, 1u);
+                mma_f16_c<A_LAST>(tmem + C, ad, xd, idesc_x, 1u);
+              } else {
+                mma_bf16(tmem, ad + a_lo, bd, idesc, first);
+                mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
+                mma_f16_c<A_LAST>(tmem, ad, bd, idesc, 1u);
+              }
+            } else if (PL == 2) {
+              mma_bf16(tmem, ad + a_lo, bd, idesc, first);
+              mma_bf16(tmem, ad, bd + b_lo, idesc, 1u);
+              mma_bf16(tmem, ad, bd, idesc, 1u);
+              if (aux) { mma_bf16(tmem + C, ad, xd, idesc_x, first); mma_bf16(tmem + C, ad + a_lo, xd, idesc_x, 1u); }
+            } else {
+              if (aux) { mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bd, idesc, first); mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem + C, ad, xd, idesc_x, first); }
+              else mma_bf16(tmem, ad, bd, idesc, first);
+            }
           }
-          if (aux) {
-            const uint64_t xd = smem_desc(smem_u32(sX) + ks * 256, 128, CORE_STRIDE);
-            mma_bf16(tmem + C, ad, xd, idesc_x, first);
-            if (PL == 2) mma_bf16(tmem + C, smem_desc(smem_u32(sJ) + BLOB_H / 2 + ks * 256, 128, CORE_STRIDE), xd, idesc_x, 1u);
-          }
+          mma_commit(&empty);
         }
-        mma_commit(&empty);
       }
-      mma_commit(&acc_ready);
+      if (elect_one()) mma_commit(&acc_ready);
     } else if (warp < 4) {
       mbar_wait(&acc_ready, 0);
       tc_fence_after();

@@ -49,6 +49,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// One lane of a CONVERGED warp (always the same one for the full mask).  The producer and MMA-issuer warps run their loops with all
+// 32 lanes - warp-uniform control flow lets the compiler keep barrier addresses, descriptors and counters in uniform registers -
+// and only the instructions with a side effect (bulk copy, tcgen05.mma / commit, mbarrier arrive) sit under elect_one().  Issued
+// from a single-lane branch instead, every UTCHMMA / UBLKCP is wrapped in an ELECT / BRA.U.ANY loop plus R2UR moves: ~75 SASS
+// instructions per three-MMA chunk, ≈150 cycles per MMA where the tensor pipe needs 128 (tools/umma_sw_probe.cu: 128.6).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ---- bulk async copy global -> shared (1-D, no tensor map), completes on an mbarrier --------------
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
@@ -236,6 +250,26 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with an explicit use of the A collector buffer (SASS: UTCHMMA gdesc[..].A_KEEP / .A_REUSE): consecutive MMAs that share
+// their A tile fetch it from shared memory ONCE.  A_FILL: read A from smem and keep it; A_USE: take it from the collector and keep
+// it; A_LAST: take it from the collector, then drop it.  A split contraction issues A_lo B_hi | A_hi B_lo (fill) | A_hi B_hi (last):
+// 8 instead of 12 KB of A reads per K = 16 chunk - with the 24 KB of B reads and the 16 KB the weight ring writes per chunk that is
+// the difference between 52 and 48 KB against the 128 B/clk x 384 cycles = 48 KB of shared-memory bandwidth three MMAs leave.
+enum { A_DISCARD = 0, A_FILL = 1, A_USE = 2, A_LAST = 3 };
+template <int MODE>
+__device__ __forceinline__ void mma_f16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if (MODE == A_FILL)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if (MODE == A_USE)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::use [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else if (MODE == A_LAST)
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
 }
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
