@@ -39,7 +39,7 @@ constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of
 constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a [256 x K] weight image
 // CTA pair (cta_group::2, build with -DDPN_PAIR=1): the two CTAs of a cluster run ONE M = 256 MMA; each CTA stages only ITS half
 // of every weight chunk (N/2 rows), which halves the shared-memory ingress per SM and doubles the ring depth.  Parity-green in all
-// modes and the pair MMA itself runs at 128 cycles per TWO tiles (tools/umma2_probe.cu; 152 per tile for cta_group::1), but the
+// modes and the pair MMA itself runs at 128 cycles per TWO tiles (tools/umma2_probe.cu; 128.6 per tile for cta_group::1, tools/umma_sw_probe.cu), but the
 // leader has to wait for the slower of two epilogues every round: measured f16x3 25.0 vs 24.3 ms, bf16 11.4 vs 10.9 ms per call.
 // Default 0 = cta_group::1, full chunks multicast to both CTAs.  The pair path pays off only with two tiles in flight per CTA.
 #ifndef DPN_PAIR

@@ -1,5 +1,8 @@
 // Hardware probe: does a swizzled K-major operand layout feed tcgen05.mma (SS form) faster than the no-swizzle core-matrix
-// layout dpn_tc.cu uses (152 cycles per M=128 N=256 K=16 MMA, tools/umma_probe.cu mode 5)?
+// layout dpn_tc.cu uses?  Answer (profiles/r01g_umma_sw_probe.txt): the no-swizzle layout already runs at 128.6 cycles per
+// M=128 N=256 K=16 MMA = the tensor-pipe floor when the issue loop is lean (the 152.4 of tools/umma_probe.cu mode 5 was that
+// probe's branchy single-lane loop).  The swizzled modes here compute correct results but their timings are issue-bound by the
+// runtime divisions in sw_desc() - do not read them as hardware rates.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc tools/umma_sw_probe.cu -o tools/bin/umma_sw_probe
 //   ./umma_sw_probe <swizzle bytes: 0 | 32 | 64 | 128> <reps>
 // Layout of a [rows x 64] 16-bit tile with swizzle width Wb: K is cut into slabs of Wb/2 elements; inside a slab row r starts at
