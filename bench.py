@@ -151,7 +151,7 @@ def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_g
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if emit:
-        print(json.dumps(line))
+        _emit(line)
     return line
 
 
@@ -197,6 +197,25 @@ def eager_gpu_arm(dev, n_points):
     return out
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line (the contract).  Libraries write there too - NCCL prints its version banner on
+    stdout during the first collective whatever NCCL_DEBUG says - so file descriptor 1 is pointed at stderr for the whole run and
+    the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,6 +233,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time the eager place_one_batch call instead of its CUDA-graph capture")
     ap.add_argument("--e2e-breakdown", action="store_true", help="print per-phase times of the e2e step to stderr")
     args = ap.parse_args()
+    _claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -229,9 +249,6 @@ def main():
     from deepphysinet_b200 import InterfacePhysics, functional as Fn, parallel as P, _native as Nat
     from deepphysinet_b200.config import DEFAULT_LOSS_FACTOR, DEFAULT_OBS_NORM
 
-    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION: keep stdout for the one JSON line of the contract
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
     rank, local_rank, world = P.init_from_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -433,7 +450,7 @@ def main():
                                  (Nat.workspace(Fn._shape(B, Np, 6, args.mode), dev)[1] / 2 ** 30)},
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "clocks": clocks,
                 "gpu_launches": int(holder.get("launches", 0)) * args.steps, "modes": modes}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
