@@ -49,7 +49,11 @@ constexpr bool PAIR = DPN_PAIR != 0;
 #ifndef DPN_REUSE_A
 #define DPN_REUSE_A 1
 #endif
-constexpr bool REUSE_A = DPN_REUSE_A != 0;               // split modes: consecutive MMAs on the same A tile share one shared-memory fetch
+constexpr bool REUSE_A = DPN_REUSE_A != 0;
+#ifndef DPN_DEFAULT_TS
+#define DPN_DEFAULT_TS 1
+#endif
+constexpr bool DEFAULT_TS = DPN_DEFAULT_TS != 0;         // split modes: pass 1 keeps its activation tile in tensor memory (pass1_ts_kernel)               // split modes: consecutive MMAs on the same A tile share one shared-memory fetch
 #ifndef DPN_NSTAGE
 #define DPN_NSTAGE (DPN_PAIR ? 10 : 5)
 #endif
@@ -784,6 +788,351 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
   __syncthreads();
   if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
   if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, Geo<PL>::TMEM_COLS); else tmem_dealloc(tmem, Geo<PL>::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pass 1 with the activation tile in TENSOR MEMORY (split modes; opt-in: DPN_TS=1).
+// The A operand of every GEMM but G1 / G2b is written by the epilogues with tcgen05.st and read by the TS form of tcgen05.mma; the
+// PE / PE6 tiles of G1 / G2b travel through the ring as K = 16 slices next to their weight chunks; tiles kept for the backward pass
+// leave with streaming 16-byte stores from registers.  No activation buffer in shared memory -> the ring holds 9 stages of 24 KB
+// instead of 5 of 16 KB (the weight stream paces today's kernel, section 9).  TMEM is full (accumulator [0,256) | A_hi [256,384) |
+// A_lo [384,512); K-chunk c of a plane = columns base + 8c .. 8c+7), so there is no FOLD: q = y W2 runs as its own round.
+// ------------------------------------------------------------------------------------------------
+namespace ts {
+constexpr int NS = 9;
+constexpr int W_BYTES = 2 * STAGE_BYTES;        // weight chunk [256 x 16] : hi 8 KB | lo 8 KB   ([192 x 16]: 6 KB | 6 KB)
+constexpr int A_PLANE = 2 * CORE_STRIDE;        // A slice [128 x 16] of one plane: 4 KB
+constexpr int STAGE = W_BYTES + 2 * A_PLANE;    // 24 KB
+constexpr uint32_t COL_AH = 256, COL_AL = 384;
+constexpr int SMEM = NS * STAGE + NVEC * H * 4 + TP * 4 * 4;
+struct PipeTS {
+  uint64_t full[NS], empty[NS], a_epi, acc_ready;
+  uint32_t tmem_base;
+};
+}  // namespace ts
+
+template <bool F16>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREADS, 1) pass1_ts_kernel(const Work w, const int sweep) {
+  constexpr int PL = 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ ts::PipeTS pipe;
+  uint8_t* ring = smem;
+  float* svec = reinterpret_cast<float*>(smem + ts::NS * ts::STAGE);
+  float* rowsum = svec + NVEC * H;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
+  const size_t g = blockIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < ts::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
+    mbar_init(&pipe.a_epi, Geo<PL>::ET);
+    mbar_init(&pipe.acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == Geo<PL>::W_MMA) tmem_alloc(&pipe.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (CLUSTER > 1) cluster_sync_all();
+  const uint32_t tmem = pipe.tmem_base;
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1);
+
+  if (warp == Geo<PL>::W_PROD) {
+    // ---------------- producer: weight chunks (multicast slices) + this tile's PE slices ----------------
+    uint32_t s = 0, ph = 0;
+    const uint64_t pol = l2_policy_evict_last();
+    auto put = [&](const uint8_t* wsrc, const uint32_t wbytes, const uint8_t* asrc) {
+      mbar_wait(&pipe.empty[s], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* stg = ring + s * ts::STAGE;
+        mbar_arrive_expect_tx(&pipe.full[s], wbytes + (asrc ? 2 * ts::A_PLANE : 0));
+        if (CLUSTER == 1) {
+          bulk_g2s_hint(stg, wsrc, wbytes, &pipe.full[s], pol);
+        } else {
+          const uint32_t slice = wbytes / CLUSTER;
+          bulk_g2s_mc_hint(stg + rank * slice, wsrc + rank * slice, slice, &pipe.full[s], MC_MASK, pol);
+        }
+        if (asrc) {
+#pragma unroll
+          for (int p = 0; p < PL; ++p) bulk_g2s_hint(stg + ts::W_BYTES + p * ts::A_PLANE, asrc + p * BLOB_C, ts::A_PLANE, &pipe.full[s], pol);
+        }
+      }
+      if (++s == ts::NS) { s = 0; ph ^= 1; }
+    };
+    const uint8_t* pe_src = w.pe_blob + g * Geo<PL>::BC;
+    const uint8_t* pe6_src = w.pe6_blob + g * Geo<PL>::BC;
+    for (int k = 0; k < w.Kn; ++k) {
+      const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
+      const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
+      const uint8_t *iW1 = gen, *iW1T = gen + PL * IMG_HC, *iW2 = gen + PL * 2 * IMG_HC, *iW2T = gen + PL * (2 * IMG_HC + IMG_HH);
+      const uint8_t *iWd = sta, *iWa = sta + PL * IMG_HC, *iWaT = sta + PL * (IMG_HC + IMG_HH);
+      for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe_src + (size_t)c * ts::A_PLANE);
+      for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
+      for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE);
+      for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
+      if (sweep) {
+        for (int c = 0; c < 16; ++c) put(iWaT + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
+        for (int c = 0; c < 16; ++c) put(iW2T + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
+        if (sweep > 1)
+          for (int c = 0; c < 16; ++c) put(iW1T + (size_t)c * (PL * 6144), PL * 6144, nullptr);
+      }
+    }
+  } else if (warp == Geo<PL>::W_MMA) {
+    // ---------------- MMA issuer ----------------
+    uint32_t s = 0, ph = 0, ae = 0;
+    const uint32_t ring_addr = smem_u32(ring);
+    const uint64_t a_base = smem_desc(ring_addr + ts::W_BYTES, CORE_STRIDE, 128);
+    auto gemm = [&](const int nchunks, const int Nn, const bool a_in_tmem, const bool accumulate) {
+      const uint32_t idesc = idesc_16(F16, Nn, 0, 0, 128);
+      const uint64_t b_base = smem_desc(ring_addr, Nn * 16, 128);
+      const uint32_t b_lo = (uint32_t)(Nn * 32) >> 4;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&pipe.full[s], ph);
+        tc_fence_after();
+        const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
+        const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
+        if (elect_one()) {
+          if (a_in_tmem) {                               // lo*hi + hi*lo + hi*hi, A planes from tensor memory
+            mma_ts(tmem, tmem + ts::COL_AL + 8 * c, bd, idesc, first);
+            mma_ts(tmem, tmem + ts::COL_AH + 8 * c, bl, idesc, 1u);
+            mma_ts(tmem, tmem + ts::COL_AH + 8 * c, bd, idesc, 1u);
+          } else {                                       // the A slice of this chunk sits behind the weights in the same stage
+            const uint64_t ad = a_base + s * (uint32_t)(ts::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
+            mma_bf16(tmem, al, bd, idesc, first);
+            mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bl, idesc, 1u);
+            mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem, ad, bd, idesc, 1u);
+          }
+          if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
+        }
+        if (++s == ts::NS) { s = 0; ph ^= 1; }
+      }
+    };
+    auto wait_epi = [&]() { mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
+    auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready); };
+    for (int k = 0; k < w.Kn; ++k) {
+      if (k > 0) wait_epi();                                               // the last epilogue of the previous net has drained the accumulator
+      gemm(12, H, false, false); ready();                                  // G1
+      wait_epi();
+      gemm(16, H, true, false); gemm(12, H, false, true); ready();         // G2a (A = h1 in TMEM) + G2b (A = PE6 slices)
+      wait_epi();
+      gemm(16, H, true, false); ready();                                   // G3 (A = c)
+      if (sweep) {
+        wait_epi();
+        gemm(16, H, true, false); ready();                                 // G4 (A = um)
+        wait_epi();
+        gemm(16, H, true, false); ready();                                 // G5 (A = y)
+        if (sweep > 1) {
+          wait_epi();
+          gemm(16, C, true, false); ready();                               // G6 (A = qm, N = 192)
+        }
+      }
+    }
+  } else if (warp < Geo<PL>::EW) {
+    // ---------------- epilogue: thread = (point r, column half) ----------------
+    constexpr int NB = Geo<PL>::NB;
+    const int half = warp >> 2, r = (warp & 3) * 32 + lane, c0 = half * NB;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tl_addr = lane_base + half * (NB * 32);
+    const int p_local = tl * TP + r;
+    const bool valid = p_local < w.P;
+    const size_t q = (size_t)b * w.N + w.p0 + p_local;
+    const size_t row = g * TP + r;
+    const float* pet = w.pet + g * (size_t)(C * TP) + r;
+    const uint64_t pol_keep = l2_policy_evict_last();
+    uint32_t ar = 0;
+    // 32 columns of this row: split into the two planes once, then -> workspace tile (if any) and / or the next A operand in TMEM
+    auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        uint4 pq[PL];
+        split8<PL, F16>(v + qd * 8, pq);
+        if (blob) {
+          const uint32_t off = piece_off(r, cg * 4 + qd);
+          __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
+          __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
+        }
+        hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
+        lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
+      }
+      if (to_a) {
+        tmem_st16(lane_base + ts::COL_AH + cg * 16, hi);
+        tmem_st16(lane_base + ts::COL_AL + cg * 16, lo);
+      }
+    };
+    auto done = [&]() { tmem_st_wait(); tc_fence_before(); mbar_arrive(&pipe.a_epi); };
+    auto acc_wait = [&]() { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
+    if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
+    for (int k = 0; k < w.Kn; ++k) {
+      uint8_t* nt = net_tile<PL>(w, b, k, tl);
+      epi_bar<PL>();
+      if (tid < H) load_vectors(svec, w, b, k, tid);
+      epi_bar<PL>();
+      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f;
+      if (F16) {
+        const NetScales t = w.sc[b * w.Kn + k];
+        i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / (t.sUM * t.sWa);
+        i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
+        sH1 = t.sH1; sC = t.sC; sG = t.sG; sUM = t.sUM; sY = t.sY;
+      }
+      uint32_t m1w[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) m1w[i] = 0u;
+      // ---- epilogue 1: h1 = relu(a1 + b1) ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_B1 * H + cg * 32 + j4 * 4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = F16 ? fmaf(v[j4 * 4 + e], i1, bb[e]) : v[j4 * 4 + e] + bb[e];
+            bits |= (a > 0.f ? 1u : 0u) << (j4 * 4 + e);
+            v[j4 * 4 + e] = F16 ? fmaxf(a, 0.f) * sH1 : fmaxf(a, 0.f);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
+        emit(cg, v, sweep ? blob_h<PL>(nt, B_H1) : nullptr, true);
+      }
+      done();
+      // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
+      float os0 = 0.f, os1 = 0.f;
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cg * 32 + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float cc = F16 ? fmaf(v[j4 * 4 + e], i2, bb[e]) : v[j4 * 4 + e] + bb[e];
+            if (e & 1) os1 = fmaf(ww[e], cc, os1); else os0 = fmaf(ww[e], cc, os0);
+            v[j4 * 4 + e] = F16 ? cc * sC : cc;
+          }
+        }
+        emit(cg, v, sweep ? blob_h<PL>(nt, B_CC) : nullptr, true);
+      }
+      done();
+      // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          float g8[8];
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cg * 32 + qd * 8 + h2 * 4);
+            const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cg * 32 + qd * 8 + h2 * 4);
+            const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = qd * 8 + h2 * 4 + e;
+              const float a = F16 ? fmaf(v[j], i3, bb[e]) : v[j] + bb[e];
+              const float gg = fmaxf(a, 0.f);
+              if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
+              g8[h2 * 4 + e] = F16 ? gg * sG : gg;
+              v[j] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;          // um replaces the accumulator value in place
+            }
+          }
+          if (sweep) stg8<PL, F16>(blob_h<PL>(nt, B_GG), BLOB_H, piece_off(r, cg * 4 + qd), g8);
+        }
+        if (sweep) emit(cg, v, blob_h<PL>(nt, B_UM), true);
+      }
+      atomicAdd(rowsum + r * 4, os0 + os1);
+      done();
+      epi_bar<PL>();
+      if (half == 0) {
+        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
+        rowsum[r * 4] = 0.f;
+      }
+      if (!sweep) continue;
+      // ---- epilogue 4: y = acc + 2wo ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
+          const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = F16 ? fmaf(v[j4 * 4 + e], i4, ww[e]) * sY : v[j4 * 4 + e] + ww[e];
+        }
+        emit(cg, v, blob_h<PL>(nt, B_YT), true);
+      }
+      done();
+      // ---- epilogue 5: qm = acc * m1 ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
+        emit(cg, v, blob_h<PL>(nt, B_QM), sweep > 1);
+      }
+      done();
+      if (sweep < 2) continue;
+      // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
+      acc_wait();
+      float dz[3] = {0.f, 0.f, 0.f};
+      {
+        const uint32_t a6 = lane_base + half * 96;
+        const float bsel = half ? 1.f : 0.f;
+#pragma unroll
+        for (int ib = 0; ib < 3; ++ib) {
+          float pp[32], v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pp[j] = ldg_f32_hint(pet + (size_t)(half * 96 + DPE_PARTNER(ib * 32 + j)) * TP, pol_keep);
+          tmem_ld32(a6 + ib * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int Jl = ib * 32 + j;
+            const float bnd = bsel * w.band[16 + Jl / 6] + (1.f - bsel) * w.band[Jl / 6];
+            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * bnd * v[j], pp[j], dz[Jl % 3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, F16 ? dz[c] * i6 : dz[c]);
+      done();
+      epi_bar<PL>();
+      if (half == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (valid) w.od[(row * w.Kn + k) * 3 + c] = rowsum[r * 4 + 1 + c];
+          rowsum[r * 4 + 1 + c] = 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();
+  if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1628,7 +1977,18 @@ static int run_planes(const Job& J, cudaStream_t st) {
     const int tiles = B * T;
     encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
     DPN_LAUNCH_OK();
-    pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
+    // split modes: pass 1 with the A operand in tensor memory; DPN_TS=0 selects the shared-memory variant
+    static const bool use_ts = getenv("DPN_TS") && getenv("DPN_TS")[0] ? atoi(getenv("DPN_TS")) != 0 : DEFAULT_TS;
+    if (PL == 2 && !PAIR && use_ts) {
+      static bool ts_attr = false;
+      if (!ts_attr) {
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
+        ts_attr = true;
+      }
+      pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
+    } else {
+      pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
+    }
     DPN_LAUNCH_OK();
     if (J.kind == JOB_DEC_FWD) {
       gather_o_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.o);

@@ -224,6 +224,17 @@ __device__ __forceinline__ void tmem_for_each_block(uint32_t taddr, F&& f) {
   }
 }
 
+// 32 lanes x 16 columns: thread i of the warp writes 16 words to columns [col, col+16) of TMEM lane (lane_base + i).  Used to hand an
+// A operand to the TS form of tcgen05.mma: 32-bit column j of a plane holds elements (2j, 2j+1) of the row.  Completion: tmem_st_wait().
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start[0,14) | LBO[16,30) | SBO[32,46) | 1<<46
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -270,6 +281,15 @@ __device__ __forceinline__ void mma_f16_c(uint32_t tmem_d, uint64_t adesc, uint6
                  "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
   else
     mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+// TS form: D[tmem] (+)= A[tmem] * B[smem].  A: lane = row, K = 16 elements = 8 consecutive 32-bit columns from a_tmem (tools/umma_ts_probe.cu)
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // arrives on the mbarrier once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
