@@ -1912,6 +1912,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
       DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
       DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
       DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
+      if (PL == 2) DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
       if (dev >= 0 && dev < 64) attr_done_mask |= 1ull << dev;
     }
   }
@@ -1980,11 +1981,6 @@ static int run_planes(const Job& J, cudaStream_t st) {
     // split modes: pass 1 with the A operand in tensor memory; DPN_TS=0 selects the shared-memory variant
     static const bool use_ts = getenv("DPN_TS") && getenv("DPN_TS")[0] ? atoi(getenv("DPN_TS")) != 0 : DEFAULT_TS;
     if (PL == 2 && !PAIR && use_ts) {
-      static bool ts_attr = false;
-      if (!ts_attr) {
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
-        ts_attr = true;
-      }
       pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
     } else {
       pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
