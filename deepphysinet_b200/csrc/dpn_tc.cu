@@ -809,6 +809,8 @@ struct PipeTS {
   uint64_t full[NS], empty[NS], a_epi, acc_ready;
   uint32_t tmem_base;
 };
+static_assert(SMEM + (int)sizeof(PipeTS) + 1024 <= 227 * 1024, "pass1_ts_kernel: ring + vectors + row sums + barriers must fit one SM's 227 KB");
+static_assert(COL_AL + 128 == 512 && COL_AH + 128 == COL_AL && COL_AH == H, "TMEM map: accumulator | A_hi | A_lo fills the 512 columns");
 }  // namespace ts
 
 template <bool F16>
