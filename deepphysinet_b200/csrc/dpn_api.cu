@@ -1,6 +1,8 @@
 // extern "C" surface of libdpn_b200.so (include/dpn_b200.h): argument validation, mode dispatch.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "dpn_fp32.cuh"
 #include "dpn_tc.cuh"
 
@@ -47,13 +49,13 @@ static int check_shape(const DpnShape* s) {
 
 static int check_device() {
   // cudaGetDeviceProperties costs milliseconds per call: ask for the one attribute, once per device
-  static int major_of[64] = {0};
+  static std::atomic<int> major_of[64];                               // zero-initialised; threads (one per GPU) may race to fill an entry
   int dev = 0;
   DPN_CUDA_OK(cudaGetDevice(&dev));
-  int major = (dev >= 0 && dev < 64) ? major_of[dev] : 0;
+  int major = (dev >= 0 && dev < 64) ? major_of[dev].load(std::memory_order_relaxed) : 0;
   if (major == 0) {
     DPN_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
-    if (dev >= 0 && dev < 64) major_of[dev] = major;
+    if (dev >= 0 && dev < 64) major_of[dev].store(major, std::memory_order_relaxed);
   }
   if (major != 10) {
     set_error("libdpn_b200 is built for sm_100a only; device %d has compute capability major %d", dev, major);
@@ -63,11 +65,8 @@ static int check_device() {
 }
 
 static size_t ws_bytes(const DpnShape& s) {
-  // the CUDA-core kernels also serve the pre-encoded (coord_pe) surface in bf16 mode, so that mode needs the larger of the two
-  const size_t a = f32::workspace_bytes(f32_chunk(s), s.K, s.B);
-  if (s.mode == DPN_MODE_FP32) return a;
-  const size_t b = tc::workspace_bytes(tc_chunk(s), s.K, s.B, planes(s));
-  return a > b ? a : b;
+  if (s.mode == DPN_MODE_FP32) return f32::workspace_bytes(f32_chunk(s), s.K, s.B);
+  return tc::workspace_bytes(tc_chunk(s), s.K, s.B, planes(s));
 }
 
 static int dispatch(Job& job, void* stream) {
@@ -84,7 +83,9 @@ static int dispatch(Job& job, void* stream) {
     return DPN_E_INVALID;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool tensor = job.shape.mode != DPN_MODE_FP32 && !job.pts->coord_pe && !job.pts->ref && job.shape.K == 6;
+  // `mode` is honoured on every surface: pre-encoded coordinates (coord_pe), an explicit skip (ref) and K < 6 nets run on the
+  // tensor cores as well (tc::encode_kernel takes the caller's encoding; the epilogues take ref)
+  const bool tensor = job.shape.mode != DPN_MODE_FP32;
   job.chunk = tensor ? tc_chunk(job.shape) : f32_chunk(job.shape);
   return tensor ? tc::run(job, st) : f32::run(job, st);
 }

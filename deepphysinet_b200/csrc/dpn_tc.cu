@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "dpn_tc.cuh"
 #include "dpn_umma.cuh"
 
@@ -67,6 +69,8 @@ constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
 constexpr int GEN_IMG = 2 * IMG_HC + 4 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T, P, PT  (P = Wa W2, see FOLD below)
 constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
+constexpr int GEN_NP = 2 * IMG_HC + 2 * IMG_HH;    // per (sample, net), half-split layout for pass1_np_kernel: W1, W1T, W2, W2T
+constexpr int STA_NP = IMG_HC + 2 * IMG_HH;        // per net, half-split: Wd, Wa, WaT
 constexpr int NBLOB_H = 8, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX
 enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
 
@@ -109,12 +113,15 @@ struct Work {
   // weight images
   const uint8_t* img_gen;  // [B][Kn][GEN_IMG]
   const uint8_t* img_sta;  // [Kn][STA_IMG]
+  const uint8_t* img_gen_np;   // [B][Kn][W1 W1T W2 W2T], half-split layout (pass1_np_kernel)
+  const uint8_t* img_sta_np;   // [Kn][Wd Wa WaT],        half-split layout
   // epilogue vectors (fp32)
   const float *b1, *bsum;  // [B][Kn][H]
   const float *ba, *uvec, *wo2, *cst;   // [Kn][H], cst [Kn]
   const float* c2;         // [B][Kn][H]  2wo W2 (FOLD)
   // per-point
   const float* coord_data; // [B*N][6]
+  const float* ref;        // [B*N][Kn] residual skip, or nullptr -> coord_data[:, k]
   uint8_t* pe_blob;        // [B*T][PL][BLOB_C]
   uint8_t* pe6_blob;       // [B*T][PL][BLOB_C]
   float* pet;              // [B*T][C][TP] fp32 transposed coordinate features
@@ -122,8 +129,7 @@ struct Work {
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
   float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
   const NetScales* sc;         // [B][Kn] scaling plan (fp16 variant only)
-  long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (DPN_PHASE_DEBUG=1), summed over CTAs
-  int dbg_flags;               // timing experiments only (DPN_DEBUG_FLAGS): 1 = no blob stores, 2 = no act stores, 4 = no TMEM loads
+  long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (debug builds with DPN_PHASE_DEBUG=1), summed over CTAs
   float band[NF];
 };
 
@@ -226,6 +232,14 @@ __host__ __device__ __forceinline__ float pow2_floor(float x) {           // lar
 __device__ __forceinline__ float scale_for(float bound) { return pow2_floor(F16_TOP / fmaxf(bound, 1e-30f)); }
 // element (r, 8*kc .. 8*kc+7) of a 128-row blob
 __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)kc * CORE_STRIDE + (uint32_t)r * 16; }
+// byte offset of the 16-byte piece (row r, k-core kc) of a workspace tile of the split modes: [point half][k-core][64 rows][16 B],
+// KC k-cores per tile.  A 64-point half of a tile is contiguous, which is what lets the weight-gradient kernel double-buffer
+// half tiles (wgrad2_kernel); a warp (32 consecutive rows) still writes 512 contiguous bytes per 16-byte store.
+__device__ __forceinline__ uint32_t gp_off(const int KC, const int r, const int kc) {
+  return (uint32_t)(r >> 6) * (uint32_t)(KC * 1024) + (uint32_t)kc * 1024u + (uint32_t)(r & 63) * 16u;
+}
+template <int PL>
+__device__ __forceinline__ uint32_t blob_off(const int KC, const int r, const int kc) { return PL == 2 ? gp_off(KC, r, kc) : piece_off(r, kc); }
 
 struct Pipe {            // shared-memory barriers of the fused kernels
   uint64_t full[NSTAGE], empty[NSTAGE];
@@ -408,18 +422,13 @@ template <int PL> __device__ __forceinline__ void epi_bar() { asm volatile("bar.
 
 // NB consecutive 32-column blocks of this thread's TMEM lane: f(block, float (&v)[32])
 template <int NB, class F>
-__device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f, const bool SKIP_TMEM_DBG = false) {
+__device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f) {
   // (software-pipelined TMEM loads - dpn_umma.cuh:tmem_for_each_block - were measured again with 168 registers per thread in the
   //  one-CTA-per-SM modes: f16x3 call 24.4 -> 26.9 ms; the plain load / wait / process sequence stays)
 #pragma unroll 1
   for (int cb = 0; cb < NB; ++cb) {
     float v[32];
-    if (SKIP_TMEM_DBG) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 1.0f;
-    } else {
-      tmem_ld32(taddr + cb * 32, v);
-    }
+    tmem_ld32(taddr + cb * 32, v);
     f(cb, v);
   }
 }
@@ -592,7 +601,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         for (int qd = 0; qd < 4; ++qd) {
           sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
-      }, (w.dbg_flags & 4) != 0);
+      });
       epi_done(&pipe); t_comp += clock64() - t_mark;
       if (sweep) drain(blob_h<PL>(nt, B_H1), true);
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
@@ -617,7 +626,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         for (int qd = 0; qd < 4; ++qd) {
           sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
         }
-      }, (w.dbg_flags & 4) != 0);
+      });
       epi_done(&pipe); t_comp += clock64() - t_mark;
       if (sweep) drain(blob_h<PL>(nt, B_CC), false);
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
@@ -648,12 +657,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
             sts8<PL, F16>(act, BLOB_H, off, um);                           // and their buffer already belongs to the next PE tile
           }
         }
-      }, (w.dbg_flags & 4) != 0);
+      });
       atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
       epi_done(&pipe); t_comp += clock64() - t_mark;
       if (sweep) drain(blob_h<PL>(nt, B_UM), Geo<PL>::FOLD && sweep < 2); else epi_bar<PL>();
       if (half == 0) {
-        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
+        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + (w.ref ? __ldg(w.ref + q * w.Kn + k) : __ldg(w.coord_data + q * 6 + k));
         rowsum[r * 4] = 0.f;
       }
       if (!sweep) continue;
@@ -718,7 +727,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
           for (int qd = 0; qd < 4; ++qd) {
             sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
           }
-        }, (w.dbg_flags & 4) != 0);
+        });
         epi_done(&pipe); t_comp += clock64() - t_mark;
         drain(blob_h<PL>(nt, B_YT), sweep < 2);
         // ---- epilogue 5: qm = acc * m1 ----
@@ -737,7 +746,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
             if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
             else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
           }
-        }, (w.dbg_flags & 4) != 0);
+        });
         epi_done(&pipe); t_comp += clock64() - t_mark;
       }
       if (sweep < 2) continue;
@@ -951,7 +960,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         uint4 pq[PL];
         split8<PL, F16>(v + qd * 8, pq);
         if (blob) {
-          const uint32_t off = piece_off(r, cg * 4 + qd);
+          const uint32_t off = gp_off(32, r, cg * 4 + qd);
           __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
           __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
         }
@@ -1053,7 +1062,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
               v[j] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;          // um replaces the accumulator value in place
             }
           }
-          if (sweep) stg8<PL, F16>(blob_h<PL>(nt, B_GG), BLOB_H, piece_off(r, cg * 4 + qd), g8);
+          if (sweep) stg8<PL, F16>(blob_h<PL>(nt, B_GG), BLOB_H, gp_off(32, r, cg * 4 + qd), g8);
         }
         if (sweep) emit(cg, v, blob_h<PL>(nt, B_UM), true);
       }
@@ -1061,7 +1070,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       done();
       epi_bar<PL>();
       if (half == 0) {
-        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + __ldg(w.coord_data + q * 6 + k);
+        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + (w.ref ? __ldg(w.ref + q * w.Kn + k) : __ldg(w.coord_data + q * 6 + k));
         rowsum[r * 4] = 0.f;
       }
       if (!sweep) continue;
@@ -1136,6 +1145,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   if (CLUSTER > 1) cluster_sync_all();
   if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 512);
 }
+
+#include "dpn_tc_np.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Pass 2: the combined tangent row, the Z-side operands of the weight gradients and three column sums.
@@ -1257,8 +1268,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
           a8[1] = __uint_as_float(__float_as_uint(dv - a8[0]) & 0xFFFF0000u);
           a8[2] = (dv - a8[0]) - a8[1];
         }
-        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 0)), pack8f<F16>(a8));
-        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + piece_off(r, 1)), make_uint4(0u, 0u, 0u, 0u));
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + blob_off<PL>(2, r, 0)), pack8f<F16>(a8));
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + blob_off<PL>(2, r, 1)), make_uint4(0u, 0u, 0u, 0u));
       }
       // ---- prologue: xt -> activation buffer; zp, zd -> workspace (each half takes 4 of the 8 column groups) ----
       t_mark = clock64();
@@ -1282,14 +1293,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         }
 #pragma unroll
         for (int qd = 0; qd < 3; ++qd) {
-          const uint32_t off = piece_off(r, it * 3 + qd);
+          const uint32_t off = piece_off(r, it * 3 + qd), goff = blob_off<PL>(24, r, it * 3 + qd);
           if (tangent) sts8<PL, F16>(act, BLOB_H, off, xt + qd * 8);
-          stg8<PL, F16>(blob_zp<PL>(nt), BLOB_C, off, zp + qd * 8);
+          stg8<PL, F16>(blob_zp<PL>(nt), BLOB_C, goff, zp + qd * 8);
           float d6[8];
           unpack_planes<PL, F16>(p6[qd], d6);
 #pragma unroll
           for (int e = 0; e < 8; ++e) d6[e] *= F16 ? dv * (sZD / S_PE) : dv;
-          stg8<PL, F16>(blob_zd<PL>(nt), BLOB_C, off, d6);
+          stg8<PL, F16>(blob_zd<PL>(nt), BLOB_C, goff, d6);
         }
       }
       if (tangent) { epi_done(&pipe); t_comp += clock64() - t_mark; }
@@ -1302,7 +1313,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
-          for (int p = 0; p < PL; ++p) nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + piece_off(r, c0 * 4 + qd)));
+          for (int p = 0; p < PL; ++p) nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + blob_off<PL>(32, r, c0 * 4 + qd)));
         // FOLD: G8 and G9 were issued together; the st = 2 phase finds its accumulator (columns 256..511) already complete
         if (tangent && !(Geo<PL>::FOLD && st == 2)) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
         t_mark = clock64();
@@ -1318,7 +1329,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
             for (int qd = 0; qd < 4; ++qd)
 #pragma unroll
               for (int p = 0; p < PL; ++p)
-                nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + piece_off(r, (cg + 1) * 4 + qd)));
+                nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + blob_off<PL>(32, r, (cg + 1) * 4 + qd)));
           }
           float z[32];
 #pragma unroll
@@ -1338,13 +1349,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
               zs[e] = F16 ? z[qd * 8 + e] * sz : z[qd * 8 + e];
             }
             const uint32_t off = piece_off(r, cg * 4 + qd);
-            if (st < 2) stg8<PL, F16>(dst, BLOB_H, off, zs);
+            if (st < 2) stg8<PL, F16>(dst, BLOB_H, blob_off<PL>(32, r, cg * 4 + qd), zs);
             if (tangent && (st == 0 || (st == 1 && !Geo<PL>::FOLD))) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);   // FOLD: ct is no A operand
           }
           if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
             const float cs = warp_colsum32(z, lane);
             atomicAdd(csum + (st - 1) * H + cg * 32 + lane, cs);
-            if (st == 2) {
+            if (st == 2 && PL == 1) {                                 // split modes: dba comes from the seed-tile MMA of wgrad2_kernel
 #pragma unroll
               for (int qd = 0; qd < 4; ++qd) {
                 float s[8];
@@ -1379,7 +1390,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
         if (lane == 0) atomicAdd(csum + 3 * H, sd);
       }
       epi_bar<PL>();
-      for (int i = tid; i < 3 * H; i += Geo<PL>::ET) {
+      for (int i = tid; i < (PL == 1 ? 3 : 2) * H; i += Geo<PL>::ET) {
         const int qn = i / H, j = i % H;
         float* dstv = qn == 0 ? w.vc : (qn == 1 ? w.vg : w.sm3);
         atomicAdd(dstv + (size_t)k * H + j, csum[i]);
@@ -1413,7 +1424,7 @@ struct WgradWork {
   const uint8_t* blobs;
   const NetScales* sc;
   float *gW1, *gW2, *gWa, *gWd;
-  float *gb1, *gb2, *ge, *gbd;
+  float *gb1, *gb2, *ge, *gbd, *gba;
 };
 
 template <int PL> constexpr int smem_wgrad() { return PL * (BLOB_H / 2 + BLOB_H) + AUX_BYTES; }   // 102400 / 200704
@@ -1546,6 +1557,169 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc(tmem, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradients of the split modes: same contraction, restructured around what limited wgrad_kernel<2> (one 200 KB stage per SM:
+// load and MMA strictly alternate, 3.8 TB/s where the same access pattern reaches 5.5 TB/s with two resident CTAs):
+//   * tiles are stored [point half][k-core][64 rows][16 B] (gp_off), so a 64-point half of every operand is contiguous and a stage is
+//     98 KB: J half-columns 2 x 16 KB | Z 2 x 32 KB (24 KB for the 192-wide layers) | seed tile 2 KB.  TWO stages: the bulk loads of
+//     half-tile i+1 run under the 12 (+ seed) MMAs of half-tile i;
+//   * the dba column sum moves here: dba[out] = sum_p (u m3)[p,out] dov[p] is the seed-tile MMA of layer 2, exactly like db1 / db2
+//     (TMEM: 256 accumulator columns + 16 for the seed product);
+//   * epilogue: every thread owns one output row; it parks the scaled row in shared memory (the stages are free by then) and hands
+//     it to the TMA engine as ONE bulk fp32 reduction (cp.reduce.async.bulk ... add.f32, 768 / 1024 contiguous bytes) instead of
+//     192 / 256 scalar red.global.add whose 32 lanes hit 32 different rows.
+// ------------------------------------------------------------------------------------------------
+namespace wg2 {
+constexpr int PT = 64;                              // points per stage
+constexpr int J_PLANE = PT * 128 * 2;               // 16384: [16 k-cores of this out-half][64][16 B]
+constexpr int Z_PLANE = PT * H * 2;                 // 32768 (24576 used by the 192-wide layers)
+constexpr int X_BYTES = PT * 16 * 2;                // 2048 seed tile
+constexpr int STAGE = 2 * J_PLANE + 2 * Z_PLANE + X_BYTES;   // 100352
+constexpr int SMEM = 2 * STAGE;                     // 200704
+constexpr int ROW_PAD = 16;                         // bytes between staged output rows: 1040-byte pitch -> conflict-free 16-byte stores
+static_assert(128 * (H * 4 + ROW_PAD) <= SMEM, "the staged [128 x 256] fp32 output must fit the two (idle) stages");
+}  // namespace wg2
+
+template <bool F16>
+__global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
+  constexpr int PL = 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t full[2], empty[2], acc_ready;
+  __shared__ uint32_t tmem_s;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  int item = blockIdx.x;
+  const int split = item % w.splits; item /= w.splits;
+  const int mh = item & 1; item >>= 1;
+  const int layer = item & 3; item >>= 2;
+  const int k = item % w.Kn, b = item / w.Kn;
+  const int Nn = (layer == 0 || layer == 3) ? C : H;
+  const int KCz = Nn / 8;                                             // k-cores of the Z tile
+  const bool aux = layer != 1;                                        // layer 1 shares its J operand (y) with layer 3, which delivers db2
+  const uint32_t zplane = (uint32_t)wg2::PT * Nn * 2;                 // bytes of one plane of a Z half-tile
+  const int jsel = layer == 0 ? B_QM : (layer == 2 ? B_UM : B_YT);
+  const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
+  const int nst = 2 * (t1 - t0);                                      // half-tiles
+  if (tid == 0) {
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1); mbar_init(&acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&tmem_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_s;
+  constexpr uint32_t COL_X = 256;                                     // seed-product columns
+  if (nst > 0) {
+    if (warp == 4) {
+      for (int i = 0; i < nst; ++i) {
+        const int t = t0 + (i >> 1), ph = i & 1;                      // tile, point half
+        const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
+        const uint8_t* jsrc = nt + (size_t)jsel * Geo<PL>::BH + (size_t)ph * (BLOB_H / 2) + (size_t)mh * wg2::J_PLANE;
+        const uint8_t* zsrc = (layer == 0 ? nt + (size_t)NBLOB_H * Geo<PL>::BH
+                             : layer == 3 ? nt + (size_t)NBLOB_H * Geo<PL>::BH + Geo<PL>::BC
+                             : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * Geo<PL>::BH) + (size_t)ph * zplane;
+        const uint32_t zstride = (layer == 0 || layer == 3) ? BLOB_C : BLOB_H;     // plane stride of the Z tile in the workspace
+        const uint8_t* xsrc = nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC + (size_t)ph * wg2::X_BYTES;
+        const int s = i & 1;
+        uint8_t* st = smem + s * wg2::STAGE;
+        mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[s], 2 * wg2::J_PLANE + 2 * zplane + (aux ? wg2::X_BYTES : 0));
+#pragma unroll
+          for (int p = 0; p < PL; ++p) {
+            bulk_g2s(st + p * wg2::J_PLANE, jsrc + (size_t)p * BLOB_H, wg2::J_PLANE, &full[s]);
+            bulk_g2s(st + 2 * wg2::J_PLANE + p * wg2::Z_PLANE, zsrc + (size_t)p * zstride, zplane, &full[s]);
+          }
+          if (aux) bulk_g2s(st + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE, xsrc, wg2::X_BYTES, &full[s]);
+        }
+      }
+    } else if (warp == 5) {
+      const uint32_t idesc = idesc_16(F16, Nn, 1, 1), idesc_x = idesc_16(F16, 16, 1, 1);
+      // MN-major operands: 8-element groups of the M / N dimension are one k-core block of [64 points][16 B] = 1024 bytes apart,
+      // 8-point groups of the K dimension 128 bytes; a K = 16-point step adds 256 bytes (>> 4) to the address field
+      constexpr uint32_t SBO = wg2::PT * 16;
+      for (int i = 0; i < nst; ++i) {
+        const int s = i & 1;
+        const uint32_t base = smem_u32(smem + s * wg2::STAGE);
+        const uint64_t a_hi = smem_desc(base, 128, SBO), b_hi = smem_desc(base + 2 * wg2::J_PLANE, 128, SBO);
+        const uint64_t x_d = smem_desc(base + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE, 128, SBO);
+        constexpr uint32_t a_lo = wg2::J_PLANE >> 4, b_lo = wg2::Z_PLANE >> 4;
+        mbar_wait(&full[s], (i >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < wg2::PT / 16; ++ks) {
+            const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
+            const uint64_t ad = a_hi + ks * 16, bd = b_hi + ks * 16, xd = x_d + ks * 16;
+            if (aux) {                                       // every J plane is fetched once per step for all MMAs that read it
+              mma_f16_c<A_FILL>(tmem, ad + a_lo, bd, idesc, first);
+              mma_f16_c<A_LAST>(tmem + COL_X, ad + a_lo, xd, idesc_x, first);
+              mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
+              mma_f16_c<A_USE>(tmem, ad, bd, idesc, 1u);
+              mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, 1u);
+            } else {
+              mma_bf16(tmem, ad + a_lo, bd, idesc, first);
+              mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
+              mma_f16_c<A_LAST>(tmem, ad, bd, idesc, 1u);
+            }
+          }
+          mma_commit(&empty[s]);
+        }
+      }
+      if (elect_one()) mma_commit(&acc_ready);
+    } else if (warp < 4) {
+      mbar_wait(&acc_ready, 0);                                        // every MMA has completed: both stages are idle
+      tc_fence_after();
+      const size_t gk = ((size_t)b * w.Kn + k);
+      float* dst = layer == 0 ? w.gW1 + gk * H * C
+                 : layer == 1 ? w.gW2 + gk * H * H
+                 : layer == 2 ? w.gWa + (size_t)k * H * H
+                 : w.gWd + (size_t)k * H * C;
+      dst += (size_t)(mh * TP + tid) * Nn;
+      float un = 1.f, un_x = 1.f;                                      // fp16 variant: undo (J tile scale) x (Z tile / seed scale)
+      if (F16) {
+        const NetScales t = w.sc[gk];
+        const float sj = layer == 0 ? t.sQ : (layer == 2 ? t.sUM : t.sY);
+        const float sz = layer == 0 ? t.sZP : (layer == 1 ? t.sZH : (layer == 2 ? t.sZC : t.sZD));
+        un = (1.f / sj) * (1.f / sz); un_x = (1.f / sj) * (1.f / t.sDV);      // separately: sj * sz may leave the fp32 range
+      }
+      uint8_t* myrow = smem + (size_t)tid * (H * 4 + wg2::ROW_PAD);
+      float v[32];
+      for (int cb = 0; cb < Nn / 32; ++cb) {
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(myrow + cb * 128 + j4 * 16) =
+              make_float4(F16 ? v[j4 * 4] * un : v[j4 * 4], F16 ? v[j4 * 4 + 1] * un : v[j4 * 4 + 1],
+                          F16 ? v[j4 * 4 + 2] * un : v[j4 * 4 + 2], F16 ? v[j4 * 4 + 3] * un : v[j4 * 4 + 3]);
+      }
+      fence_proxy_async();                                             // my generic-proxy row -> visible to the bulk engine
+      bulk_red_add_f32(dst, myrow, (uint32_t)Nn * 4u);
+      bulk_commit();
+      if (aux) {
+        float x[16];
+        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_X, x);
+        const float bsum = (x[0] + x[1] + x[2]) * un_x;                // the three 16-bit terms of the seed
+        const int out = mh * TP + tid;
+        if (layer == 0) {
+          atomicAdd(w.gb1 + gk * H + out, bsum);
+        } else if (layer == 2) {
+          atomicAdd(w.gba + (size_t)k * H + out, bsum);
+        } else {
+          atomicAdd(w.gb2 + gk * H + out, bsum);
+          atomicAdd(w.ge + gk * H + out, bsum);
+          atomicAdd(w.gbd + (size_t)k * H + out, bsum);
+        }
+      }
+      bulk_wait_read_all();                                            // the engine has read my row: shared memory may go away
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1708,7 +1882,7 @@ __global__ void zscale_kernel(int n, const int* __restrict__ seedmax, NetScales*
 // [hi plane | lo plane], so the producer still fetches one contiguous block per chunk.
 template <int PL, bool F16>
 __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
-                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which) {
+                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which, int split) {
   const float* S = src + blockIdx.y * src_stride;
   uint8_t* D = dst + blockIdx.y * dst_stride;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;             // 16-byte piece index
@@ -1725,9 +1899,9 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   }
   uint4 pq[PL];
   split8<PL, F16>(v, pq);
-  // chunk = [rows of CTA 0 | rows of CTA 1] (PAIR: each CTA of a pair stages its half of the rows), each part [hi plane | lo plane],
-  // each plane two k-cores of (part rows) x 16 bytes
-  const int prows = PAIR ? rows / 2 : rows, part = r / prows, rr = r % prows;
+  // chunk = [first half of the rows | second half] (PAIR: each CTA of a pair stages its half of the rows; split: the N-half pipeline of
+  // pass1_np_kernel streams (chunk, half) pieces), each part [hi plane | lo plane], each plane two k-cores of (part rows) x 16 bytes
+  const int prows = (PAIR || split) ? rows / 2 : rows, part = r / prows, rr = r % prows;
   const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)part * PL * prows * 32 + (size_t)(kc & 1) * prows * 16 + (size_t)rr * 16;
 #pragma unroll
   for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * prows * 32) = pq[p];
@@ -1736,7 +1910,8 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
 // coordinate / data features of one tile: bf16 blobs (GEMM operands) and the fp32 transposed copy (epilogues)
 template <int PL, bool F16>
 __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Work w, const float* __restrict__ x,
-                                                    const float* __restrict__ y, const float* __restrict__ t) {
+                                                    const float* __restrict__ y, const float* __restrict__ t,
+                                                    const float* __restrict__ coord_pe) {
   const size_t g = blockIdx.x;
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T, r = threadIdx.x;
   const int p_local = tl * TP + r;
@@ -1744,7 +1919,7 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
   const size_t q = (size_t)b * w.N + w.p0 + p_local;
   float z[3] = {0.f, 0.f, 0.f}, d[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (valid) {
-    z[0] = (x[q] / K.dxf) / K.wm1; z[1] = (y[q] / K.dyf) / K.hm1; z[2] = t[q] / K.t_span;
+    if (!coord_pe) { z[0] = (x[q] / K.dxf) / K.wm1; z[1] = (y[q] / K.dyf) / K.hm1; z[2] = t[q] / K.t_span; }
 #pragma unroll
     for (int c = 0; c < 6; ++c) d[c] = w.coord_data[q * 6 + c];
   }
@@ -1760,9 +1935,16 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float s = 0.f, co = 0.f;
-        if (valid) sincosf(z[c] * band, &s, &co);
+        if (valid && !coord_pe) sincosf(z[c] * band, &s, &co);
         buf[ff * 6 + c] = s;
         buf[ff * 6 + 3 + c] = co;
+      }
+    }
+    if (coord_pe && valid) {                                           // PhysicsNet.forward surface: the caller's encoding (values only)
+#pragma unroll
+      for (int j4 = 0; j4 < 6; ++j4) {
+        const float4 pv = __ldg(reinterpret_cast<const float4*>(coord_pe + q * C + it * 24) + j4);
+        buf[j4 * 4] = pv.x; buf[j4 * 4 + 1] = pv.y; buf[j4 * 4 + 2] = pv.z; buf[j4 * 4 + 3] = pv.w;
       }
     }
 #pragma unroll
@@ -1823,7 +2005,7 @@ __global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
 // Workspace and driver
 // ------------------------------------------------------------------------------------------------
 struct Carve {
-  uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
+  uint8_t *img_gen, *img_sta, *img_gen_np, *img_sta_np, *pe_blob, *pe6_blob, *blobs;
   float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo, *P, *c2;
   long long* dbg;
   NetScales* sc;
@@ -1840,6 +2022,8 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B, int pl) {
   auto take = [&](size_t bytes) { uint8_t* p = base + off; off += al(bytes); return p; };
   c.img_gen = take((size_t)B * Kn * GEN_IMG * pl);
   c.img_sta = take((size_t)Kn * STA_IMG * pl);
+  c.img_gen_np = take(pl == 2 ? (size_t)B * Kn * GEN_NP * pl : 0);
+  c.img_sta_np = take(pl == 2 ? (size_t)Kn * STA_NP * pl : 0);
   c.pe_blob = take((size_t)B * T * BLOB_C * pl);
   c.pe6_blob = take((size_t)B * T * BLOB_C * pl);
   c.pet = reinterpret_cast<float*>(take((size_t)B * T * C * TP * 4));
@@ -1874,24 +2058,33 @@ int default_chunk(int B, int planes) {
 size_t workspace_bytes(int chunk, int Kn, int B, int planes) { return carve(nullptr, chunk, Kn, B, planes).bytes; }
 
 template <int PL, bool F16>
-static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
-  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; };
+static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, bool use_np, cudaStream_t st) {
+  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; int split; };
+  const int np = (PL == 2 && use_np) ? 1 : 0;                          // pass 1 of the split modes reads half-split images
   const Spec specs[] = {
-      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0},                       // W1  : rows = out, k = in
-      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0},                  // W1T : rows = in,  k = out
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1},
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen, 1},
-      {c.P, (size_t)H * H, 2 * IMG_HC + 2 * IMG_HH, GEN_IMG, H, H, 0, PL == 2 ? B * Kn : 0, c.img_gen, 4},   // P  : rows = a3 index, k = a1 index (pass 2, G9)
-      {c.P, (size_t)H * H, 2 * IMG_HC + 3 * IMG_HH, GEN_IMG, H, H, 1, PL == 2 ? B * Kn : 0, c.img_gen, 4},   // PT : rows = a1 index, k = a3 index (pass 1, G5)
-      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta, 2},
-      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta, 3},
-      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta, 3},
+      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0, 0},                       // W1  : rows = out, k = in
+      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, np ? 0 : B * Kn, c.img_gen, 0, 0},         // W1T : rows = in,  k = out
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1, 0},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, np ? 0 : B * Kn, c.img_gen, 1, 0},
+      {c.P, (size_t)H * H, 2 * IMG_HC + 2 * IMG_HH, GEN_IMG, H, H, 0, PL == 2 ? B * Kn : 0, c.img_gen, 4, 0},   // P  : rows = a3 index, k = a1 index (pass 2, G9)
+      {c.P, (size_t)H * H, 2 * IMG_HC + 3 * IMG_HH, GEN_IMG, H, H, 1, (PL == 2 && !np) ? B * Kn : 0, c.img_gen, 4, 0},   // PT : pass1_kernel<2> FOLD only
+      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, np ? 0 : Kn, c.img_sta, 2, 0},
+      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, np ? 0 : Kn, c.img_sta, 3, 0},
+      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, np ? 0 : Kn, c.img_sta, 3, 0},
+      // half-split images of pass1_np_kernel
+      {Wt.W1, (size_t)H * C, 0, GEN_NP, H, C, 0, np ? B * Kn : 0, c.img_gen_np, 0, 1},
+      {Wt.W1, (size_t)H * C, IMG_HC, GEN_NP, C, H, 1, np ? B * Kn : 0, c.img_gen_np, 0, 1},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_NP, H, H, 0, np ? B * Kn : 0, c.img_gen_np, 1, 1},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_NP, H, H, 1, np ? B * Kn : 0, c.img_gen_np, 1, 1},
+      {Wt.Wd, (size_t)H * C, 0, STA_NP, H, C, 0, np ? Kn : 0, c.img_sta_np, 2, 1},
+      {Wt.Wa, (size_t)H * H, IMG_HC, STA_NP, H, H, 0, np ? Kn : 0, c.img_sta_np, 3, 1},
+      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_NP, H, H, 1, np ? Kn : 0, c.img_sta_np, 3, 1},
   };
   for (const Spec& s : specs) {
     if (s.batches == 0) continue;
     const int pieces = s.rows * s.kd / 8;
     image_kernel<PL, F16><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
-                                                                                 s.rows, s.kd, s.tr, c.sc, s.which);
+                                                                                 s.rows, s.kd, s.tr, c.sc, s.which, s.split);
     DPN_LAUNCH_OK();
   }
   return 0;
@@ -1900,22 +2093,25 @@ static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cuda
 template <int PL, bool F16>
 static int run_planes(const Job& J, cudaStream_t st) {
   const int B = J.shape.B, N = J.shape.N, Kn = J.shape.K, chunk = J.chunk;
-  if (J.pts->coord_pe) {
-    set_error("the tensor-core modes derive the coordinate encoding from x,y,t; pre-encoded coord_pe is served by the fp32 kernels");
-    return DPN_E_UNSUPPORTED;
-  }
   const int smem_fused = tc::smem_fused<PL>(), smem_pass2 = tc::smem_pass2<PL>(), smem_wgrad = tc::smem_wgrad<PL>();
+  // split modes: pass 1 as the N-half pipeline (pass1_np_kernel, default) or the strict chain (pass1_ts_kernel, DPN_P1=ts: A/B only)
+  static const bool use_np = !(getenv("DPN_P1") && strcmp(getenv("DPN_P1"), "ts") == 0);
   {
     // function attributes are per device: set them once for every device this process drives (bit d of the mask)
-    static unsigned long long attr_done_mask = 0ull;
+    static std::atomic<unsigned long long> attr_done_mask{0ull};
     int dev = 0;
     DPN_CUDA_OK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !((attr_done_mask >> dev) & 1ull)) {
-      DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+    if (dev < 0 || dev >= 64 || !((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
       DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
-      DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
-      if (PL == 2) DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
-      if (dev >= 0 && dev < 64) attr_done_mask |= 1ull << dev;
+      if constexpr (PL == 2) {
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_np_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, np::SMEM));
+        DPN_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM));
+      } else {
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
+        DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
+      }
+      if (dev >= 0 && dev < 64) attr_done_mask.fetch_or(1ull << dev, std::memory_order_release);
     }
   }
   Carve c = carve(reinterpret_cast<uint8_t*>(J.workspace), chunk, Kn, B, PL);
@@ -1926,8 +2122,12 @@ static int run_planes(const Job& J, cudaStream_t st) {
   const double inv_n = 1.0 / (double)(J.shape.n_norm > 0 ? J.shape.n_norm : N);
   const double seed_scale = J.shape.seed_scale != 0.f ? (double)J.shape.seed_scale : 1.0;
   int rc;
+#ifdef DPN_DEBUG_BUILD                                                 // cycle counters + a stream synchronisation: never in the release library
   static const bool phase_debug = getenv("DPN_PHASE_DEBUG") != nullptr;
   if (phase_debug) DPN_CUDA_OK(cudaMemsetAsync(c.dbg, 0, 16 * 8, st));
+#else
+  constexpr bool phase_debug = false;
+#endif
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
   if (Geo<PL>::FOLD || F16) {                                         // (the scaling plan reads P even when the kernels do not)
     pfold_kernel<<<dim3(H / 32, H / 32, B * Kn), 256, 0, st>>>(Kn, Wt.Wa, Wt.W2, c.P);
@@ -1941,7 +2141,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     plan_kernel<<<1, 32, 0, st>>>(B, Kn, c.sc);
     DPN_LAUNCH_OK();
   }
-  if ((rc = make_images<PL, F16>(Wt, c, B, Kn, st))) return rc;
+  if ((rc = make_images<PL, F16>(Wt, c, B, Kn, use_np, st))) return rc;
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
   if (want_bwd) {
     const DpnGrads& G = *J.grads;
@@ -1967,23 +2167,21 @@ static int run_planes(const Job& J, cudaStream_t st) {
     Work w;
     memset(&w, 0, sizeof(w));
     w.B = B; w.Kn = Kn; w.T = T; w.P = P; w.N = N; w.p0 = p0;
-    w.img_gen = c.img_gen; w.img_sta = c.img_sta;
+    w.img_gen = c.img_gen; w.img_sta = c.img_sta; w.img_gen_np = c.img_gen_np; w.img_sta_np = c.img_sta_np;
     w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst; w.c2 = c.c2;
-    w.coord_data = J.pts->coord_data;
+    w.coord_data = J.pts->coord_data; w.ref = J.pts->ref;
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
     w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
     w.sc = c.sc;
     w.phase_dbg = phase_debug ? c.dbg : nullptr;
-    w.dbg_flags = getenv("DPN_DEBUG_FLAGS") ? atoi(getenv("DPN_DEBUG_FLAGS")) : 0;
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
-    encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t);
+    encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t, J.pts->coord_pe);
     DPN_LAUNCH_OK();
-    // split modes: pass 1 with the A operand in tensor memory; DPN_TS=0 selects the shared-memory variant
-    static const bool use_ts = getenv("DPN_TS") && getenv("DPN_TS")[0] ? atoi(getenv("DPN_TS")) != 0 : DEFAULT_TS;
-    if (PL == 2 && !PAIR && use_ts) {
-      pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
+    if constexpr (PL == 2) {                      // split modes: the A operand lives in tensor memory
+      if (use_np) pass1_np_kernel<F16><<<tiles, Geo<2>::THREADS, np::SMEM, st>>>(w, sweep);
+      else pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
     } else {
       pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
     }
@@ -2024,7 +2222,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
-    ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd;
+    ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd; ww.gba = G.ba;
     const int items = B * Kn * 8;
     // point-splits per (sample, net, layer, out-half): fill whole waves of resident CTAs (148 SMs x CTAs per SM); every split
     // adds one fp32 red.add pass over the gradient tile, so prefer the smallest count within 2 % of the best wave efficiency
@@ -2044,9 +2242,11 @@ static int run_planes(const Job& J, cudaStream_t st) {
       if (PL == 2 && wgrad_tiles > 0 && (T + splits - 1) / splits > wgrad_tiles) splits = (T + wgrad_tiles - 1) / wgrad_tiles;
     }
     ww.splits = splits;
-    wgrad_kernel<PL, F16><<<items * splits, 192, smem_wgrad, st>>>(ww);
+    if constexpr (PL == 2) wgrad2_kernel<F16><<<items * splits, 192, wg2::SMEM, st>>>(ww);
+    else wgrad_kernel<PL, F16><<<items * splits, 192, smem_wgrad, st>>>(ww);
     DPN_LAUNCH_OK();
   }
+#ifdef DPN_DEBUG_BUILD
   if (phase_debug) {
     long long h[16];
     DPN_CUDA_OK(cudaStreamSynchronize(st));
@@ -2057,10 +2257,13 @@ static int run_planes(const Job& J, cudaStream_t st) {
     fprintf(stderr, "[dpn phase] pass2 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f || "
                     "epilogue-thread total %.0f | wait accumulator %.0f | compute %.0f\n", h[8] / n2, h[9] / n2, h[10] / n2, h[12] / n2, h[13] / n2, h[15] / n2);
   }
+#endif
   if (want_bwd) {
     if ((rc = f32::launch_finalize(Kn, Wt, c.vc, c.vg, c.sdo, *J.grads, st))) return rc;
-    finalize_ba_kernel<<<(Kn * H + 255) / 256, 256, 0, st>>>(Kn * H, c.uvec, c.sm3, J.grads->ba);
-    DPN_LAUNCH_OK();
+    if (PL == 1) {                                                    // split modes: dba is a seed-tile product of wgrad2_kernel
+      finalize_ba_kernel<<<(Kn * H + 255) / 256, 256, 0, st>>>(Kn * H, c.uvec, c.sm3, J.grads->ba);
+      DPN_LAUNCH_OK();
+    }
   }
   return 0;
 }
