@@ -45,6 +45,16 @@ class DpnPdeOut(C.Structure):
     _fields_ = [("loss_terms", C.c_void_p), ("vals", C.c_void_p), ("jac", C.c_void_p)]
 
 
+class DpnMargin(C.Structure):
+    _fields_ = [("target", C.c_void_p), ("beta", C.c_double), ("factor", C.c_double), ("loss", C.c_void_p), ("o", C.c_void_p)]
+
+
+class DpnQueryGen(C.Structure):
+    _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("lat_size", C.c_int32), ("lon_size", C.c_int32), ("t_steps", C.c_int32),
+                ("on_grid", C.c_int32), ("dx", C.c_double), ("dy", C.c_double), ("dt", C.c_double),
+                ("seed", C.c_uint64), ("offset", C.c_uint64)]
+
+
 class DpnSampler(C.Structure):
     _fields_ = [("B", C.c_int32), ("N", C.c_int32), ("Tt", C.c_int32), ("Hc", C.c_int32), ("Wc", C.c_int32),
                 ("pad_", C.c_int32), ("dx", C.c_double), ("dy", C.c_double), ("cells_per_coarse", C.c_double),
@@ -53,8 +63,9 @@ class DpnSampler(C.Structure):
 
 _lib = None
 
-EXPORTS = ("dpn_abi_version", "dpn_last_error", "dpn_workspace_bytes", "dpn_pde_fwd_bwd",
-           "dpn_decoder_fwd", "dpn_decoder_bwd", "dpn_sample_field", "dpn_last_launch_count")
+ABI_VERSION = 2
+EXPORTS = ("dpn_abi_version", "dpn_last_error", "dpn_workspace_bytes", "dpn_pde_fwd_bwd", "dpn_pde_margin_fwd_bwd",
+           "dpn_decoder_fwd", "dpn_decoder_bwd", "dpn_sample_field", "dpn_generate_queries", "dpn_last_launch_count")
 
 
 def lib():
@@ -71,6 +82,10 @@ def lib():
         L.dpn_pde_fwd_bwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
                                       C.POINTER(DpnWeights), C.POINTER(DpnPdeOut), C.POINTER(DpnGrads),
                                       C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dpn_pde_margin_fwd_bwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
+                                             C.POINTER(DpnWeights), C.POINTER(DpnMargin), C.POINTER(DpnPdeOut), C.POINTER(DpnGrads),
+                                             C.c_void_p, C.c_size_t, C.c_void_p]
+        L.dpn_generate_queries.argtypes = [C.POINTER(DpnQueryGen), C.POINTER(DpnSampler)] + [C.c_void_p] * 7
         L.dpn_decoder_fwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
                                       C.POINTER(DpnWeights), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.dpn_decoder_bwd.argtypes = [C.POINTER(DpnShape), C.POINTER(DpnConsts), C.POINTER(DpnPoints),
@@ -78,7 +93,7 @@ def lib():
                                       C.c_void_p, C.c_size_t, C.c_void_p]
         L.dpn_sample_field.argtypes = [C.POINTER(DpnSampler)] + [C.c_void_p] * 7
         L.dpn_last_launch_count.restype = C.c_int
-        if L.dpn_abi_version() != 1:
+        if L.dpn_abi_version() != ABI_VERSION:
             raise RuntimeError("libdpn_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -130,12 +145,27 @@ _ws = {}
 
 
 def workspace(shape: DpnShape, device):
-    """Caller-owned scratch, cached per device and grown on demand (torch caching allocator memory)."""
+    """Caller-owned scratch for one library call on the CURRENT stream (torch caching-allocator memory).
+
+    * Outside CUDA-graph capture: one buffer per (device, stream), grown on demand.  A dropped buffer returns to the caching
+      allocator, which only re-issues it in stream order, so kernels already enqueued on that stream stay safe; two streams
+      never share a buffer.
+    * During capture: a fresh allocation from the capturing graph's private pool.  The graph bakes the pointer into its
+      kernel nodes, so the memory must belong to the graph - it then lives exactly as long as the graph does, whatever later
+      eager calls (a larger shape, another mode) do to the cached buffers."""
     need = C.c_size_t(0)
     check(lib().dpn_workspace_bytes(C.byref(shape), C.byref(need)), "dpn_workspace_bytes")
-    key = (device.type, device.index)
+    nbytes = max(need.value, 256)
+    if device.type == "cuda" and torch.cuda.is_current_stream_capturing():
+        return torch.empty(nbytes, dtype=torch.uint8, device=device), need.value
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     buf = _ws.get(key)
-    if buf is None or buf.numel() < need.value:
-        buf = torch.empty(max(need.value, 256), dtype=torch.uint8, device=device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf, need.value
+
+
+def release_workspaces():
+    """Drops every cached scratch buffer (they are re-created on demand)."""
+    _ws.clear()

@@ -11,6 +11,9 @@ namespace dpn {
 int run_sampler(const DpnSampler& S, const float* coarse, const float* x, const float* y, const float* t,
                 float* coord_data, float* f, cudaStream_t st);
 
+int run_query_gen(const DpnQueryGen& G, const DpnSampler* S, const float* coarse, float* x, float* y, float* t,
+                  float* coord_data, float* f, cudaStream_t st);
+
 static thread_local char g_err[1024] = "";
 thread_local int g_launches = 0;
 
@@ -134,9 +137,9 @@ int dpn_workspace_bytes(const DpnShape* shape, size_t* bytes) {
   return 0;
 }
 
-int dpn_pde_fwd_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
-                    const DpnPdeOut* out, const DpnGrads* grads, void* workspace, size_t workspace_bytes,
-                    void* cuda_stream) {
+int dpn_pde_margin_fwd_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
+                           const DpnMargin* margin, const DpnPdeOut* out, const DpnGrads* grads, void* workspace,
+                           size_t workspace_bytes, void* cuda_stream) {
   int rc = check_common(shape, consts, pts, w);
   if (rc) return rc;
   if (shape->K != 6) { set_error("the PDE residual needs K = 6 nets (u,v,p,T,q,rho), got %d", shape->K); return DPN_E_INVALID; }
@@ -147,9 +150,19 @@ int dpn_pde_fwd_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoi
   Job job;
   memset(&job, 0, sizeof(job));
   job.kind = JOB_PDE; job.shape = *shape; job.dc = make_dev_consts(*consts);
-  job.pts = pts; job.w = w; job.out = out; job.grads = grads;
+  if (margin && (!margin->target || !margin->loss || !(margin->beta > 0.0))) {
+    set_error("margin needs target, loss and beta > 0");
+    return DPN_E_INVALID;
+  }
+  job.pts = pts; job.w = w; job.out = out; job.grads = grads; job.margin = margin;
   job.workspace = workspace; job.workspace_bytes = workspace_bytes;
   return dispatch(job, cuda_stream);
+}
+
+int dpn_pde_fwd_bwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
+                    const DpnPdeOut* out, const DpnGrads* grads, void* workspace, size_t workspace_bytes,
+                    void* cuda_stream) {
+  return dpn_pde_margin_fwd_bwd(shape, consts, pts, w, nullptr, out, grads, workspace, workspace_bytes, cuda_stream);
 }
 
 int dpn_decoder_fwd(const DpnShape* shape, const DpnConsts* consts, const DpnPoints* pts, const DpnWeights* w,
@@ -193,6 +206,26 @@ int dpn_sample_field(const DpnSampler* s, const float* coarse, const float* x, c
   int rc = check_device();
   if (rc) return rc;
   return run_sampler(*s, coarse, x, y, t, coord_data, f, reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int dpn_generate_queries(const DpnQueryGen* g, const DpnSampler* s, const float* coarse, float* x, float* y, float* t,
+                         float* coord_data, float* f, void* cuda_stream) {
+  if (!g || !x || !y || !t) { set_error("dpn_generate_queries: NULL argument"); return DPN_E_INVALID; }
+  if (g->B <= 0 || g->N <= 0 || g->lat_size < 2 || g->lon_size < 2 || g->t_steps < 1) {
+    set_error("dpn_generate_queries: bad generator B=%d N=%d grid %dx%d t_steps=%d", g->B, g->N, g->lat_size, g->lon_size, g->t_steps);
+    return DPN_E_INVALID;
+  }
+  if (s) {
+    if (!coarse || !coord_data) { set_error("dpn_generate_queries: sampler given without coarse / coord_data"); return DPN_E_INVALID; }
+    if (s->B != g->B || s->N != g->N || s->Tt < 2 || s->Hc < 2 || s->Wc < 2 || !(s->cells_per_coarse > 0) || !(s->t_step > 0)) {
+      set_error("dpn_generate_queries: sampler shape does not match the generator");
+      return DPN_E_INVALID;
+    }
+  }
+  g_launches = 0;
+  int rc = check_device();
+  if (rc) return rc;
+  return run_query_gen(*g, s, coarse, x, y, t, coord_data, f, reinterpret_cast<cudaStream_t>(cuda_stream));
 }
 
 }  // extern "C"

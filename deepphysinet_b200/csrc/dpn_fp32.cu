@@ -286,6 +286,37 @@ __global__ void residual_kernel(const DevConsts K, int P, const float* __restric
   }
 }
 
+// Supervised data loss on the points of a PDE call (interface_physics.py:464-474, losses/weights_loss.py:12-20):
+// loss += factor * inv_n/6 * sum smooth_l1(o - target; beta) and the seed of the value row gets d(loss)/d(o) added, so the one
+// backward pass that follows serves both losses.  One thread per point; o is the normalised net output (before inverse_norm).
+__global__ void margin_seed_kernel(int P, const float* __restrict__ o, const float* __restrict__ target, double beta, double coef,
+                                   double seed_scale, double* __restrict__ loss, float* __restrict__ dov, float* __restrict__ o_out) {
+  __shared__ double red[8];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double acc = 0.0;
+  if (p < P) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float ov = o[(size_t)p * 6 + k];
+      const double d = (double)ov - (double)target[(size_t)p * 6 + k], ad = fabs(d);
+      const bool quad = ad < beta;
+      acc += quad ? 0.5 * d * d / beta : ad - 0.5 * beta;
+      const double g = quad ? d / beta : (d > 0.0 ? 1.0 : -1.0);
+      dov[(size_t)p * 6 + k] += (float)(seed_scale * coef * g);
+      if (o_out) o_out[(size_t)p * 6 + k] = ov;
+    }
+  }
+#pragma unroll
+  for (int w = 16; w; w >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, w);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w];
+    atomicAdd(loss, coef * v);
+  }
+}
+
 // Backward inputs: XT[k][p,j] = dod[p,k,j%3] dPE[p,j];  ZP = dov PE + XT;  ZD = dov PE6.
 __global__ void bwd_in_kernel(const DevConsts K, int P, int Kn, const float* __restrict__ pe,
                               const float* __restrict__ pe6, const float* __restrict__ dov,
@@ -465,6 +496,7 @@ int run(const Job& J, cudaStream_t st) {
   prep_kernel<<<Kn, 256, 0, st>>>(B, Kn, Wt.Wb, Wt.bb, Wt.wo, Wt.bo, Wt.b2, Wt.bd, Wt.e, w.uvec, w.wo2, w.cst, w.bsum);
   DPN_LAUNCH_OK();
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
+  if (pde && J.margin) DPN_CUDA_OK(cudaMemsetAsync(J.margin->loss, 0, sizeof(double) * B, st));
   if (want_bwd) {
     const DpnGrads& G = *J.grads;
     const size_t BK_ = (size_t)B * Kn;
@@ -539,6 +571,9 @@ int run(const Job& J, cudaStream_t st) {
                                                          J.out->vals ? J.out->vals + q0 * 6 : nullptr,
                                                          J.out->jac ? J.out->jac + q0 * 18 : nullptr);
         DPN_LAUNCH_OK();
+        if (J.margin && (rc = launch_margin(P, w.o, J.margin->target + q0 * 6, *J.margin, inv_n, seed_scale, J.margin->loss + b,
+                                            w.dov, J.margin->o ? J.margin->o + q0 * 6 : nullptr, st)))
+          return rc;
       } else {
         const size_t n = (size_t)P * Kn;
         copy_seed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, J.d_o + q0 * Kn, (float)seed_scale, w.dov);
@@ -608,6 +643,13 @@ int launch_prep(int B, int Kn, const DpnWeights& Wt, float* uvec, float* wo2, fl
 int launch_residual(const DevConsts& DC, int P, const float* o, const float* od, const float* f, double inv_n,
                     double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st) {
   residual_kernel<<<(P + 255) / 256, 256, 0, st>>>(DC, P, o, od, f, inv_n, seed_scale, loss6, dov, dod, vals, jac);
+  DPN_LAUNCH_OK();
+  return 0;
+}
+
+int launch_margin(int P, const float* o, const float* target, const DpnMargin& M, double inv_n, double seed_scale, double* loss,
+                  float* dov, float* o_out, cudaStream_t st) {
+  margin_seed_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, o, target, M.beta, M.factor * inv_n / 6.0, seed_scale, loss, dov, o_out);
   DPN_LAUNCH_OK();
   return 0;
 }

@@ -104,6 +104,13 @@ enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, V_C2, NVEC };   // epilogue vectors s
 
 struct NetScales;
 
+// Work-skipping switches for timing experiments exist only in debug builds (-DDPN_DEBUG_BUILD, never the shipped library)
+#ifdef DPN_DEBUG_BUILD
+#define DPN_DBG(w, bit) (((w).dbg_flags & (bit)) != 0)
+#else
+#define DPN_DBG(w, bit) false
+#endif
+
 struct Work {
   // geometry of this pass
   int B, Kn, T;            // samples, nets, tiles per sample
@@ -130,6 +137,7 @@ struct Work {
   float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
   const NetScales* sc;         // [B][Kn] scaling plan (fp16 variant only)
   long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (debug builds with DPN_PHASE_DEBUG=1), summed over CTAs
+  int dbg_flags;               // DEBUG BUILDS ONLY (tools/build_debug.sh, DPN_DEBUG_FLAGS): 1 = no MMAs, 2 = empty epilogues, 4 = no tile stores
   float band[NF];
 };
 
@@ -2143,6 +2151,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
   }
   if ((rc = make_images<PL, F16>(Wt, c, B, Kn, use_np, st))) return rc;
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
+  if (pde && J.margin) DPN_CUDA_OK(cudaMemsetAsync(J.margin->loss, 0, sizeof(double) * B, st));
   if (want_bwd) {
     const DpnGrads& G = *J.grads;
     const size_t BKn = (size_t)B * Kn;
@@ -2175,6 +2184,9 @@ static int run_planes(const Job& J, cudaStream_t st) {
     w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
     w.sc = c.sc;
     w.phase_dbg = phase_debug ? c.dbg : nullptr;
+#ifdef DPN_DEBUG_BUILD
+    w.dbg_flags = getenv("DPN_DEBUG_FLAGS") ? atoi(getenv("DPN_DEBUG_FLAGS")) : 0;
+#endif
     memcpy(w.band, J.dc.band, sizeof(w.band));
     const int tiles = B * T;
     encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t, J.pts->coord_pe);
@@ -2202,6 +2214,9 @@ static int run_planes(const Job& J, cudaStream_t st) {
                                        J.out->loss_terms + (size_t)b * 6, c.dov + r0 * 6, c.dod + r0 * 18,
                                        J.out->vals ? J.out->vals + q0 * 6 : nullptr,
                                        J.out->jac ? J.out->jac + q0 * 18 : nullptr, st)))
+          return rc;
+        if (J.margin && (rc = f32::launch_margin(P, c.o + r0 * 6, J.margin->target + q0 * 6, *J.margin, inv_n, seed_scale,
+                                                 J.margin->loss + b, c.dov + r0 * 6, J.margin->o ? J.margin->o + q0 * 6 : nullptr, st)))
           return rc;
       }
     } else {
@@ -2247,6 +2262,15 @@ static int run_planes(const Job& J, cudaStream_t st) {
     DPN_LAUNCH_OK();
   }
 #ifdef DPN_DEBUG_BUILD
+  if (phase_debug && PL == 2 && use_np) {
+    long long h[16];
+    DPN_CUDA_OK(cudaStreamSynchronize(st));
+    DPN_CUDA_OK(cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+    const double n1 = h[6] > 0 ? (double)h[6] : 1.0;
+    fprintf(stderr, "[dpn phase] pass1_np per CTA (cycles): mma-warp total %.0f | wait ring %.0f | wait epilogue %.0f || "
+                    "epilogue-thread total %.0f | wait accumulator %.0f | working %.0f || producer wait empty %.0f\n",
+            h[0] / n1, h[1] / n1, h[2] / n1, h[4] / n1, h[5] / n1, h[7] / n1, h[3] / n1);
+  }
   if (phase_debug) {
     long long h[16];
     DPN_CUDA_OK(cudaStreamSynchronize(st));

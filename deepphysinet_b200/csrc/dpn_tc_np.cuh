@@ -107,13 +107,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   if (warp == Geo<PL>::W_PROD) {
     // ---------------- producer: weight half-chunks (multicast slices) and this tile's PE / PE6 slices ----------------
     struct Prod {
-      np::PipeNP* pp; uint8_t* ring; uint32_t rank; uint64_t pol; uint32_t s, ph;
+      np::PipeNP* pp; uint8_t* ring; uint32_t rank; uint64_t pol; uint32_t s, ph; long long t_empty; bool timed;
       __device__ __forceinline__ void advance() { if (++s == np::NSLOT) { s = 0; ph ^= 1; } }
       __device__ __forceinline__ void unit(const uint8_t* img, const int c0, const int nch, const int Nh, const int half, const uint8_t* a_tile,
                                            bool, bool, bool) {
         const uint32_t hb = (uint32_t)Nh * 64u;                       // bytes of one (chunk, half): 2 planes x 2 k-cores x Nh rows x 16 B
         for (int c = c0; c < c0 + nch; ++c) {
-          mbar_wait(&pp->empty[s], ph ^ 1);
+          if (timed) mbar_wait_t(&pp->empty[s], ph ^ 1, t_empty); else mbar_wait(&pp->empty[s], ph ^ 1);
           if (elect_one()) {
             uint8_t* dst = ring + s * np::SLOT;
             const uint8_t* src = img + (size_t)(2 * c + half) * hb;
@@ -138,20 +138,24 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           }
         }
       }
-    } pr{&pipe, ring, cluster_ctarank(), l2_policy_evict_last(), 0u, 0u};
+    } pr{&pipe, ring, cluster_ctarank(), l2_policy_evict_last(), 0u, 0u, 0ll, w.phase_dbg != nullptr};
     for (int k = 0; k < w.Kn; ++k) {
       const np::NetImages im = images(k);
       np::walk_net(pr, im, sweep, k == 0);
     }
+    if (w.phase_dbg && lane == 0) atomicAdd((unsigned long long*)w.phase_dbg + 3, (unsigned long long)pr.t_empty);
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
     struct Iss {
-      np::PipeNP* pp; uint32_t ring_addr, tmem; uint32_t s, ph; uint32_t we[2];
+      np::PipeNP* pp; uint32_t ring_addr, tmem; uint32_t s, ph; uint32_t we[2]; long long t_full, t_epi; bool timed, no_mma;
       __device__ __forceinline__ void advance() { if (++s == np::NSLOT) { s = 0; ph ^= 1; } }
+      __device__ __forceinline__ void bwait(uint64_t* bar, uint32_t parity, long long& t) {
+        if (timed) mbar_wait_t(bar, parity, t); else mbar_wait(bar, parity);
+      }
       __device__ __forceinline__ void unit(const uint8_t*, const int c0, const int nch, const int Nh, const int half, const uint8_t* a_tile,
                                            const bool fresh, const bool wait, const bool commit) {
         if (wait) {                                                    // epilogue (g-1, half) has drained ACC_half and written its part of A
-          mbar_wait(&pp->epi_done[half], we[half] & 1); ++we[half];
+          bwait(&pp->epi_done[half], we[half] & 1, t_epi); ++we[half];
           tc_fence_after();
         }
         const uint32_t idesc = idesc_16(F16, Nh, 0, 0, 128);
@@ -160,25 +164,29 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         const uint64_t a_base = smem_desc(ring_addr, CORE_STRIDE, 128);
         const uint32_t b_lo = ((uint32_t)Nh * 32u) >> 4;
         for (int c = c0; c < c0 + nch; ++c) {
-          mbar_wait(&pp->full[s], ph);
+          bwait(&pp->full[s], ph, t_full);
           const uint32_t sW = s;
           advance();
           uint32_t sA = 0;
-          if (a_tile) { mbar_wait(&pp->full[s], ph); sA = s; advance(); }
+          if (a_tile) { bwait(&pp->full[s], ph, t_full); sA = s; advance(); }
           tc_fence_after();
           const uint64_t bd = b_base + sW * (uint32_t)(np::SLOT >> 4), bl = bd + b_lo;
           const uint32_t first = (!fresh || c > c0) ? 1u : 0u;
           if (elect_one()) {
             if (!a_tile) {                                             // lo*hi + hi*lo + hi*hi, A planes from tensor memory
-              mma_ts(d, tmem + np::COL_AL + 8 * c, bd, idesc, first);
-              mma_ts(d, tmem + np::COL_AH + 8 * c, bl, idesc, 1u);
-              mma_ts(d, tmem + np::COL_AH + 8 * c, bd, idesc, 1u);
+              if (!no_mma) {
+                mma_ts(d, tmem + np::COL_AL + 8 * c, bd, idesc, first);
+                mma_ts(d, tmem + np::COL_AH + 8 * c, bl, idesc, 1u);
+                mma_ts(d, tmem + np::COL_AH + 8 * c, bd, idesc, 1u);
+              }
               if (CLUSTER == 1) mma_commit(&pp->empty[sW]); else mma_commit_mc(&pp->empty[sW], np::MC_MASK);
             } else {
               const uint64_t ad = a_base + sA * (uint32_t)(np::SLOT >> 4), al = ad + (4096 >> 4);
-              mma_bf16(d, al, bd, idesc, first);
-              mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
-              mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
+              if (!no_mma) {
+                mma_bf16(d, al, bd, idesc, first);
+                mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
+                mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
+              }
               if (CLUSTER == 1) { mma_commit(&pp->empty[sW]); mma_commit(&pp->empty[sA]); }
               else { mma_commit_mc(&pp->empty[sW], np::MC_MASK); mma_commit_mc(&pp->empty[sA], np::MC_MASK); }
             }
@@ -186,10 +194,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         }
         if (commit && elect_one()) mma_commit(&pp->acc_ready[half]);
       }
-    } is{&pipe, smem_u32(ring), tmem, 0u, 0u, {0u, 0u}};
+    } is{&pipe, smem_u32(ring), tmem, 0u, 0u, {0u, 0u}, 0ll, 0ll, w.phase_dbg != nullptr, DPN_DBG(w, 1)};
+    const long long t_begin = clock64();
     for (int k = 0; k < w.Kn; ++k) {
       const np::NetImages im = images(k);
       np::walk_net(is, im, sweep, k == 0);
+    }
+    if (w.phase_dbg && lane == 0) {
+      atomicAdd((unsigned long long*)w.phase_dbg + 0, (unsigned long long)(clock64() - t_begin));
+      atomicAdd((unsigned long long*)w.phase_dbg + 1, (unsigned long long)is.t_full);
+      atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)is.t_epi);
     }
   } else if (warp < Geo<PL>::EW) {
     // ---------------- epilogue: thread = (point r, 64-column group `sub` of the current N half) ----------------
@@ -202,6 +216,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t ar[2] = {0u, 0u};
+    long long t_acc = 0;
+    const long long t_begin = clock64();
+    const bool timed = w.phase_dbg != nullptr, skip_epi = DPN_DBG(w, 2), skip_st = DPN_DBG(w, 4);
     // 32 columns (block cg of the 256) of this row: split into the two planes once, then -> workspace tile (if any) and / or the next A operand
     auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a) {
       uint32_t hi[16], lo[16];
@@ -209,7 +226,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int qd = 0; qd < 4; ++qd) {
         uint4 pq[PL];
         split8<PL, F16>(v + qd * 8, pq);
-        if (blob) {
+        if (blob && !skip_st) {
           const uint32_t off = gp_off(32, r, cg * 4 + qd);
           __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
           __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
@@ -222,7 +239,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         tmem_st16(lane_base + np::COL_AL + cg * 16, lo);
       }
     };
-    auto acc_wait = [&](const int h) { mbar_wait(&pipe.acc_ready[h], ar[h] & 1); ++ar[h]; tc_fence_after(); };
+    auto acc_wait = [&](const int h) {
+      if (timed) mbar_wait_t(&pipe.acc_ready[h], ar[h] & 1, t_acc); else mbar_wait(&pipe.acc_ready[h], ar[h] & 1);
+      ++ar[h]; tc_fence_after();
+    };
     auto done = [&](const int h) { tmem_st_wait(); tc_fence_before(); mbar_arrive(&pipe.epi_done[h]); };
     if (sub == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
@@ -243,7 +263,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int h = 0; h < 2; ++h) {
         acc_wait(h);
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < (skip_epi ? 0 : 2); ++cb) {
           const int cg = 4 * h + 2 * sub + cb;
           float v[32];
           tmem_ld32(lane_base + cg * 32, v);
@@ -271,7 +291,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int h = 0; h < 2; ++h) {
         acc_wait(h);
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < (skip_epi ? 0 : 2); ++cb) {
           const int cg = 4 * h + 2 * sub + cb;
           float v[32];
           tmem_ld32(lane_base + cg * 32, v);
@@ -296,7 +316,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int h = 0; h < 2; ++h) {
         acc_wait(h);
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < (skip_epi ? 0 : 2); ++cb) {
           const int cg = 4 * h + 2 * sub + cb;
           float v[32];
           tmem_ld32(lane_base + cg * 32, v);
@@ -318,7 +338,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
                 v[j] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;          // um replaces the accumulator value in place
               }
             }
-            if (sweep) {
+            if (sweep && !skip_st) {
               uint4 pq[PL];
               split8<PL, F16>(g8, pq);
               const uint32_t off = gp_off(32, r, cg * 4 + qd);
@@ -343,7 +363,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int h = 0; h < 2; ++h) {
         acc_wait(h);
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < (skip_epi ? 0 : 2); ++cb) {
           const int cg = 4 * h + 2 * sub + cb;
           float v[32];
           tmem_ld32(lane_base + cg * 32, v);
@@ -363,7 +383,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int h = 0; h < 2; ++h) {
         acc_wait(h);
 #pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        for (int cb = 0; cb < (skip_epi ? 0 : 2); ++cb) {
           const int cg = 4 * h + 2 * sub + cb;
           float v[32];
           tmem_ld32(lane_base + cg * 32, v);
@@ -383,6 +403,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         acc_wait(h);
+        if (skip_epi) { done(h); continue; }
         const int fb = 96 * h + 48 * sub;
         const uint32_t a6 = lane_base + (uint32_t)(128 * h + 48 * sub);
         {
@@ -413,6 +434,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           rowsum[r * 4 + 1 + c] = 0.f;
         }
       }
+    }
+    if (w.phase_dbg && tid == 0) {
+      const long long tot = clock64() - t_begin;
+      atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)tot);
+      atomicAdd((unsigned long long*)w.phase_dbg + 5, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 7, (unsigned long long)(tot - t_acc));
+      atomicAdd((unsigned long long*)w.phase_dbg + 6, 1ull);
     }
   }
   tc_fence_before();

@@ -77,9 +77,13 @@ def _shape(B, Np, K, mode, n_norm=0, seed_scale=1.0, chunk=0):
 
 
 class PDEResidualFn(torch.autograd.Function):
-    """(total, terms[B,6]) = PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode, n_norm, want_fields, *weights)
+    """(total, terms[B,6][, vals, jac][, margin_loss[B], o]) =
+           PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode, n_norm, want_fields, margin, *weights)
 
     x, y, t, f: [B,N] (or [N], [N,1] for B=1); coord_data [B,N,6].
+    margin: None, or (target [B,N,6], beta, factor): the supervised SmoothL1 data loss of the train loop on the same points
+    (interface_physics.py:464-474), fused into the call - then `total` = mean over samples of (six PDE terms +
+    margin loss), and margin_loss [B] (float64) and the normalised values o [B,N,6] are returned as non-differentiable extras.
     total = mean over samples of the sum of the six terms (SURVEY D4: DDP sample-mean semantics);
     terms (float64, per sample, non-differentiable) are what place_one_batch logs (:303-318).
     Forward already runs the fused backward kernels and caches d(total)/d(weights); backward only
@@ -87,7 +91,7 @@ class PDEResidualFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, y, t, f, coord_data, consts: PhysicsConsts, mode, n_norm, want_fields, *weights):
+    def forward(ctx, x, y, t, f, coord_data, consts: PhysicsConsts, mode, n_norm, want_fields, margin, *weights):
         W = DecoderWeights(*weights)
         B, K = _check_weights(W)
         if K != 6:
@@ -97,7 +101,7 @@ class PDEResidualFn(torch.autograd.Function):
         Np = cd.shape[1]
         xs = [_prep(a, (B, Np)) for a in (x, y, t, f)]
         ws = [_prep(w) for w in W]
-        need_grad = any(w.requires_grad for w in weights)
+        need_grad = any(ctx.needs_input_grad[10:])            # False under no_grad / for detached weights: no backward kernels then
         grads = [torch.empty_like(w) for w in ws] if need_grad else None
         terms = torch.empty(B, 6, dtype=torch.float64, device=dev)
         vals = torch.empty(B, Np, 6, device=dev) if want_fields else None
@@ -111,24 +115,37 @@ class PDEResidualFn(torch.autograd.Function):
         wstruct = _weights_struct(ws)
         gstruct = _grads_struct(grads) if need_grad else None
         wsbuf, nbytes = N.workspace(shape, dev)
-        N.check(N.lib().dpn_pde_fwd_bwd(C.byref(shape), C.byref(cst), C.byref(pts), C.byref(wstruct), C.byref(out),
-                                        C.byref(gstruct) if need_grad else None,
-                                        N.ptr(wsbuf), nbytes, N.stream_ptr()), "dpn_pde_fwd_bwd")
+        mstruct = mloss = o_norm = None
+        if margin is not None:
+            target, beta, factor = margin
+            tg = _prep(target, (B, Np, 6))
+            mloss = torch.empty(B, dtype=torch.float64, device=dev)
+            o_norm = torch.empty(B, Np, 6, device=dev)
+            mstruct = N.DpnMargin(target=tg.data_ptr(), beta=float(beta), factor=float(factor), loss=mloss.data_ptr(), o=o_norm.data_ptr())
+        N.check(N.lib().dpn_pde_margin_fwd_bwd(C.byref(shape), C.byref(cst), C.byref(pts), C.byref(wstruct),
+                                               C.byref(mstruct) if mstruct is not None else None, C.byref(out),
+                                               C.byref(gstruct) if need_grad else None,
+                                               N.ptr(wsbuf), nbytes, N.stream_ptr()), "dpn_pde_margin_fwd_bwd")
         ctx.grads = grads
         ctx.dtypes = [w.dtype for w in weights]
-        total = terms.sum(dim=1).mean().to(torch.float32)
+        total = terms.sum(dim=1).mean() if mloss is None else (terms.sum(dim=1) + mloss).mean()
+        total = total.to(torch.float32)
         ctx.mark_non_differentiable(terms)
+        ret = (total, terms)
         if want_fields:
             ctx.mark_non_differentiable(vals, jac)
-            return total, terms, vals, jac
-        return total, terms
+            ret = ret + (vals, jac)
+        if mloss is not None:
+            ctx.mark_non_differentiable(mloss, o_norm)
+            ret = ret + (mloss, o_norm)
+        return ret
 
     @staticmethod
     def backward(ctx, g_total, *unused):
         if ctx.grads is None:
-            return (None,) * 22
+            return (None,) * 23
         gs = [(g * g_total).to(dt) for g, dt in zip(ctx.grads, ctx.dtypes)]
-        return (None,) * 9 + tuple(gs)
+        return (None,) * 10 + tuple(gs)
 
 
 class DecoderValuesFn(torch.autograd.Function):
@@ -157,7 +174,7 @@ class DecoderValuesFn(torch.autograd.Function):
                                         N.ptr(wsbuf), nbytes, N.stream_ptr()), "dpn_decoder_fwd")
         ctx.saved = (pe, xs, cd, rf, ws, consts, mode, B, Np, K)
         ctx.dtypes = [w.dtype for w in weights]
-        ctx.need = any(w.requires_grad for w in weights)
+        ctx.need = any(ctx.needs_input_grad[8:])
         return o
 
     @staticmethod
@@ -200,7 +217,46 @@ def default_mode():
 def pde_residual(x, y, t, f, coord_data, W: DecoderWeights, consts: Optional[PhysicsConsts] = None, mode=None,
                  n_norm=0, want_fields=False):
     consts = consts or PhysicsConsts()
-    return PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode or _DEFAULT_MODE, n_norm, want_fields, *W)
+    return PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode or _DEFAULT_MODE, n_norm, want_fields, None, *W)
+
+
+def pde_margin_residual(x, y, t, f, coord_data, target, W: DecoderWeights, beta=0.1, factor=1.0e6,
+                        consts: Optional[PhysicsConsts] = None, mode=None, n_norm=0):
+    """PDE residual loss AND the supervised margin (data) loss on the same points in one library call (SURVEY 8(f) N1;
+    interface_physics.py:464-474 + :489-496): returns (total, terms [B,6], margin_loss [B], o [B,N,6]) with
+    total = mean over samples of (sum of the six PDE terms + factor * mean smooth_l1(o - target; beta)), differentiable w.r.t.
+    every DecoderWeights tensor; one forward, one reverse sweep and one backward instead of the reference's two passes."""
+    consts = consts or PhysicsConsts()
+    return PDEResidualFn.apply(x, y, t, f, coord_data, consts, mode or _DEFAULT_MODE, n_norm, False, (target, beta, factor), *W)
+
+
+def generate_queries(B, Np, seed, offset=0, on_grid=False, consts: Optional[PhysicsConsts] = None, t_steps=25, dt=3600.0,
+                     coarse=None, device=None, cells_per_coarse=4.0, t_step=6 * 3600.0, begin_lat=18.0, deg_per_cell=0.25,
+                     omega=7.29e-5):
+    """On-GPU query-point generator: Philox4x32-10 draws with the distributions of
+    dataset/physics_dataset.py:442-446 (interior: continuous) or :334-338 (on_grid: margin nodes); with `coarse` [B,Tt,Hc,Wc,6]
+    the same launch also interpolates coord_data [B,N,6] and evaluates the Coriolis parameter f [B,N].
+    Returns (x, y, t) or (x, y, t, coord_data, f), all device tensors."""
+    consts = consts or PhysicsConsts()
+    dev = torch.device(device) if device is not None else (coarse.device if coarse is not None else torch.device("cuda"))
+    if dev.type != "cuda":
+        raise RuntimeError("deepphysinet_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+    x, y, t = (torch.empty(B, Np, device=dev) for _ in range(3))
+    G = N.DpnQueryGen(B=B, N=Np, lat_size=consts.lat_size, lon_size=consts.lon_size, t_steps=int(t_steps), on_grid=int(bool(on_grid)),
+                      dx=consts.dx, dy=consts.dy, dt=float(dt), seed=int(seed) & (2 ** 64 - 1), offset=int(offset))
+    S = cd = f = cz = None
+    if coarse is not None:
+        cz = _prep(coarse)
+        if cz.dim() != 5 or cz.shape[-1] != 6 or cz.shape[0] != B:
+            raise ValueError("coarse must be [B,Tt,Hc,Wc,6], got %s" % (tuple(cz.shape),))
+        _, Tt, Hc, Wc, _ = cz.shape
+        cd, f = torch.empty(B, Np, 6, device=dev), torch.empty(B, Np, device=dev)
+        S = N.DpnSampler(B=B, N=Np, Tt=Tt, Hc=Hc, Wc=Wc, pad_=0, dx=consts.dx, dy=consts.dy, cells_per_coarse=float(cells_per_coarse),
+                         t_step=float(t_step), begin_lat=float(begin_lat), deg_per_cell=float(deg_per_cell), omega=float(omega))
+    with torch.cuda.device(dev):
+        N.check(N.lib().dpn_generate_queries(C.byref(G), C.byref(S) if S is not None else None, N.ptr(cz), N.ptr(x), N.ptr(y), N.ptr(t),
+                                             N.ptr(cd), N.ptr(f), N.stream_ptr()), "dpn_generate_queries")
+    return (x, y, t) if coarse is None else (x, y, t, cd, f)
 
 
 def decoder_values(coord_pe, coord_data, W: DecoderWeights, ref=None, xyz=None, consts=None, mode=None):

@@ -1,5 +1,8 @@
 """CUDA-graph capture of one whole PDE step through the reference-facing call.
 
+The library's scratch memory is allocated INSIDE the capture (deepphysinet_b200._native.workspace), i.e. from the graph's private
+pool: it lives exactly as long as this object and no later eager call can free or reuse it.
+
 `place_one_batch` + `backward()` is ~500 small PyTorch launches (encoder, hyper-network, their backward) around the
 fused operator; on the host they cost more than the GPU work they enqueue.  `GraphedPlaceOneBatch` captures the whole
 step once - host->device copies of the pinned inputs, encoder, fused operator, backward - and replays it with a single
@@ -32,6 +35,8 @@ class GraphedPlaceOneBatch:
                 self._eager().backward()
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
+        from . import _native
+        _native.release_workspaces()                       # the warm-up's scratch was keyed to the side stream; the capture allocates its own
         model.physics_net.zero_grad(set_to_none=True)      # grads are (re)created inside the capture: static addresses
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):

@@ -134,38 +134,56 @@ class InterfacePhysics(nn.Module):
         from .config import DEFAULT_LOSS_FACTOR
         return getattr(self, "_loss_factor", DEFAULT_LOSS_FACTOR)
 
-    def training_losses(self, batch, loss_factor, with_pde=True, beta=0.1):
-        """One training step's loss exactly as interface_physics.py:464-501 composes it (margin data loss + interior
-        PDE loss + PDE loss on the margin points), with ONE encoder / hyper-network pass shared by the three terms
-        (the reference re-runs MetaNet for each, physics_net.py:42).  `batch` holds device tensors:
-        field_data [B,159,2405], forecast_h [B,1,1], margin_{x,y,t,f} [B,M], margin_input_data [B,M,6], margin_data [B,M,6],
-        inter_{x,y,t,f} [B,N], inter_data [B,N,6].  Returns (train_loss, parts dict)."""
+    def training_losses(self, batch, loss_factor, with_pde=True, beta=0.1, fuse_margin=True):
+        """One training step's loss exactly as interface_physics.py:464-501 composes it (margin data loss + interior PDE loss +
+        PDE loss on the margin points), with ONE encoder / hyper-network pass shared by the three terms (the reference re-runs
+        MetaNet for each, physics_net.py:42) and - SURVEY 8(f) N1 - ONE library call for the margin points: the reference sends
+        them through the decoder twice (values for WeightSmoothL1Loss :467-474, then place_one_batch :489-496); here
+        `functional.pde_margin_residual` returns both losses from one forward / reverse sweep / backward.
+        `batch` holds device tensors: field_data [B,159,2405], forecast_h [B,1,1], margin_{x,y,t,f} [B,M],
+        margin_input_data [B,M,6], margin_data [B,M,6], inter_{x,y,t,f} [B,N], inter_data [B,N,6].
+        Returns (train_loss, parts dict).  fuse_margin=False keeps the two separate calls (cross-check)."""
         self._loss_factor = loss_factor
         W = self.physics_net.decoder_weights(batch["field_data"], batch["forecast_h"])
         consts = self.consts(loss_factor)
+        mfac = loss_factor.get("margin_factor", 1.0e6)
         parts = {}
-        parts["margin_loss"] = self.margin_loss(W, batch["margin_x"], batch["margin_y"], batch["margin_t"],
-                                                batch["margin_input_data"], batch["margin_data"], beta=beta,
-                                                factor=loss_factor.get("margin_factor", 1.0e6))
-        total = parts["margin_loss"]
+        if not (with_pde and fuse_margin):
+            parts["margin_loss"] = self.margin_loss(W, batch["margin_x"], batch["margin_y"], batch["margin_t"],
+                                                    batch["margin_input_data"], batch["margin_data"], beta=beta, factor=mfac)
+            total = parts["margin_loss"]
         if with_pde:
-            for prefix, dkey in (("inter", "inter_data"), ("margin", "margin_input_data")):
-                tot, terms = Fn.pde_residual(batch[prefix + "_x"], batch[prefix + "_y"], batch[prefix + "_t"],
-                                             batch[prefix + "_f"], batch[dkey], W, consts=consts, mode=self.mode)
-                parts[prefix + "_pde_loss"] = tot
-                parts[prefix + "_terms"] = terms
-                total = total + tot
+            tot, terms = Fn.pde_residual(batch["inter_x"], batch["inter_y"], batch["inter_t"], batch["inter_f"], batch["inter_data"],
+                                         W, consts=consts, mode=self.mode)
+            parts["inter_pde_loss"], parts["inter_terms"] = tot, terms
+            if fuse_margin:
+                B = W.W1.shape[0]
+                both, mterms, mloss, _ = Fn.pde_margin_residual(
+                    batch["margin_x"], batch["margin_y"], batch["margin_t"], batch["margin_f"], batch["margin_input_data"],
+                    batch["margin_data"].reshape(B, -1, 6), W, beta=beta, factor=mfac, consts=consts, mode=self.mode)
+                # logging split (no gradient of its own: `both` carries it)
+                parts["margin_loss"] = mloss.mean().float()
+                parts["margin_pde_loss"] = mterms.sum(dim=1).mean().float()
+                parts["margin_terms"] = mterms
+                total = tot + both
+            else:
+                mt, mterms = Fn.pde_residual(batch["margin_x"], batch["margin_y"], batch["margin_t"], batch["margin_f"],
+                                             batch["margin_input_data"], W, consts=consts, mode=self.mode)
+                parts["margin_pde_loss"], parts["margin_terms"] = mt, mterms
+                total = total + tot + mt
         return total, parts
 
     @torch.no_grad()
-    def predict_grid(self, field_data, coarse, forecast_h, time_ids, dt=3600.0):
+    def predict_grid(self, field_data, coarse, forecast_h, time_ids, dt=3600.0, weights=None):
         """Dense-grid continuous-time forward (the working inference of the reference, interface_physics.py:538-606):
         every node of the lat_size x lon_size grid at each lead time `time_ids[i] * dt`, x-major node order (:541-545),
         coord_data from the coarse field by the on-GPU trilinear sampler (dataset.get_margin_grid :528-588), values only,
         inverse_norm WITHOUT clip (:533).  Returns physical fields [len(time_ids), lat_size, lon_size, 6]."""
         dev = field_data.device
         Hh, Ww = int(self.lat_size), int(self.lon_size)
-        W = self.physics_net.decoder_weights(field_data[:1], forecast_h[:1])
+        # the generated weights depend on (field_data, forecast_h) only: a lead-time sweep over one encoded field passes the
+        # DecoderWeights of its first call back in (`weights=`) and skips encoder + hyper-network (SURVEY 8(f) N4)
+        W = weights if weights is not None else self.physics_net.decoder_weights(field_data[:1], forecast_h[:1])
         xs, ys = torch.meshgrid(torch.arange(Ww, device=dev, dtype=torch.float32),
                                 torch.arange(Hh, device=dev, dtype=torch.float32), indexing="ij")
         x = (xs.reshape(1, -1) * self.dx).repeat(1, len(time_ids))

@@ -37,10 +37,20 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 class FlatGradAllReduce:
-    """Packs the .grad of `params` into one flat buffer, all-reduces it (sum) and writes back the mean over ranks
-    (DDP semantics: loss = mean over samples).  Parameters whose grad is None contribute zeros."""
+    """Packs the .grad of `params` into one flat buffer and all-reduces it with ONE collective.
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    op="mean" (default): writes back SUM / world - DDP semantics for LEVEL-1 sharding (every rank owns whole samples and its
+        loss is already the mean over ITS samples; the global loss is the mean over ranks).
+    op="sum": writes back the plain SUM - LEVEL-2 sharding (one sample's query points split across ranks, the operator called
+        with n_norm = total points of the sample): every rank's gradient is then a partial sum that is already normalised by
+        n_norm, and averaging would scale the step by 1/world.  The partial loss terms add up the same way:
+        `reduce_partial_losses` below.
+    Parameters whose grad is None contribute zeros."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], op: str = "mean"):
+        if op not in ("mean", "sum"):
+            raise ValueError("op must be 'mean' (sample sharding) or 'sum' (point sharding), got %r" % (op,))
+        self.op = op
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.numel = sum(p.numel() for p in self.params)
         self.flat = None
@@ -62,21 +72,40 @@ class FlatGradAllReduce:
             torch._foreach_zero_(dead)
         if live:
             torch._foreach_copy_([v for v, _ in live], [p.grad for _, p in live])
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, async_op=async_op)
+        # NCCL divides inside the collective (ReduceOp.AVG); gloo (CPU tests) has no AVG: sum, then one scale pass
+        fused_avg = self.op == "mean" and dist.get_backend() == "nccl"
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if fused_avg else dist.ReduceOp.SUM, async_op=async_op)
 
         def finish():
             if work is not None:
                 work.wait()
-            self.flat.mul_(1.0 / dist.get_world_size())
+            if self.op == "mean" and not fused_avg:
+                self.flat.mul_(1.0 / dist.get_world_size())
+            dst, src = [], []
             for v, p in zip(views, self.params):
                 if p.grad is None:
                     p.grad = v.clone()
                 else:
-                    p.grad.copy_(v)
+                    dst.append(p.grad)
+                    src.append(v)
+            if dst:
+                torch._foreach_copy_(dst, src)
         if async_op:
             return finish
         finish()
         return None
+
+
+def reduce_partial_losses(total: torch.Tensor, terms: torch.Tensor = None):
+    """LEVEL-2 (point) sharding: `total` / `terms` returned by the operator on this rank's points with n_norm = all points of
+    the sample are PARTIAL sums; the sample's loss is their sum over ranks.  Returns detached, reduced copies (for logging and
+    the loss value - the gradient path is FlatGradAllReduce(op="sum"))."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return total.detach(), terms
+    buf = torch.cat([total.detach().reshape(1).double(), terms.detach().reshape(-1).double()]) if terms is not None \
+        else total.detach().reshape(1).double()
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf[0].to(total.dtype), (buf[1:].reshape(terms.shape) if terms is not None else None)
 
 
 def allreduce_max(value: float, device) -> float:

@@ -93,6 +93,47 @@ class PhysicsNet(nn.Module):
     def decoder_weights(self, field_x, forecast_h) -> "Fn.DecoderWeights":
         """Encoder + hyper-network (PyTorch, differentiable): everything the fused operator consumes.
         field_x [B,159,2405]; forecast_h [B,1,1] or [1,1,1].  Shapes: generated [B,6,...], static [6,...]."""
+        return self.decoder_weights_from_meta(self.meta_net(field_x, forecast_h), forecast_h)
+
+    def decoder_weights_from_meta(self, meta, forecast_h) -> "Fn.DecoderWeights":
+        """The hyper-network of all six nets as ONE GEMM (variable_net.py:57-65 applies two nn.Linear per net to the same
+        token matrix: 12 small GEMMs forward, 24 backward, plus 5 x 6 slices to stack).  The 12 weight matrices are
+        concatenated row-wise - [6 x 192 rows of coord_input_fc (w1) | 6 x 256 rows of coord_hidden_fc (w2) | 6 b1 rows | 6 b2 rows]
+        = 2 700 output columns - so one [B*256, 256] x [256, 2 700] product yields every generated tensor; the lead-time
+        embedding e (:75-78) is one [B,192] x [192, 6*256] product.  Same arithmetic per output element as the per-net Linears
+        (fp32 dot products over the 256 tokens), parameters untouched (state_dict unchanged).  With fixed `meta` and
+        `forecast_h` (a lead-time sweep over one encoded field, interface_physics.py:538-606) the result can be cached by the
+        caller: `predict_grid` does."""
+        nets = self.nets
+        K, C, Hd, T = len(nets), nets[0].in_channels, nets[0].hidden_channels, nets[0].token_num
+        B = meta.shape[0]
+        wall = torch.cat([n.coord_input_fc.weight[:C] for n in nets] + [n.coord_hidden_fc.weight[:Hd] for n in nets] +
+                         [n.coord_input_fc.weight[C:] for n in nets] + [n.coord_hidden_fc.weight[Hd:] for n in nets])   # [2700, T]
+        ball = torch.cat([n.coord_input_fc.bias[:C] for n in nets] + [n.coord_hidden_fc.bias[:Hd] for n in nets] +
+                         [n.coord_input_fc.bias[C:] for n in nets] + [n.coord_hidden_fc.bias[Hd:] for n in nets])
+        tok = meta[:, :T].transpose(1, 2)                                   # [B, D, T]: hidden index = encoder channel (A.3)
+        g = torch.nn.functional.linear(tok, wall, ball)                     # [B, D, 2700]
+        D = g.shape[1]
+        o1, o2 = K * C, K * C + K * Hd
+        W1 = g[..., :o1].reshape(B, D, K, C).permute(0, 2, 1, 3)            # [B, K, D, C]
+        W2 = g[..., o1:o2].reshape(B, D, K, Hd).permute(0, 2, 1, 3)         # [B, K, D, Hd]
+        b1 = g[..., o2:o2 + K].transpose(1, 2)                              # [B, K, D]
+        b2 = g[..., o2 + K:].transpose(1, 2)
+        fh = forecast_h.reshape(-1, 1).expand(B, 1)
+        pe = nets[0].pe_fore_h(fh)                                          # identical fixed encoding in every net
+        e = torch.nn.functional.linear(pe, torch.cat([n.fore_h_fc.weight for n in nets]),
+                                       torch.cat([n.fore_h_fc.bias for n in nets])).reshape(B, K, Hd)
+        st = lambda f: torch.stack([f(n) for n in nets])
+        return Fn.DecoderWeights(
+            W1=W1, b1=b1, W2=W2, b2=b2, e=e,
+            Wd=st(lambda n: n.data_input_fc.weight), bd=st(lambda n: n.data_input_fc.bias),
+            Wa=st(lambda n: n.cat_fc1.fc[0].weight), ba=st(lambda n: n.cat_fc1.fc[0].bias),
+            Wb=st(lambda n: n.cat_fc1.fc[2].weight), bb=st(lambda n: n.cat_fc1.fc[2].bias),
+            wo=st(lambda n: n.out_fc.weight.reshape(-1)), bo=st(lambda n: n.out_fc.bias.reshape(())))
+
+    def decoder_weights_per_net(self, field_x, forecast_h) -> "Fn.DecoderWeights":
+        """The same tensors through VariableNet.generate, net by net (the literal structure of variable_net.py:57-65) - kept as
+        the cross-check of the batched hyper-network (tests/test_hypernet_batched.py)."""
         meta = self.meta_net(field_x, forecast_h)
         gen = [n.generate(meta, forecast_h) for n in self.nets]
         st = lambda f: torch.stack([f(n) for n in self.nets])

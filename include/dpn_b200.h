@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define DPN_ABI_VERSION 1
+#define DPN_ABI_VERSION 2
 
 #define DPN_H 256
 #define DPN_C 192
@@ -135,6 +135,24 @@ int dpn_pde_fwd_bwd(const DpnShape *shape, const DpnConsts *consts, const DpnPoi
                     const DpnWeights *w, const DpnPdeOut *out, const DpnGrads *grads,
                     void *workspace, size_t workspace_bytes, void *cuda_stream);
 
+/* The supervised data loss of the train loop on the SAME points as a PDE call: the reference evaluates the
+ * margin (label) points twice per step - values only for WeightSmoothL1Loss (interface_physics.py:464-474,
+ * losses/weights_loss.py:12-20) and again inside place_one_batch for their PDE residual (:489-496).  With `margin` set the
+ * PDE call adds, per sample,  loss[b] = factor * mean_{N x 6} smooth_l1(o - target; beta)  (o = the six NORMALISED net outputs,
+ * exactly what PhysicsNet.forward returns) and the gradients it writes are d(sum of the six PDE terms + loss[b]) / d(weights):
+ * one forward, one reverse sweep, one backward for both losses. */
+typedef struct DpnMargin {
+  const float *target;  /* [B*N,6] normalised observations (margin_data), u,v,p,T,q,rho order            */
+  double beta;          /* SmoothL1 transition (cfg train_cfg.losses: beta = 0.1)                        */
+  double factor;        /* margin_factor (cfg: 1e6)                                                      */
+  double *loss;         /* out [B]                                                                       */
+  float *o;             /* out [B*N,6] normalised values, optional (NULL to skip)                         */
+} DpnMargin;
+
+int dpn_pde_margin_fwd_bwd(const DpnShape *shape, const DpnConsts *consts, const DpnPoints *pts,
+                           const DpnWeights *w, const DpnMargin *margin, const DpnPdeOut *out,
+                           const DpnGrads *grads, void *workspace, size_t workspace_bytes, void *cuda_stream);
+
 /* Replaces the six VariableNet.forward calls of PhysicsNet.forward (physics_net.py:49-54,
  * variable_net.py:67-87): normalised outputs o [B*N,K].  Values only (dense-grid inference,
  * interface_physics.py:538-563, and the supervised margin loss :467-474). */
@@ -165,6 +183,27 @@ typedef struct DpnSampler {
 
 int dpn_sample_field(const DpnSampler *s, const float *coarse, const float *x, const float *y, const float *t,
                      float *coord_data, float *f, void *cuda_stream);
+
+/* Query-point generator (the other half of the producer): replaces the numpy draws of
+ * dataset/physics_dataset.py:442-446 (interior points: x = U[0,1) (W-1) dx, y = U[0,1) (H-1) dy, t = randint(0, t_steps) dt) and
+ * :334-338 (margin points: x = randint(0, W) dx, y = randint(0, H) dy - grid nodes) with a counter-based generator on the GPU:
+ * Philox4x32-10, key = seed, counter = (point index + offset, sample, 0): one 128-bit block per point, words 0/1/2 -> x/y/t.
+ * U[0,1) = (word >> 8) 2^-24; randint(0, n) = (word * n) >> 32.  Same distributions as the reference, NOT the same stream as
+ * numpy's MT19937 (oracle/query_oracle.py restates the generator bit for bit).  With `sampler` and `coarse` given the same kernel
+ * also interpolates coord_data and evaluates f for the points it just drew (dpn_sample_field semantics), so a training step's
+ * per-point inputs are produced by ONE launch and never exist on the host.
+ *   x, y, t [B*N] out;  coord_data [B*N,6], f [B*N] out (NULL with sampler == NULL). */
+typedef struct DpnQueryGen {
+  int32_t B, N;
+  int32_t lat_size, lon_size;  /* fine grid nodes: 145, 257                                                   */
+  int32_t t_steps;             /* exclusive upper bound of the time draw: input_time_step * nums + 1 = 25      */
+  int32_t on_grid;             /* 0: interior (continuous x, y)   1: margin (integer grid nodes)               */
+  double dx, dy, dt;           /* metres per fine cell, seconds per time unit (3600)                           */
+  uint64_t seed, offset;
+} DpnQueryGen;
+
+int dpn_generate_queries(const DpnQueryGen *g, const DpnSampler *sampler, const float *coarse, float *x, float *y,
+                         float *t, float *coord_data, float *f, void *cuda_stream);
 
 /* Introspection for tests and bench: number of kernels the last call on this thread launched. */
 int dpn_last_launch_count(void);

@@ -27,6 +27,10 @@ def trilinear(coarse, x, y, t, dx=27000.0, dy=27000.0, cells_per_coarse=4.0, t_s
             for dx_ in (0, 1):
                 w = (wt if dt_ else 1 - wt) * (wy if dy_ else 1 - wy) * (wx if dx_ else 1 - wx)
                 out += w * coarse[it + dt_, iy + dy_, ix + dx_]
+    # outside the stack: NaN, as DataArray.interp / interpn(bounds_error=False) fill (no silent extrapolation)
+    eps = 1e-9
+    inside = ((gx >= -eps) & (gx <= Wc - 1 + eps) & (gy >= -eps) & (gy <= Hc - 1 + eps) & (gt >= -eps) & (gt <= Tt - 1 + eps))
+    out[~inside] = np.nan
     return out
 
 

@@ -25,7 +25,7 @@ def test_every_declared_symbol_is_exported():
     L = N.lib()
     for sym in declared:
         assert getattr(L, sym) is not None
-    assert L.dpn_abi_version() == 1
+    assert L.dpn_abi_version() == N.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header_sizes():
@@ -33,6 +33,7 @@ def test_struct_layouts_match_header_sizes():
     assert C.sizeof(N.DpnShape) == 32
     assert C.sizeof(N.DpnConsts) == 8 * 2 + 4 * 2 + 8 + 4 * 2 + 8 * 30 + 8 * 4 + 4 * 48
     assert C.sizeof(N.DpnPoints) == 7 * 8 and C.sizeof(N.DpnWeights) == 13 * 8 and C.sizeof(N.DpnPdeOut) == 3 * 8
+    assert C.sizeof(N.DpnMargin) == 5 * 8 and C.sizeof(N.DpnQueryGen) == 6 * 4 + 3 * 8 + 2 * 8 and C.sizeof(N.DpnSampler) == 6 * 4 + 7 * 8
 
 
 def test_argument_validation_without_gpu():

@@ -31,6 +31,10 @@ def _batch(seed=3, n_inter=160, n_margin=96):
                 margin_data=(0.5 * torch.randn(1, n_margin, 6, generator=g)).cuda())
 
 
+def _model_and_batch():
+    return _model(), _batch()
+
+
 def test_train_step_phases_and_update(tmp_path):
     from deepphysinet_b200.trainer import TrainStep
     m = _model()

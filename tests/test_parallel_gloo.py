@@ -37,6 +37,13 @@ def _worker(rank, world, port, q):
     P.FlatGradAllReduce(lin.parameters())()
     exp2 = sum(2 * r for r in range(world)) / world
     ok = ok and all(torch.allclose(p.grad, torch.full_like(p, exp2)) for p in lin.parameters())
+    # point sharding (level 2): partial gradients and partial loss terms ADD UP, no division by the world size
+    for p in lin.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    P.FlatGradAllReduce(lin.parameters(), op="sum")()
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, float(sum(range(1, world + 1))))) for p in lin.parameters())
+    tot, terms = P.reduce_partial_losses(torch.tensor(1.5 * (rank + 1)), torch.full((1, 6), float(rank + 1), dtype=torch.float64))
+    ok = ok and abs(float(tot) - 1.5 * sum(range(1, world + 1))) < 1e-6 and bool((terms == sum(range(1, world + 1))).all())
     # max-over-ranks timing reduction
     ok = ok and P.allreduce_max(float(rank), "cpu") == world - 1
     # sample sharding covers [0, n) exactly once

@@ -38,6 +38,40 @@ def test_oracle_matches_scipy_interpn():
         np.testing.assert_allclose(got[:, v], ref, rtol=1e-12, atol=1e-12)
 
 
+def _out_of_range_queries():
+    # x beyond the last node, negative y, t beyond the last slice (hours passed as if they were seconds x 3600 x 10), NaN, one good point
+    x = np.array([257 * 27000.0, 10 * 27000.0, 10 * 27000.0, np.nan, 10 * 27000.0])
+    y = np.array([10 * 27000.0, -1.0 * 27000.0, 10 * 27000.0, 10 * 27000.0, 10 * 27000.0])
+    t = np.array([3600.0, 3600.0, 240 * 3600.0, 3600.0, 3600.0])
+    return x, y, t
+
+
+def test_oracle_out_of_range_is_nan_like_interpn():
+    from scipy.interpolate import interpn
+    fld = _field()
+    x, y, t = _out_of_range_queries()
+    got = SO.trilinear(fld, x, y, t)
+    lat = np.arange(37.0); lon = np.arange(65.0); hrs = np.arange(5.0) * 6.0
+    pts = np.stack([y / 27000.0 / 4.0, x / 27000.0 / 4.0, t / 3600.0], 1)
+    data = np.transpose(fld[..., 0].astype(np.float64), (1, 2, 0))
+    ref = interpn((lat, lon, hrs), data, pts, method="linear", bounds_error=False, fill_value=np.nan)
+    assert np.array_equal(np.isnan(got[:, 0]), np.isnan(ref))
+    assert np.isnan(got[:4]).all() and np.isfinite(got[4]).all()
+    np.testing.assert_allclose(got[4, 0], ref[4], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_sampler_out_of_range_is_nan():
+    from deepphysinet_b200 import functional as Fn
+    fld = _field(seed=3)
+    x, y, t = _out_of_range_queries()
+    tt = lambda a: torch.tensor(a[None], dtype=torch.float32).cuda()
+    cd, _ = Fn.sample_field(torch.from_numpy(fld[None]).cuda(), tt(x), tt(y), tt(t))
+    cd = cd[0].cpu().numpy()
+    assert np.isnan(cd[:4]).all() and np.isfinite(cd[4]).all()
+    np.testing.assert_allclose(cd[4], SO.trilinear(fld, x[4:], y[4:], t[4:])[0], rtol=2e-6, atol=2e-6)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,N", [(1, 1), (2, 1000), (1, 4097)])
 def test_cuda_sampler_matches_oracle(B, N):
