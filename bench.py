@@ -104,20 +104,36 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_gpus=1):
-    """The reference's CPU path: oracle port (oracle/dpn_oracle.py, an autograd restatement of
-    InterfacePhysics.place_one_batch pinned to the reference's golden vectors) + the PyTorch encoder, all host
-    threads, one sample of n_points query points per step, backward included."""
+def _reference_step_factory(n_points, device):
+    """One fwd+bwd step of the reference's path on `device` for B=1 x n_points query points.  Returns (step, kind, threads):
+    kind "reference" = the UNMODIFIED reference - InterfacePhysics.place_one_batch (interface_physics.py:271-320) + backward(),
+    imported from its tree through oracle/ref_harness.py (stubs for GDAL / xarray only; present in the build container, absent
+    on a GPU box unless DPN_REFERENCE_ROOT points at a copy) - otherwise kind "port" = oracle/dpn_oracle.py (the restatement
+    pinned to the reference's golden vectors) + this package's PyTorch encoder."""
     import torch
-    from deepphysinet_b200.physics_net import PhysicsNet
     from oracle import dpn_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    net = PhysicsNet(META_CFG, NET_CFG)
+    from oracle import ref_harness as RH
     gen = torch.Generator().manual_seed(1234)
-    x, y, t, f, cd = O.synthetic_points(n_points, gen)
-    field = torch.randn(1, 159, 2405, generator=gen)
-    fh = torch.tensor([[[24.0 / 360.0]]])
+    x, y, t, f, cd = (a.to(device) for a in O.synthetic_points(n_points, gen))
+    field = torch.randn(1, 159, 2405, generator=gen).to(device)
+    if RH.available():
+        m, builder_loss, cfg = RH.build_reference_model(seed=0)
+        m = m.to(device)
+        crit = builder_loss(name="MSELoss")
+        lf = cfg["train_cfg"]["losses"]["loss_factor"]
+        fh = torch.tensor([[[24.0 / 360.0]]], device=device)
+
+        def step():
+            m.physics_net.zero_grad(set_to_none=True)
+            xs, ys, ts = (a.detach().clone().requires_grad_(True) for a in (x, y, t))
+            loss = m.place_one_batch(xs, ys, ts, f, field, cd, fh, crit, lf, 0, 0, device, None, "inter")
+            loss.backward()
+            return loss
+        return step, "reference", m
+    from deepphysinet_b200.physics_net import PhysicsNet
+    torch.manual_seed(0)
+    net = PhysicsNet(META_CFG, NET_CFG).to(device)
+    fh = torch.tensor([[[24.0 / 360.0]]], device=device)
     params = O.split_params(dict(net.named_parameters()))
 
     def step():
@@ -125,20 +141,31 @@ def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_g
         meta = net.meta_net(field, fh)
         total, _ = O.place_one_batch(x, y, t, f, cd, fh, meta, params)
         total.backward()
-        return float(total.detach())
+        return total
+    return step, "port", net
+
+
+def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_gpus=1):
+    """The reference's CPU path on all host threads, one sample of n_points query points per step, backward included
+    (the unmodified reference when its tree is present, else the oracle port: _reference_step_factory)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    step, kind, _keep = _reference_step_factory(n_points, "cpu")
+    what = ("unmodified reference InterfacePhysics.place_one_batch + backward" if kind == "reference"
+            else "oracle port of place_one_batch + backward")
 
     for _ in range(warmup):
         step()
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        step()
+        float(step().detach())
         times.append(time.perf_counter() - t0)
     if as_baseline:
         best = min(times)
-        return dict(value=n_points / best, unit=UNIT, cores=torch.get_num_threads(), kind="port",
-                    sample="B=1 x %d query points of the same workload, fwd+bwd incl. encoder, best of %d after %d warm-up"
-                           % (n_points, steps, warmup))
+        return dict(value=n_points / best, unit=UNIT, cores=torch.get_num_threads(), kind=kind,
+                    sample="B=1 x %d query points of the same workload, %s incl. encoder, best of %d after %d warm-up"
+                           % (n_points, what, steps, warmup))
     mean = sum(times) / len(times)
     val = n_points / mean
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": n_gpus, "steps": steps, "warmup": warmup,
@@ -146,8 +173,8 @@ def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_g
             "data": "synthetic",
             "config": {"workload": "configs[1] 0.25deg grid (145x257), batch 8 x 65536 query points - bounded CPU sample per step",
                        "sample_points_per_step": n_points},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "B=1 x %d query points per step, fwd+bwd incl. encoder" % n_points},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": "B=1 x %d query points per step, %s incl. encoder" % (n_points, what)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     if emit:
@@ -157,27 +184,12 @@ def cpu_reference_arm(steps, warmup, n_points, emit=True, as_baseline=False, n_g
 
 def eager_gpu_arm(dev, n_points):
     """The competitor on the same box: the reference's formulation - six nets, one autograd.grad(create_graph=True)
-    per derivative, double backward - executed by PyTorch eager on this GPU in fp32.  It is the oracle port moved to CUDA
-    (a baseline leg like cpu_baseline: reported beside the product, never part of it); B = 1 x n_points, decoder only
-    (the encoder output is computed once outside the timed region)."""
+    per derivative, double backward - executed by PyTorch eager on this GPU in fp32: the unmodified reference when its tree is
+    present (kind "reference"), else the oracle port moved to CUDA (kind "port").  A baseline leg like cpu_baseline: reported
+    beside the product, never part of it.  B = 1 x n_points, encoder included."""
     import torch
-    from deepphysinet_b200.physics_net import PhysicsNet
-    from oracle import dpn_oracle as O
-    torch.manual_seed(0)
-    net = PhysicsNet(META_CFG, NET_CFG).to(dev)
-    gen = torch.Generator().manual_seed(1234)
-    x, y, t, f, cd = (a.to(dev) for a in O.synthetic_points(n_points, gen))
-    field = torch.randn(1, 159, 2405, generator=gen).to(dev)
-    fh = torch.tensor([[[24.0 / 360.0]]], device=dev)
-    params = O.split_params(dict(net.named_parameters()))
-
-    def step():
-        net.zero_grad(set_to_none=True)
-        meta = net.meta_net(field, fh)
-        total, _ = O.place_one_batch(x, y, t, f, cd, fh, meta, params)
-        total.backward()
-
     try:
+        step, kind, _keep = _reference_step_factory(n_points, dev)
         for _ in range(2):
             step()
         torch.cuda.synchronize()
@@ -188,11 +200,11 @@ def eager_gpu_arm(dev, n_points):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
-        out = {"value": n_points / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
-               "sample": "B=1 x %d query points, PyTorch eager fp32 autograd double backward (oracle port on cuda), incl. encoder" % n_points}
+        out = {"value": n_points / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kind": kind,
+               "sample": "B=1 x %d query points, PyTorch eager fp32 autograd double backward (%s on cuda), incl. encoder" % (n_points, kind)}
+        del step, _keep
     except Exception as ex:                                                  # a baseline leg must never take the bench down
         out = {"unavailable": str(ex)[:200]}
-    del net, params
     torch.cuda.empty_cache()
     return out
 
