@@ -69,10 +69,12 @@ constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
 constexpr int GEN_IMG = 2 * IMG_HC + 4 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T, P, PT  (P = Wa W2, see FOLD below)
 constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
-constexpr int GEN_NP = 2 * IMG_HC + 2 * IMG_HH;    // per (sample, net), half-split layout for pass1_np_kernel: W1, W1T, W2, W2T
-constexpr int STA_NP = IMG_HC + 2 * IMG_HH;        // per net, half-split: Wd, Wa, WaT
-constexpr int NBLOB_H = 8, NBLOB_C = 2;             // per (net, tile): H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX
+// Workspace tile of one (net, point tile).  bf16 mode: H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX.  Split modes: UM YT QM ZH ZC | ZP ZD | AUX |
+// MASK - pass 2 runs as the forward pass of the combined row and needs only the two ReLU masks of pass 1
+// (2 x 256 bits per point) instead of the h1 / c / g tiles (3 x 1 KB per point).
+constexpr int NBLOB_H = 8, NBLOB_C = 2;
 enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
+constexpr int MASK_BYTES = 2 * TP * 32;       // [m1 | m3][128 rows][8 words]
 
 // Sizes that depend on the number of operand planes PL (1: bf16, 2: bf16 hi + lo).  Planes of one tile are contiguous,
 // in shared memory and in the workspace alike, so a tile still moves with one bulk copy.
@@ -82,13 +84,14 @@ struct Geo {
   static constexpr int ACT = BLOB_H * PL;                        // activation buffer: plane p at p * BLOB_H
   static constexpr int BH = BLOB_H * PL, BC = BLOB_C * PL;       // workspace blobs: plane p at p * BLOB_H (p * BLOB_C)
   static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
-  static constexpr size_t NET_TILE = (size_t)NBLOB_H * BH + (size_t)NBLOB_C * BC + AUX_BYTES;
+  static constexpr int NBH = PL == 2 ? 5 : NBLOB_H;              // [128 x 256] tiles kept per (net, tile)
+  static constexpr size_t NET_TILE = (size_t)NBH * BH + (size_t)NBLOB_C * BC + AUX_BYTES + (PL == 2 ? MASK_BYTES : 0);
   static constexpr int CTAS_PER_SM = PL == 1 ? 2 : 1;
   // FOLD (one CTA per SM, all 512 TMEM columns): two GEMMs that share their A operand run back to back into TWO accumulators and
   // share ONE epilogue round.  Pass 1: y = um Wa (G4) and q = um (Wa W2) + 2wo W2 (G5 with the pre-multiplied P = Wa W2) both read
   // the um tile; pass 2: ct = ht W2^T (G8) and gt = ht P^T (G9) both read the ht tile.  Same result, one MMA -> epilogue -> MMA
   // serialisation less per net in each pass.
-  static constexpr bool FOLD = PL == 2;
+  static constexpr bool FOLD = false;    // (round 1 used it for the shared-memory variants of the split modes; they are gone: TMEM is full in the TS form)
   static constexpr int TMEM_COLS = FOLD ? 512 : 256;
   // Epilogue warps: warps w, w+4, w+8, ... share the TMEM lanes 32 (w % 4) .. +31 and split the 256 columns into NQ groups.
   // 8 warps everywhere: 16 warps (column quarters) were measured for the one-CTA-per-SM split modes and LOSE 11 % - the 96-register
@@ -120,8 +123,6 @@ struct Work {
   // weight images
   const uint8_t* img_gen;  // [B][Kn][GEN_IMG]
   const uint8_t* img_sta;  // [Kn][STA_IMG]
-  const uint8_t* img_gen_np;   // [B][Kn][W1 W1T W2 W2T], half-split layout (pass1_np_kernel)
-  const uint8_t* img_sta_np;   // [Kn][Wd Wa WaT],        half-split layout
   // epilogue vectors (fp32)
   const float *b1, *bsum;  // [B][Kn][H]
   const float *ba, *uvec, *wo2, *cst;   // [Kn][H], cst [Kn]
@@ -145,10 +146,16 @@ template <int PL>
 __device__ __forceinline__ uint8_t* net_tile(const Work& w, int b, int k, int tl) {
   return w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * Geo<PL>::NET_TILE;
 }
-template <int PL> __device__ __forceinline__ uint8_t* blob_h(uint8_t* nt, int which) { return nt + (size_t)which * Geo<PL>::BH; }
-template <int PL> __device__ __forceinline__ uint8_t* blob_zp(uint8_t* nt) { return nt + (size_t)NBLOB_H * Geo<PL>::BH; }
-template <int PL> __device__ __forceinline__ uint8_t* blob_zd(uint8_t* nt) { return nt + (size_t)NBLOB_H * Geo<PL>::BH + Geo<PL>::BC; }
-template <int PL> __device__ __forceinline__ uint8_t* blob_aux(uint8_t* nt) { return nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC; }
+template <int PL> __host__ __device__ constexpr size_t off_h(int which) { return (size_t)(which - (PL == 2 ? (int)B_UM : 0)) * Geo<PL>::BH; }
+template <int PL> __host__ __device__ constexpr size_t off_zp() { return (size_t)Geo<PL>::NBH * Geo<PL>::BH; }
+template <int PL> __host__ __device__ constexpr size_t off_zd() { return off_zp<PL>() + Geo<PL>::BC; }
+template <int PL> __host__ __device__ constexpr size_t off_aux() { return off_zp<PL>() + 2 * Geo<PL>::BC; }
+template <int PL> __host__ __device__ constexpr size_t off_mask() { return off_aux<PL>() + AUX_BYTES; }
+template <int PL> __device__ __forceinline__ uint8_t* blob_h(uint8_t* nt, int which) { return nt + off_h<PL>(which); }
+template <int PL> __device__ __forceinline__ uint8_t* blob_zp(uint8_t* nt) { return nt + off_zp<PL>(); }
+template <int PL> __device__ __forceinline__ uint8_t* blob_zd(uint8_t* nt) { return nt + off_zd<PL>(); }
+template <int PL> __device__ __forceinline__ uint8_t* blob_aux(uint8_t* nt) { return nt + off_aux<PL>(); }
+template <int PL> __device__ __forceinline__ uint8_t* blob_mask(uint8_t* nt) { return nt + off_mask<PL>(); }
 
 // ------------------------------------------------------------------------------------------------
 // Small helpers
@@ -988,12 +995,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       epi_bar<PL>();
       if (tid < H) load_vectors(svec, w, b, k, tid);
       epi_bar<PL>();
-      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f;
+      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sUM = 1.f, sY = 1.f;
       if (F16) {
         const NetScales t = w.sc[b * w.Kn + k];
         i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / (t.sUM * t.sWa);
         i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
-        sH1 = t.sH1; sC = t.sC; sG = t.sG; sUM = t.sUM; sY = t.sY;
+        sH1 = t.sH1; sC = t.sC; sUM = t.sUM; sY = t.sY;
       }
       uint32_t m1w[NB];
 #pragma unroll
@@ -1019,7 +1026,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
-        emit(cg, v, sweep ? blob_h<PL>(nt, B_H1) : nullptr, true);
+        emit(cg, v, nullptr, true);                                   // h1 itself is not kept: pass 2 needs only its mask
       }
       done();
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
@@ -1042,37 +1049,44 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
             v[j4 * 4 + e] = F16 ? cc * sC : cc;
           }
         }
-        emit(cg, v, sweep ? blob_h<PL>(nt, B_CC) : nullptr, true);
+        emit(cg, v, nullptr, true);
       }
       done();
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
+      uint32_t m3w[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) m3w[i] = 0u;
       acc_wait();
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
         tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0u;
 #pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          float g8[8];
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cg * 32 + j4 * 4);
+          const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cg * 32 + j4 * 4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cg * 32 + qd * 8 + h2 * 4);
-            const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cg * 32 + qd * 8 + h2 * 4);
-            const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = qd * 8 + h2 * 4 + e;
-              const float a = F16 ? fmaf(v[j], i3, bb[e]) : v[j] + bb[e];
-              const float gg = fmaxf(a, 0.f);
-              if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
-              g8[h2 * 4 + e] = F16 ? gg * sG : gg;
-              v[j] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;          // um replaces the accumulator value in place
-            }
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            const float a = F16 ? fmaf(v[j], i3, bb[e]) : v[j] + bb[e];
+            const float gg = fmaxf(a, 0.f);
+            if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
+            bits |= (a > 0.f ? 1u : 0u) << j;
+            v[j] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;          // um replaces the accumulator value in place
           }
-          if (sweep) stg8<PL, F16>(blob_h<PL>(nt, B_GG), BLOB_H, gp_off(32, r, cg * 4 + qd), g8);
         }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) m3w[i] = (cb == i) ? bits : m3w[i];
         if (sweep) emit(cg, v, blob_h<PL>(nt, B_UM), true);
+      }
+      if (sweep) {                                                     // the two ReLU masks of this (net, tile): all pass 2 needs of h1 / c / g
+        uint4* mk = reinterpret_cast<uint4*>(blob_mask<PL>(nt));
+        static_assert(NB == 4, "one uint4 of mask words per thread");
+        mk[r * 2 + half] = make_uint4(m1w[0], m1w[1], m1w[2], m1w[3]);
+        mk[(TP + r) * 2 + half] = make_uint4(m3w[0], m3w[1], m3w[2], m3w[3]);
       }
       atomicAdd(rowsum + r * 4, os0 + os1);
       done();
@@ -1153,8 +1167,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   if (CLUSTER > 1) cluster_sync_all();
   if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 512);
 }
-
-#include "dpn_tc_np.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // Pass 2: the combined tangent row, the Z-side operands of the weight gradients and three column sums.
@@ -1421,6 +1433,344 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pass 2 of the split modes as the FORWARD PASS OF THE COMBINED ROW.
+// The Z-side operands of the weight gradients are  zh = dov h1 + ht,  zc = dov c + ct,  gz = dov g + gt  with the tangent chain
+// ht = (xt W1^T) m1, ct = ht W2^T, gt = (ct Wa^T) m3.  Because h1 = m1 (PE W1^T + b1), c = h1 W2^T + PE6 Wd^T + bsum and
+// g = m3 (c Wa^T + ba) are (masked) affine in their inputs, the sums collapse:
+//        zh = m1 ( zp W1^T + dov b1 )            zp = dov PE + xt   (the operand of dW1, computed by the prologue anyway)
+//        zc = zh W2^T + zd Wd^T + dov bsum       zd = dov PE6       (the operand of dWd)
+//        gz = m3 ( zc Wa^T + dov ba )
+// i.e. pass 2 is pass 1's value chain applied to the row zp with the FROZEN masks and dov-scaled biases.  It needs from pass 1
+// two bit masks per point (64 bytes) instead of the h1 / c / g tiles (3 KB), no separate tangent row, and every tile it produces
+// is at once the next A operand and the stored wgrad operand (one split instead of two).
+// Structure = pass1_ts_kernel: accumulator TMEM [0,256), A planes [256,384) | [384,512), TS-form MMAs; the zd tile is staged in
+// shared memory (96 KB, layout (*)) as the A operand of the K = 192 accumulate of G8; 7 x 16 KB weight ring.
+// ------------------------------------------------------------------------------------------------
+namespace p2z {
+constexpr int NS = 7;
+constexpr int W_BYTES = 2 * STAGE_BYTES;         // one K = 16 chunk of a [256 x K] image: hi 8 KB | lo 8 KB
+constexpr int ZD_BYTES = 2 * BLOB_C;             // zd staging: plane hi | plane lo, [128 x 192] each, layout (*)
+enum { V2_B1 = 0, V2_BSUM, V2_BA, NV2 };
+constexpr int SMEM = NS * W_BYTES + ZD_BYTES + NV2 * H * 4 + 2 * H * 4 + 16;      // + column sums [zc | gz] + sum of dov
+constexpr uint32_t COL_AH = 256, COL_AL = 384;
+struct PipeZ {
+  uint64_t full[NS], empty[NS], a_epi, acc_ready;
+  uint32_t tmem_base;
+};
+static_assert(SMEM + (int)sizeof(PipeZ) + 1024 <= 227 * 1024, "pass2z_kernel: ring + zd tile + vectors must fit one SM's 227 KB");
+}  // namespace p2z
+
+template <bool F16>
+__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREADS, 1) pass2z_kernel(const Work w) {
+  constexpr int PL = 2;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ p2z::PipeZ pipe;
+  uint8_t* ring = smem;
+  uint8_t* zdt = smem + p2z::NS * p2z::W_BYTES;
+  float* svec = reinterpret_cast<float*>(zdt + p2z::ZD_BYTES);
+  float* csum = svec + p2z::NV2 * H;                               // [2][H] + sdo
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
+  const size_t g = blockIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < p2z::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
+    mbar_init(&pipe.a_epi, Geo<PL>::ET);
+    mbar_init(&pipe.acc_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == Geo<PL>::W_MMA) tmem_alloc(&pipe.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (CLUSTER > 1) cluster_sync_all();
+  const uint32_t tmem = pipe.tmem_base;
+  const uint32_t rank = cluster_ctarank();
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1);
+
+  if (warp == Geo<PL>::W_PROD) {
+    // ---------------- producer: weight chunks (multicast slices) ----------------
+    uint32_t s = 0, ph = 0;
+    const uint64_t pol = l2_policy_evict_last();
+    auto put = [&](const uint8_t* wsrc) {
+      mbar_wait(&pipe.empty[s], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* stg = ring + s * p2z::W_BYTES;
+        mbar_arrive_expect_tx(&pipe.full[s], p2z::W_BYTES);
+        if (CLUSTER == 1) {
+          bulk_g2s_hint(stg, wsrc, p2z::W_BYTES, &pipe.full[s], pol);
+        } else {
+          constexpr uint32_t slice = p2z::W_BYTES / CLUSTER;
+          bulk_g2s_mc_hint(stg + rank * slice, wsrc + rank * slice, slice, &pipe.full[s], MC_MASK, pol);
+        }
+      }
+      if (++s == p2z::NS) { s = 0; ph ^= 1; }
+    };
+    for (int k = 0; k < w.Kn; ++k) {
+      const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
+      const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
+      const uint8_t *iW1 = gen, *iW2 = gen + PL * 2 * IMG_HC, *iWd = sta, *iWa = sta + PL * IMG_HC;
+      for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * p2z::W_BYTES);
+      for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * p2z::W_BYTES);
+      for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * p2z::W_BYTES);
+      for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * p2z::W_BYTES);
+    }
+  } else if (warp == Geo<PL>::W_MMA) {
+    // ---------------- MMA issuer ----------------
+    uint32_t s = 0, ph = 0, ae = 0;
+    const uint32_t ring_addr = smem_u32(ring);
+    const uint32_t idesc = idesc_16(F16, H, 0, 0, 128);
+    const uint64_t b_base = smem_desc(ring_addr, H * 16, 128);
+    const uint64_t zd_base = smem_desc(smem_u32(zdt), CORE_STRIDE, 128);
+    constexpr uint32_t b_lo = (uint32_t)(H * 32) >> 4, zd_lo = BLOB_C >> 4, zd_step = (2 * CORE_STRIDE) >> 4;
+    auto gemm = [&](const int nchunks, const bool a_in_tmem, const bool accumulate) {
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(&pipe.full[s], ph);
+        tc_fence_after();
+        const uint64_t bd = b_base + s * (uint32_t)(p2z::W_BYTES >> 4), bl = bd + b_lo;
+        const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
+        if (elect_one()) {
+          if (a_in_tmem) {                               // lo*hi + hi*lo + hi*hi, A planes from tensor memory
+            mma_ts(tmem, tmem + p2z::COL_AL + 8 * c, bd, idesc, first);
+            mma_ts(tmem, tmem + p2z::COL_AH + 8 * c, bl, idesc, 1u);
+            mma_ts(tmem, tmem + p2z::COL_AH + 8 * c, bd, idesc, 1u);
+          } else {                                       // A = K-slice c of the zd tile in shared memory
+            const uint64_t ad = zd_base + (uint32_t)c * zd_step, al = ad + zd_lo;
+            mma_bf16(tmem, al, bd, idesc, first);
+            mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bl, idesc, 1u);
+            mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem, ad, bd, idesc, 1u);
+          }
+          if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
+        }
+        if (++s == p2z::NS) { s = 0; ph ^= 1; }
+      }
+    };
+    auto wait_epi = [&]() { mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
+    auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready); };
+    for (int k = 0; k < w.Kn; ++k) {
+      wait_epi();                                                          // prologue: zp in tensor memory, zd in shared memory
+      gemm(12, true, false); ready();                                      // G7' = zp W1^T
+      wait_epi();
+      gemm(16, true, false); gemm(12, false, true); ready();               // G8' = zh W2^T + zd Wd^T
+      wait_epi();
+      gemm(16, true, false); ready();                                      // G9' = zc Wa^T
+    }
+  } else if (warp < Geo<PL>::EW) {
+    // ---------------- prologue + epilogues: thread = (point r, column half) ----------------
+    constexpr int NB = Geo<PL>::NB;
+    const int half = warp >> 2, r = (warp & 3) * 32 + lane, c0 = half * NB;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t tl_addr = lane_base + half * (NB * 32);
+    const size_t row = g * TP + r;
+    const float* pet = w.pet + g * (size_t)(C * TP) + r;
+    const uint8_t* pe6 = w.pe6_blob + g * Geo<PL>::BC;
+    const uint64_t pol_keep = l2_policy_evict_last();
+    uint32_t ar = 0;
+    auto done = [&]() { tmem_st_wait(); tc_fence_before(); fence_proxy_async(); mbar_arrive(&pipe.a_epi); };
+    auto acc_wait = [&]() { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
+    // 32 columns of this row, already scaled: split once -> workspace tile (wgrad operand) and / or the next A operand in TMEM
+    auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        uint4 pq[PL];
+        split8<PL, F16>(v + qd * 8, pq);
+        if (blob) {
+          const uint32_t off = gp_off(32, r, cg * 4 + qd);
+          __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
+          __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
+        }
+        hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
+        lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
+      }
+      if (to_a) {
+        tmem_st16(lane_base + p2z::COL_AH + cg * 16, hi);
+        tmem_st16(lane_base + p2z::COL_AL + cg * 16, lo);
+      }
+    };
+    for (int i = tid; i < 2 * H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
+    for (int k = 0; k < w.Kn; ++k) {
+      uint8_t* nt = net_tile<PL>(w, b, k, tl);
+      epi_bar<PL>();                                                   // previous net's vectors / column sums are flushed
+      if (tid < H) {
+        const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+        svec[p2z::V2_B1 * H + tid] = __ldg(w.b1 + vb + tid);
+        svec[p2z::V2_BSUM * H + tid] = __ldg(w.bsum + vb + tid);
+        svec[p2z::V2_BA * H + tid] = __ldg(w.ba + vk + tid);
+      }
+      epi_bar<PL>();
+      const float dv = w.dov[row * w.Kn + k];
+      float dd[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];          // zero for the values-only backward
+      const uint4 m1q = __ldg(reinterpret_cast<const uint4*>(blob_mask<PL>(nt)) + r * 2 + half);
+      const uint4 m3q = __ldg(reinterpret_cast<const uint4*>(blob_mask<PL>(nt)) + (TP + r) * 2 + half);
+      const uint32_t m1w[4] = {m1q.x, m1q.y, m1q.z, m1q.w}, m3w[4] = {m3q.x, m3q.y, m3q.z, m3q.w};
+      // fp16 variant: every tile carries one power-of-two scale per (sample, net) (zscale_kernel); accumulators carry
+      // (A tile scale) x (weight image scale) and i7 / i8 / i9 undo that
+      // zd exists twice: the stored tile (wgrad operand of dWd) with its own scale sZD, and the A operand of G8' whose scale is tied
+      // to the accumulator it shares with zh W2^T: sZH sW2 = sZDa sWd, and plan_kernel made sH1 sW2 = S_PE sWd  =>  sZDa = sZH S_PE / sH1
+      float sZP = 1.f, sZH = 1.f, sZC = 1.f, sZD = 1.f, sZDa = 1.f, sDV = 1.f, i7 = 1.f, i8 = 1.f, i9 = 1.f;
+      if (F16) {
+        const NetScales t = w.sc[b * w.Kn + k];
+        sZP = t.sZP; sZH = t.sZH; sZC = t.sZC; sZD = t.sZD; sDV = t.sDV;
+        sZDa = t.sZH * (S_PE / t.sH1);
+        i7 = (1.f / t.sZP) * (1.f / t.sW1); i8 = (1.f / t.sZH) * (1.f / t.sW2); i9 = (1.f / t.sZC) * (1.f / t.sWa);
+      }
+      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three 16-bit terms, rest 0
+      if (half == 0) {
+        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (F16) {
+          const float x = dv * sDV;
+          a8[0] = __half2float(__float2half_rn(x));
+          a8[1] = __half2float(__float2half_rn(x - a8[0]));
+          a8[2] = (x - a8[0]) - a8[1];
+        } else {
+          a8[0] = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
+          a8[1] = __uint_as_float(__float_as_uint(dv - a8[0]) & 0xFFFF0000u);
+          a8[2] = (dv - a8[0]) - a8[1];
+        }
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + gp_off(2, r, 0)), pack8f<F16>(a8));
+        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + gp_off(2, r, 1)), make_uint4(0u, 0u, 0u, 0u));
+      }
+      // ---- prologue: zp = dov PE + sum_c dod_c dPE_c -> A operand (TMEM) + workspace;  zd = dov PE6 -> shared memory + workspace ----
+#pragma unroll 1
+      for (int it = half * NB; it < half * NB + NB; ++it) {          // 24 columns = 4 frequencies = 3 pieces = 12 packed words per plane
+        float pe[24], zp[24];
+        uint4 p6[3][PL];
+#pragma unroll
+        for (int j = 0; j < 24; ++j) pe[j] = ldg_f32_hint(pet + (size_t)(it * 24 + j) * TP, pol_keep);
+#pragma unroll
+        for (int qd = 0; qd < 3; ++qd)
+#pragma unroll
+          for (int p = 0; p < PL; ++p) p6[qd][p] = ldg_v4_hint(pe6 + p * BLOB_C + piece_off(r, it * 3 + qd), pol_keep);
+#pragma unroll
+        for (int j = 0; j < 24; ++j) {
+          const int J = it * 24 + j;                                  // it*24 is a multiple of 6: the partner stays inside the block
+          const float xt = dd[j % 3] * (DPE_SIGN(j) * w.band[J / 6]) * pe[DPE_PARTNER(j)];
+          zp[j] = fmaf(dv, pe[j], xt);
+          if (F16) zp[j] *= sZP;
+        }
+        uint32_t hi[12], lo[12];
+#pragma unroll
+        for (int qd = 0; qd < 3; ++qd) {
+          uint4 pq[PL];
+          split8<PL, F16>(zp + qd * 8, pq);
+          const uint32_t goff = gp_off(24, r, it * 3 + qd);
+          __stcs(reinterpret_cast<uint4*>(blob_zp<PL>(nt) + goff), pq[0]);
+          __stcs(reinterpret_cast<uint4*>(blob_zp<PL>(nt) + BLOB_C + goff), pq[1]);
+          hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
+          lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
+          float d6[8], da[8];
+          unpack_planes<PL, F16>(p6[qd], d6);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { da[e] = F16 ? d6[e] * (dv * (sZDa / S_PE)) : d6[e] * dv; d6[e] *= F16 ? dv * (sZD / S_PE) : dv; }
+          split8<PL, F16>(d6, pq);
+          __stcs(reinterpret_cast<uint4*>(blob_zd<PL>(nt) + goff), pq[0]);
+          __stcs(reinterpret_cast<uint4*>(blob_zd<PL>(nt) + BLOB_C + goff), pq[1]);
+          if (F16) split8<PL, F16>(da, pq);                           // (bf16x3: no scales, the same planes serve both)
+          const uint32_t soff = piece_off(r, it * 3 + qd);
+          *reinterpret_cast<uint4*>(zdt + soff) = pq[0];
+          *reinterpret_cast<uint4*>(zdt + BLOB_C + soff) = pq[1];
+        }
+        tmem_st8(lane_base + p2z::COL_AH + it * 12, hi); tmem_st4(lane_base + p2z::COL_AH + it * 12 + 8, hi + 8);
+        tmem_st8(lane_base + p2z::COL_AL + it * 12, lo); tmem_st4(lane_base + p2z::COL_AL + it * 12 + 8, lo + 8);
+      }
+      done();
+      // ---- epilogue 7: zh = m1 (acc + dov b1) ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(svec + p2z::V2_B1 * H + cg * 32 + j4 * 4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            const float z = F16 ? fmaf(v[j], i7, dv * bb[e]) : fmaf(dv, bb[e], v[j]);
+            v[j] = ((bits >> j) & 1u) ? (F16 ? z * sZH : z) : 0.f;
+          }
+        }
+        emit(cg, v, blob_h<PL>(nt, B_ZH), true);
+      }
+      done();
+      // ---- epilogue 8: zc = acc + dov (b2 + bd + e);  column sum -> vc ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32], z[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(svec + p2z::V2_BSUM * H + cg * 32 + j4 * 4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            z[j] = F16 ? fmaf(v[j], i8, dv * bb[e]) : fmaf(dv, bb[e], v[j]);
+            v[j] = F16 ? z[j] * sZC : z[j];
+          }
+        }
+        emit(cg, v, blob_h<PL>(nt, B_ZC), true);
+        const float cs = warp_colsum32(z, lane);
+        atomicAdd(csum + cg * 32 + lane, cs);
+      }
+      done();
+      // ---- epilogue 9: gz = m3 (acc + dov ba);  column sum -> vg ----
+      acc_wait();
+#pragma unroll 1
+      for (int cb = 0; cb < NB; ++cb) {
+        const int cg = c0 + cb;
+        float v[32];
+        tmem_ld32(tl_addr + cb * 32, v);
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) bits = (cb == i) ? m3w[i] : bits;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 bv = *reinterpret_cast<const float4*>(svec + p2z::V2_BA * H + cg * 32 + j4 * 4);
+          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = j4 * 4 + e;
+            const float z = F16 ? fmaf(v[j], i9, dv * bb[e]) : fmaf(dv, bb[e], v[j]);
+            v[j] = ((bits >> j) & 1u) ? z : 0.f;
+          }
+        }
+        const float cs = warp_colsum32(v, lane);
+        atomicAdd(csum + H + cg * 32 + lane, cs);
+      }
+      // ---- flush this net's column sums ----
+      if (half == 0) {
+        float sd = dv;
+#pragma unroll
+        for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
+        if (lane == 0) atomicAdd(csum + 2 * H, sd);
+      }
+      epi_bar<PL>();
+      for (int i = tid; i < 2 * H; i += Geo<PL>::ET) {
+        float* dstv = i < H ? w.vc : w.vg;
+        atomicAdd(dstv + (size_t)k * H + (i % H), csum[i]);
+        csum[i] = 0.f;
+      }
+      if (tid == 0) { atomicAdd(w.sdo + k, csum[2 * H]); csum[2 * H] = 0.f; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all();
+  if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Weight gradients: D[out-half (128 lanes) x in (N cols)] += sum over points  J[p,out] Z[p,in]
 // Both operands are MN-major views of the stored [128 points x width] blobs.  One CTA per
 // (sample, net, layer, out-half, split); single smem stage, 2 CTAs per SM interleave load and MMA.
@@ -1625,12 +1975,11 @@ __global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
       for (int i = 0; i < nst; ++i) {
         const int t = t0 + (i >> 1), ph = i & 1;                      // tile, point half
         const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
-        const uint8_t* jsrc = nt + (size_t)jsel * Geo<PL>::BH + (size_t)ph * (BLOB_H / 2) + (size_t)mh * wg2::J_PLANE;
-        const uint8_t* zsrc = (layer == 0 ? nt + (size_t)NBLOB_H * Geo<PL>::BH
-                             : layer == 3 ? nt + (size_t)NBLOB_H * Geo<PL>::BH + Geo<PL>::BC
-                             : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * Geo<PL>::BH) + (size_t)ph * zplane;
+        const uint8_t* jsrc = nt + off_h<PL>(jsel) + (size_t)ph * (BLOB_H / 2) + (size_t)mh * wg2::J_PLANE;
+        const uint8_t* zsrc = (layer == 0 ? nt + off_zp<PL>() : layer == 3 ? nt + off_zd<PL>()
+                             : nt + off_h<PL>(layer == 1 ? B_ZH : B_ZC)) + (size_t)ph * zplane;
         const uint32_t zstride = (layer == 0 || layer == 3) ? BLOB_C : BLOB_H;     // plane stride of the Z tile in the workspace
-        const uint8_t* xsrc = nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC + (size_t)ph * wg2::X_BYTES;
+        const uint8_t* xsrc = nt + off_aux<PL>() + (size_t)ph * wg2::X_BYTES;
         const int s = i & 1;
         uint8_t* st = smem + s * wg2::STAGE;
         mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
@@ -1803,7 +2152,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
   }
   float r2 = 0.f, c2 = 0.f, m2 = 0.f, ra = 0.f, ca = 0.f, ma = 0.f, mp = 0.f;
   for (int i = 0; i < H; ++i) {
-    mp = fmaxf(mp, fabsf(P[((size_t)bk * H + j) * H + i]));
+    if (P) mp = fmaxf(mp, fabsf(P[((size_t)bk * H + j) * H + i]));
     const float x2 = fabsf(w2[(size_t)j * H + i]), y2 = fabsf(w2[(size_t)i * H + j]);
     const float xa = fabsf(wa[(size_t)j * H + i]), ya = fabsf(wa[(size_t)i * H + j]);
     r2 += x2; c2 += y2; m2 = fmaxf(m2, x2); ra += xa; ca += ya; ma = fmaxf(ma, xa);
@@ -1890,7 +2239,7 @@ __global__ void zscale_kernel(int n, const int* __restrict__ seedmax, NetScales*
 // [hi plane | lo plane], so the producer still fetches one contiguous block per chunk.
 template <int PL, bool F16>
 __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
-                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which, int split) {
+                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which) {
   const float* S = src + blockIdx.y * src_stride;
   uint8_t* D = dst + blockIdx.y * dst_stride;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;             // 16-byte piece index
@@ -1907,9 +2256,9 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   }
   uint4 pq[PL];
   split8<PL, F16>(v, pq);
-  // chunk = [first half of the rows | second half] (PAIR: each CTA of a pair stages its half of the rows; split: the N-half pipeline of
-  // pass1_np_kernel streams (chunk, half) pieces), each part [hi plane | lo plane], each plane two k-cores of (part rows) x 16 bytes
-  const int prows = (PAIR || split) ? rows / 2 : rows, part = r / prows, rr = r % prows;
+  // chunk = [rows of CTA 0 | rows of CTA 1] (PAIR: each CTA of a pair stages its half of the rows), each part [hi plane | lo plane],
+  // each plane two k-cores of (part rows) x 16 bytes
+  const int prows = PAIR ? rows / 2 : rows, part = r / prows, rr = r % prows;
   const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)part * PL * prows * 32 + (size_t)(kc & 1) * prows * 16 + (size_t)rr * 16;
 #pragma unroll
   for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * prows * 32) = pq[p];
@@ -2013,7 +2362,7 @@ __global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
 // Workspace and driver
 // ------------------------------------------------------------------------------------------------
 struct Carve {
-  uint8_t *img_gen, *img_sta, *img_gen_np, *img_sta_np, *pe_blob, *pe6_blob, *blobs;
+  uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
   float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo, *P, *c2;
   long long* dbg;
   NetScales* sc;
@@ -2030,8 +2379,6 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B, int pl) {
   auto take = [&](size_t bytes) { uint8_t* p = base + off; off += al(bytes); return p; };
   c.img_gen = take((size_t)B * Kn * GEN_IMG * pl);
   c.img_sta = take((size_t)Kn * STA_IMG * pl);
-  c.img_gen_np = take(pl == 2 ? (size_t)B * Kn * GEN_NP * pl : 0);
-  c.img_sta_np = take(pl == 2 ? (size_t)Kn * STA_NP * pl : 0);
   c.pe_blob = take((size_t)B * T * BLOB_C * pl);
   c.pe6_blob = take((size_t)B * T * BLOB_C * pl);
   c.pet = reinterpret_cast<float*>(take((size_t)B * T * C * TP * 4));
@@ -2066,33 +2413,22 @@ int default_chunk(int B, int planes) {
 size_t workspace_bytes(int chunk, int Kn, int B, int planes) { return carve(nullptr, chunk, Kn, B, planes).bytes; }
 
 template <int PL, bool F16>
-static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, bool use_np, cudaStream_t st) {
-  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; int split; };
-  const int np = (PL == 2 && use_np) ? 1 : 0;                          // pass 1 of the split modes reads half-split images
+static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
+  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; };
   const Spec specs[] = {
-      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0, 0},                       // W1  : rows = out, k = in
-      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, np ? 0 : B * Kn, c.img_gen, 0, 0},         // W1T : rows = in,  k = out
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1, 0},
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, np ? 0 : B * Kn, c.img_gen, 1, 0},
-      {c.P, (size_t)H * H, 2 * IMG_HC + 2 * IMG_HH, GEN_IMG, H, H, 0, PL == 2 ? B * Kn : 0, c.img_gen, 4, 0},   // P  : rows = a3 index, k = a1 index (pass 2, G9)
-      {c.P, (size_t)H * H, 2 * IMG_HC + 3 * IMG_HH, GEN_IMG, H, H, 1, (PL == 2 && !np) ? B * Kn : 0, c.img_gen, 4, 0},   // PT : pass1_kernel<2> FOLD only
-      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, np ? 0 : Kn, c.img_sta, 2, 0},
-      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, np ? 0 : Kn, c.img_sta, 3, 0},
-      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, np ? 0 : Kn, c.img_sta, 3, 0},
-      // half-split images of pass1_np_kernel
-      {Wt.W1, (size_t)H * C, 0, GEN_NP, H, C, 0, np ? B * Kn : 0, c.img_gen_np, 0, 1},
-      {Wt.W1, (size_t)H * C, IMG_HC, GEN_NP, C, H, 1, np ? B * Kn : 0, c.img_gen_np, 0, 1},
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_NP, H, H, 0, np ? B * Kn : 0, c.img_gen_np, 1, 1},
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_NP, H, H, 1, np ? B * Kn : 0, c.img_gen_np, 1, 1},
-      {Wt.Wd, (size_t)H * C, 0, STA_NP, H, C, 0, np ? Kn : 0, c.img_sta_np, 2, 1},
-      {Wt.Wa, (size_t)H * H, IMG_HC, STA_NP, H, H, 0, np ? Kn : 0, c.img_sta_np, 3, 1},
-      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_NP, H, H, 1, np ? Kn : 0, c.img_sta_np, 3, 1},
+      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0},                       // W1  : rows = out, k = in
+      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0},                  // W1T : rows = in,  k = out
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen, 1},
+      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta, 2},
+      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta, 3},
+      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta, 3},
   };
   for (const Spec& s : specs) {
     if (s.batches == 0) continue;
     const int pieces = s.rows * s.kd / 8;
     image_kernel<PL, F16><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
-                                                                                 s.rows, s.kd, s.tr, c.sc, s.which, s.split);
+                                                                                 s.rows, s.kd, s.tr, c.sc, s.which);
     DPN_LAUNCH_OK();
   }
   return 0;
@@ -2102,20 +2438,18 @@ template <int PL, bool F16>
 static int run_planes(const Job& J, cudaStream_t st) {
   const int B = J.shape.B, N = J.shape.N, Kn = J.shape.K, chunk = J.chunk;
   const int smem_fused = tc::smem_fused<PL>(), smem_pass2 = tc::smem_pass2<PL>(), smem_wgrad = tc::smem_wgrad<PL>();
-  // split modes: pass 1 as the N-half pipeline (pass1_np_kernel, default) or the strict chain (pass1_ts_kernel, DPN_P1=ts: A/B only)
-  static const bool use_np = !(getenv("DPN_P1") && strcmp(getenv("DPN_P1"), "ts") == 0);
   {
     // function attributes are per device: set them once for every device this process drives (bit d of the mask)
     static std::atomic<unsigned long long> attr_done_mask{0ull};
     int dev = 0;
     DPN_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
-      DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
       if constexpr (PL == 2) {
         DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_np_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, np::SMEM));
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass2z_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2z::SMEM));
         DPN_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM));
       } else {
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
         DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
         DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
       }
@@ -2137,19 +2471,19 @@ static int run_planes(const Job& J, cudaStream_t st) {
   constexpr bool phase_debug = false;
 #endif
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
-  if (Geo<PL>::FOLD || F16) {                                         // (the scaling plan reads P even when the kernels do not)
+  if (Geo<PL>::FOLD) {
     pfold_kernel<<<dim3(H / 32, H / 32, B * Kn), 256, 0, st>>>(Kn, Wt.Wa, Wt.W2, c.P);
     DPN_LAUNCH_OK();
     c2_kernel<<<B * Kn, 256, 0, st>>>(Kn, c.wo2, Wt.W2, c.c2);
     DPN_LAUNCH_OK();
   }
   if (F16) {                                                          // scaling plan before anything is converted to fp16
-    bounds_kernel<<<B * Kn, 256, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, c.P, c.sc);
+    bounds_kernel<<<B * Kn, 256, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, Geo<PL>::FOLD ? c.P : nullptr, c.sc);
     DPN_LAUNCH_OK();
     plan_kernel<<<1, 32, 0, st>>>(B, Kn, c.sc);
     DPN_LAUNCH_OK();
   }
-  if ((rc = make_images<PL, F16>(Wt, c, B, Kn, use_np, st))) return rc;
+  if ((rc = make_images<PL, F16>(Wt, c, B, Kn, st))) return rc;
   if (pde) DPN_CUDA_OK(cudaMemsetAsync(J.out->loss_terms, 0, sizeof(double) * 6 * B, st));
   if (pde && J.margin) DPN_CUDA_OK(cudaMemsetAsync(J.margin->loss, 0, sizeof(double) * B, st));
   if (want_bwd) {
@@ -2176,7 +2510,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     Work w;
     memset(&w, 0, sizeof(w));
     w.B = B; w.Kn = Kn; w.T = T; w.P = P; w.N = N; w.p0 = p0;
-    w.img_gen = c.img_gen; w.img_sta = c.img_sta; w.img_gen_np = c.img_gen_np; w.img_sta_np = c.img_sta_np;
+    w.img_gen = c.img_gen; w.img_sta = c.img_sta;
     w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst; w.c2 = c.c2;
     w.coord_data = J.pts->coord_data; w.ref = J.pts->ref;
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
@@ -2192,8 +2526,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t, J.pts->coord_pe);
     DPN_LAUNCH_OK();
     if constexpr (PL == 2) {                      // split modes: the A operand lives in tensor memory
-      if (use_np) pass1_np_kernel<F16><<<tiles, Geo<2>::THREADS, np::SMEM, st>>>(w, sweep);
-      else pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
+      pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
     } else {
       pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
     }
@@ -2232,7 +2565,8 @@ static int run_planes(const Job& J, cudaStream_t st) {
       zscale_kernel<<<(B * Kn + 63) / 64, 64, 0, st>>>(B * Kn, c.seedmax, c.sc);
       DPN_LAUNCH_OK();
     }
-    pass2_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
+    if constexpr (PL == 2) pass2z_kernel<F16><<<tiles, Geo<2>::THREADS, p2z::SMEM, st>>>(w);
+    else pass2_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc;
@@ -2262,15 +2596,6 @@ static int run_planes(const Job& J, cudaStream_t st) {
     DPN_LAUNCH_OK();
   }
 #ifdef DPN_DEBUG_BUILD
-  if (phase_debug && PL == 2 && use_np) {
-    long long h[16];
-    DPN_CUDA_OK(cudaStreamSynchronize(st));
-    DPN_CUDA_OK(cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost));
-    const double n1 = h[6] > 0 ? (double)h[6] : 1.0;
-    fprintf(stderr, "[dpn phase] pass1_np per CTA (cycles): mma-warp total %.0f | wait ring %.0f | wait epilogue %.0f || "
-                    "epilogue-thread total %.0f | wait accumulator %.0f | working %.0f || producer wait empty %.0f\n",
-            h[0] / n1, h[1] / n1, h[2] / n1, h[4] / n1, h[5] / n1, h[7] / n1, h[3] / n1);
-  }
   if (phase_debug) {
     long long h[16];
     DPN_CUDA_OK(cudaStreamSynchronize(st));

@@ -1,0 +1,97 @@
+"""Child of tests/test_gpu_multirank.py, launched by torchrun with one rank per GPU.  Checks SURVEY 8(e) "Check": the gradients
+R ranks obtain after the gradient all-reduce equal the 1-rank gradients on the concatenated batch (<= 1e-6 relative, fp32
+reduction-order noise), for both sharding levels:
+  level 1  samples sharded (run_train_interface_dist semantics: DistributedSampler + DDP mean, interface_physics.py:899-907,936);
+  level 2  one batch's query points sharded, every rank holding all samples (n_norm = total points, all-reduce SUM).
+Every rank computes the single-rank reference itself, so the comparison needs no extra communication."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from deepphysinet_b200 import InterfacePhysics, functional as Fn, parallel as P      # noqa: E402
+from deepphysinet_b200.config import DEFAULT_LOSS_FACTOR, DEFAULT_OBS_NORM            # noqa: E402
+from tests import helpers as H                                                        # noqa: E402
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300)).item()
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+    rank, local_rank, world = P.init_from_env()
+    dev = torch.device("cuda", local_rank)
+    obs = {k: dict(v, norm_type="mean_norm", use_norm=True) for k, v in DEFAULT_OBS_NORM.items()}
+    torch.manual_seed(0)                                    # identical replicas
+    model = InterfacePhysics(H.META_CFG, H.NET_CFG, obs, None, dict(img_size=(145, 257), dx=27000, dy=27000)).to(dev)
+    model.mode = mode
+    crit = torch.nn.MSELoss()
+    g = torch.Generator().manual_seed(7)                    # the same global batch on every rank
+    B, N = 2 * world, 1024
+    x = (torch.rand(B, N, generator=g) * 256 * 27000.0).to(dev)
+    yc = torch.rand(B, N, generator=g) * 144
+    f = (2 * 7.29e-5 * torch.sin((18.0 + yc * 0.25) / 180 * 3.141592653589793)).to(dev)
+    y = (yc * 27000.0).to(dev)
+    t = (torch.randint(0, 25, (B, N), generator=g).float() * 3600.0).to(dev)
+    cd = (0.5 * torch.randn(B, N, 6, generator=g)).to(dev)
+    field = torch.randn(B, 159, 2405, generator=g).to(dev)
+    fh = torch.full((B, 1, 1), 24.0 / 360.0, device=dev)
+    params = [p for p in model.physics_net.parameters()]
+
+    def grads_of(loss):
+        model.physics_net.zero_grad(set_to_none=True)
+        loss.backward()
+        return [None if p.grad is None else p.grad.clone() for p in params]
+
+    # ---- single-rank reference on the concatenated batch ----
+    ref_loss = model.place_one_batch(x, y, t, f, field, cd, fh, crit, DEFAULT_LOSS_FACTOR, 0, rank, dev)
+    ref = grads_of(ref_loss)
+    gmax = max(gr.abs().max() for gr in ref if gr is not None)
+    worst = {}
+    for level in (1, 2):
+        model.physics_net.zero_grad(set_to_none=True)
+        if level == 1:                                      # my samples, all their points
+            lo, hi = P.shard_range(B, rank, world)
+            loss = model.place_one_batch(x[lo:hi], y[lo:hi], t[lo:hi], f[lo:hi], field[lo:hi], cd[lo:hi], fh[lo:hi], crit,
+                                         DEFAULT_LOSS_FACTOR, 0, rank, dev)
+            loss.backward()
+            P.FlatGradAllReduce(params, op="mean")()
+            total = loss.detach().clone()
+            dist.all_reduce(total)
+            total /= world
+        else:                                               # all samples, my points of each: partial sums normalised by N
+            lo, hi = P.shard_range(N, rank, world)
+            W = model.physics_net.decoder_weights(field, fh)
+            part, terms = Fn.pde_residual(x[:, lo:hi], y[:, lo:hi], t[:, lo:hi], f[:, lo:hi], cd[:, lo:hi], W,
+                                          consts=model.consts(DEFAULT_LOSS_FACTOR), mode=mode, n_norm=N)
+            part.backward()
+            P.FlatGradAllReduce(params, op="sum")()
+            total, _ = P.reduce_partial_losses(part, terms)
+        lrel = abs(total.item() - ref_loss.item()) / abs(ref_loss.item())
+        w = 0.0
+        for p, r in zip(params, ref):
+            if r is None:
+                continue
+            # parameters with an analytically zero gradient (key_projection.bias) are pure round-off: judged on the global scale
+            err = (p.grad.double() - r.double()).norm().item()
+            w = max(w, err / max(r.double().norm().item(), 1e-6 * gmax.item() * r.numel() ** 0.5))
+        worst[level] = (lrel, w)
+    if rank == 0:
+        print("MULTIRANK mode=%s world=%d level1 loss %.2e grad %.2e | level2 loss %.2e grad %.2e" %
+              (mode, world, worst[1][0], worst[1][1], worst[2][0], worst[2][1]), flush=True)
+    tol = float(sys.argv[2]) if len(sys.argv) > 2 else 1e-6
+    ok = all(l < tol and gr < tol for l, gr in worst.values())
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()

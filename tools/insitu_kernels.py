@@ -1,5 +1,5 @@
 """In-situ durations of the library's kernels inside back-to-back dpn_pde_fwd_bwd calls (torch.profiler / CUPTI: no serialisation,
-no cache flush - complements the ncu launch list).   python tools/insitu_kernels.py [mode]     (DPN_P1=ts for the chained pass-1 variant)"""
+no cache flush - complements the ncu launch list).   python tools/insitu_kernels.py [mode]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -25,6 +25,6 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = [(e.key, e.count, e.device_time_total / 1e3) for e in prof.key_averages() if e.device_time_total > 0]
 rows.sort(key=lambda r: -r[2])
 tot = sum(r[2] for r in rows)
-print("[DPN_P1=%s] %s: %d calls, kernel time %.2f ms per call" % (os.environ.get("DPN_P1", "np"), mode, n, tot / n))
+print("%s: %d calls, kernel time %.2f ms per call" % (mode, n, tot / n))
 for k, c, t in rows[:6]:
     print("   %-60s %4d launches  %8.3f ms per call  mean %.3f ms" % (k[:60], c, t / n, t / c))
