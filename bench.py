@@ -241,6 +241,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2] / configs[3] legs (1 GPU only)")
     ap.add_argument("--no-eager-gpu", action="store_true", help="skip the PyTorch-eager-on-this-GPU baseline leg")
     ap.add_argument("--no-graph", action="store_true", help="time the eager place_one_batch call instead of its CUDA-graph capture")
     ap.add_argument("--e2e-breakdown", action="store_true", help="print per-phase times of the e2e step to stderr")
@@ -296,6 +297,7 @@ def main():
     def op_step():
         total, terms = Fn.pde_residual(dx_, dy_, dt_, df_, dcd, Fn.DecoderWeights(*leaves), consts=consts, mode=args.mode)
         holder["launches"] = Nat.lib().dpn_last_launch_count()
+        holder["last_total"], holder["last_terms"] = total, terms
         if world > 1:
             grads = total.grad_fn.grads if hasattr(total.grad_fn, "grads") else None
             off = 0
@@ -324,11 +326,66 @@ def main():
             dist.barrier()
         return P.allreduce_max(e0.elapsed_time(e1) / steps, dev)
 
+    if os.environ.get("DPN_DEBUG_FLAGS") or os.environ.get("DPN_PHASE_DEBUG") or os.environ.get("DPN_LIB_OVERRIDE"):
+        raise SystemExit("bench.py measures the shipped library: unset DPN_DEBUG_FLAGS / DPN_PHASE_DEBUG / DPN_LIB_OVERRIDE")
+    first_total = float(op_step().detach())                          # reference value of the loss for the checksum below
     with ClockSampler(local_rank) as clk:
         ms = timed(op_step, args.steps, args.warmup)
     clocks = clk.summary()
     pts_step = B * Np * world
     value = pts_step / (ms * 1e-3)
+    # the timed op really computed the loss: finite, and identical (up to the order of the fp64 atomics) on every step
+    last_total = float(holder["last_total"].detach())
+    terms_mean = [float(v) for v in holder["last_terms"].mean(0).tolist()]
+    if not (last_total == last_total and abs(last_total) < float("inf")) or abs(last_total - first_total) > 1e-6 * abs(first_total):
+        raise SystemExit("timed operator returned loss %r, first call %r" % (last_total, first_total))
+    checksum = {"total": last_total, "terms_mean_over_samples": terms_mean, "first_call_total": first_total}
+
+    # ---- strong scaling (configs[1] sharded over the ranks), N > 1 only: total batch fixed at 8 samples ----
+    strong = None
+    if world > 1:
+        s_steps = max(3, min(args.steps, 10))
+        # level 1: samples sharded (8 / world per rank), all-reduce of the static-decoder gradients as in the weak-scaling op
+        Bs = max(1, 8 // world)
+        l1 = [w_[:Bs].detach().clone().requires_grad_(True) if i < 5 else leaves[i] for i, w_ in enumerate(leaves)]
+
+        def strong_samples():
+            total, terms = Fn.pde_residual(dx_[:Bs], dy_[:Bs], dt_[:Bs], df_[:Bs], dcd[:Bs], Fn.DecoderWeights(*l1), consts=consts, mode=args.mode)
+            grads = total.grad_fn.grads
+            off = 0
+            for i in static_idx:
+                n = grads[i].numel()
+                flat[off:off + n].copy_(grads[i].reshape(-1))
+                off += n
+            flat[n_static:].copy_(terms.mean(0).float())
+            dist.all_reduce(flat)
+            return total
+        ms_s1 = timed(strong_samples, s_steps, 3)
+        # level 2: every rank holds all 8 samples and 1 / world of each sample's points (n_norm = all points); EVERY gradient the
+        # call produces is a partial sum, generated weights included: one all-reduce (sum) of all 13 tensors
+        lo, hi = P.shard_range(Np, rank, world)
+        sl = lambda a: a[:, lo:hi].contiguous()
+        px, py, pt_, pf, pcd = sl(dx_), sl(dy_), sl(dt_), sl(df_), sl(dcd)
+        flat_all = torch.zeros(sum(w_.numel() for w_ in leaves) + 6 * B, device=dev)
+
+        def strong_points():
+            total, terms = Fn.pde_residual(px, py, pt_, pf, pcd, Fn.DecoderWeights(*leaves), consts=consts, mode=args.mode, n_norm=Np)
+            grads = total.grad_fn.grads
+            off = 0
+            for g_ in grads:
+                flat_all[off:off + g_.numel()].copy_(g_.reshape(-1))
+                off += g_.numel()
+            flat_all[off:].copy_(terms.reshape(-1).float())
+            dist.all_reduce(flat_all)
+            return total
+        ms_s2 = timed(strong_points, s_steps, 3)
+        tot_pts = 8 * Np if world <= 8 else Bs * world * Np
+        strong = {"scaling": "strong", "batch_total": Bs * world, "points_per_sample": Np,
+                  "samples_sharded": {"value": Bs * world * Np / (ms_s1 * 1e-3), "unit": UNIT, "ms_per_step": ms_s1, "samples_per_rank": Bs,
+                                      "collective": "all-reduce of static-decoder gradients + loss terms (%.1f MB)" % (flat.numel() * 4 / 2 ** 20)},
+                  "points_sharded": {"value": B * Np / (ms_s2 * 1e-3), "unit": UNIT, "ms_per_step": ms_s2, "points_per_rank_and_sample": hi - lo,
+                                     "collective": "all-reduce (sum) of all 13 gradient tensors + loss terms (%.1f MB)" % (flat_all.numel() * 4 / 2 ** 20)},
+                  "steps": s_steps}
 
     # ---- e2e through the reference-facing API, host buffers ----
     e2e = None
@@ -422,6 +479,53 @@ def main():
             ms_m = e0.elapsed_time(e1) / n_m
             modes[m] = {"value": B * Np / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m, "note": notes[m]}
 
+    # ---- the other single-GPU configurations of BASELINE.json, a few steps each ----
+    configs = {}
+    if rank == 0 and world == 1 and not args.no_configs:
+        def time_it(fn, n):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        # configs[2]: fused decoder + Jacobian + residual + backward microbench, one sample, 1M - 16M random query points
+        micro = {}
+        l1 = [w_[:1].detach().clone().requires_grad_(True) if i < 5 else leaves[i] for i, w_ in enumerate(leaves)]
+        for logn in (20, 22, 24):
+            n_ = 1 << logn
+            gq = torch.Generator(device=dev).manual_seed(logn)
+            qx = torch.rand(1, n_, generator=gq, device=dev) * 256 * 27000.0
+            qy = torch.rand(1, n_, generator=gq, device=dev) * 144
+            qf = 2 * 7.29e-5 * torch.sin((18.0 + qy * 0.25) / 180 * 3.141592653589793)
+            qy = qy * 27000.0
+            qt = torch.randint(0, 25, (1, n_), generator=gq, device=dev).float() * 3600.0
+            qcd = 0.5 * torch.randn(1, n_, 6, generator=gq, device=dev)
+            ms_c = time_it(lambda: Fn.pde_residual(qx, qy, qt, qf, qcd, Fn.DecoderWeights(*l1), consts=consts, mode=args.mode), 2)
+            micro["2^%d" % logn] = {"value": n_ / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c}
+            del qx, qy, qf, qt, qcd
+        configs["configs[2] microbench B=1, fwd+Jacobian+residual+bwd"] = micro
+        # configs[3]: continuous-time dense-grid inference, 145 x 257 nodes x 48 hourly leads, values only (no residuals)
+        coarse = torch.randn(1, 5, 37, 65, 6, device=dev)
+        fd, fh1 = hfield[:1].to(dev), hfh[:1].to(dev)
+        leads = list(range(48))
+        model.pred_t_span = 48 * 3600.0                                       # one window spanning the 48 leads
+        ms_g = time_it(lambda: model.predict_grid(fd, coarse, fh1, leads), 3)
+        with torch.no_grad():
+            Wg = model.physics_net.decoder_weights(fd, fh1)
+        ms_gc = time_it(lambda: model.predict_grid(fd, coarse, fh1, leads, weights=Wg), 3)
+        model.pred_t_span = 86400
+        npts = 145 * 257 * 48
+        configs["configs[3] dense-grid inference 145x257 x 48 leads, values only"] = {
+            "value": npts / (ms_g * 1e-3), "unit": "grid points/s", "ms_per_sweep": ms_g, "points": npts,
+            "with_cached_generated_weights": {"value": npts / (ms_gc * 1e-3), "ms_per_sweep": ms_gc}}
+        del coarse
+        torch.cuda.empty_cache()
+
     pk = peaks()
     per_gpu_pts = B * Np / (ms * 1e-3)
     achieved = ALGO_FLOP_PER_POINT * per_gpu_pts / 1e12
@@ -461,7 +565,8 @@ def main():
                            "l2": "per-step working set (%.1f GB workspace) >> 126 MB L2; no flush needed" %
                                  (Nat.workspace(Fn._shape(B, Np, 6, args.mode), dev)[1] / 2 ** 30)},
                 "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu_base, "eager_gpu_baseline": eager_gpu, "clocks": clocks,
-                "gpu_launches": int(holder.get("launches", 0)) * args.steps, "modes": modes}
+                "gpu_launches": int(holder.get("launches", 0)) * args.steps, "loss_checksum": checksum, "strong_scaling": strong,
+                "other_configs": configs, "modes": modes}
         _emit(line)
     if world > 1:
         dist.barrier()

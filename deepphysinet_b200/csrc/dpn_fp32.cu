@@ -243,11 +243,17 @@ __global__ void jac_kernel(const DevConsts K, int P, int Kn, const float* __rest
 }
 
 // Residuals, loss sums and seeds (see residual_point).  One thread per point; block-reduced fp64 atomics.
+// blockIdx.y = sample: per-point work arrays advance by `srow` rows per sample, caller arrays (f, vals, jac) by `sq` points.
 __global__ void residual_kernel(const DevConsts K, int P, const float* __restrict__ o, const float* __restrict__ od,
                                 const float* __restrict__ f, double inv_n, double seed_scale,
                                 double* __restrict__ loss6, float* __restrict__ dov, float* __restrict__ dod,
-                                float* __restrict__ vals, float* __restrict__ jac) {
+                                float* __restrict__ vals, float* __restrict__ jac, size_t srow, size_t sq) {
   __shared__ double red[6][8];
+  const size_t bs = blockIdx.y;
+  o += bs * srow * 6; od += bs * srow * 18; dov += bs * srow * 6; dod += bs * srow * 18;
+  f += bs * sq; loss6 += bs * 6;
+  if (vals) vals += bs * sq * 6;
+  if (jac) jac += bs * sq * 18;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double r2w[6] = {0, 0, 0, 0, 0, 0};
   if (p < P) {
@@ -290,8 +296,12 @@ __global__ void residual_kernel(const DevConsts K, int P, const float* __restric
 // loss += factor * inv_n/6 * sum smooth_l1(o - target; beta) and the seed of the value row gets d(loss)/d(o) added, so the one
 // backward pass that follows serves both losses.  One thread per point; o is the normalised net output (before inverse_norm).
 __global__ void margin_seed_kernel(int P, const float* __restrict__ o, const float* __restrict__ target, double beta, double coef,
-                                   double seed_scale, double* __restrict__ loss, float* __restrict__ dov, float* __restrict__ o_out) {
+                                   double seed_scale, double* __restrict__ loss, float* __restrict__ dov, float* __restrict__ o_out,
+                                   size_t srow, size_t sq) {
   __shared__ double red[8];
+  const size_t bs = blockIdx.y;
+  o += bs * srow * 6; dov += bs * srow * 6; target += bs * sq * 6; loss += bs;
+  if (o_out) o_out += bs * sq * 6;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   double acc = 0.0;
   if (p < P) {
@@ -569,9 +579,9 @@ int run(const Job& J, cudaStream_t st) {
         residual_kernel<<<(P + 255) / 256, 256, 0, st>>>(DC, P, w.o, w.od, J.pts->f + q0, inv_n, seed_scale,
                                                          J.out->loss_terms + (size_t)b * 6, w.dov, w.dod,
                                                          J.out->vals ? J.out->vals + q0 * 6 : nullptr,
-                                                         J.out->jac ? J.out->jac + q0 * 18 : nullptr);
+                                                         J.out->jac ? J.out->jac + q0 * 18 : nullptr, 0, 0);
         DPN_LAUNCH_OK();
-        if (J.margin && (rc = launch_margin(P, w.o, J.margin->target + q0 * 6, *J.margin, inv_n, seed_scale, J.margin->loss + b,
+        if (J.margin && (rc = launch_margin(1, P, 0, 0, w.o, J.margin->target + q0 * 6, *J.margin, inv_n, seed_scale, J.margin->loss + b,
                                             w.dov, J.margin->o ? J.margin->o + q0 * 6 : nullptr, st)))
           return rc;
       } else {
@@ -640,16 +650,17 @@ int launch_prep(int B, int Kn, const DpnWeights& Wt, float* uvec, float* wo2, fl
   return 0;
 }
 
-int launch_residual(const DevConsts& DC, int P, const float* o, const float* od, const float* f, double inv_n,
-                    double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st) {
-  residual_kernel<<<(P + 255) / 256, 256, 0, st>>>(DC, P, o, od, f, inv_n, seed_scale, loss6, dov, dod, vals, jac);
+int launch_residual(const DevConsts& DC, int B, int P, size_t srow, size_t sq, const float* o, const float* od, const float* f,
+                    double inv_n, double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st) {
+  residual_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(DC, P, o, od, f, inv_n, seed_scale, loss6, dov, dod, vals, jac, srow, sq);
   DPN_LAUNCH_OK();
   return 0;
 }
 
-int launch_margin(int P, const float* o, const float* target, const DpnMargin& M, double inv_n, double seed_scale, double* loss,
-                  float* dov, float* o_out, cudaStream_t st) {
-  margin_seed_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, o, target, M.beta, M.factor * inv_n / 6.0, seed_scale, loss, dov, o_out);
+int launch_margin(int B, int P, size_t srow, size_t sq, const float* o, const float* target, const DpnMargin& M, double inv_n,
+                  double seed_scale, double* loss, float* dov, float* o_out, cudaStream_t st) {
+  margin_seed_kernel<<<dim3((P + 255) / 256, B), 256, 0, st>>>(P, o, target, M.beta, M.factor * inv_n / 6.0, seed_scale, loss, dov, o_out,
+                                                               srow, sq);
   DPN_LAUNCH_OK();
   return 0;
 }

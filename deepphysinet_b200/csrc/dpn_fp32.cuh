@@ -56,10 +56,10 @@ int run(const Job& job, cudaStream_t st);
 
 // pieces reused by the tensor-core mode
 int launch_prep(int B, int Kn, const DpnWeights& Wt, float* uvec, float* wo2, float* cst, float* bsum, cudaStream_t st);
-int launch_residual(const DevConsts& DC, int P, const float* o, const float* od, const float* f, double inv_n,
-                    double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st);
-int launch_margin(int P, const float* o, const float* target, const DpnMargin& M, double inv_n, double seed_scale, double* loss,
-                  float* dov, float* o_out, cudaStream_t st);
+int launch_residual(const DevConsts& DC, int B, int P, size_t srow, size_t sq, const float* o, const float* od, const float* f,
+                    double inv_n, double seed_scale, double* loss6, float* dov, float* dod, float* vals, float* jac, cudaStream_t st);
+int launch_margin(int B, int P, size_t srow, size_t sq, const float* o, const float* target, const DpnMargin& M, double inv_n,
+                  double seed_scale, double* loss, float* dov, float* o_out, cudaStream_t st);
 int launch_finalize(int Kn, const DpnWeights& Wt, const float* vc, const float* vg, const float* sdo, const DpnGrads& G,
                     cudaStream_t st);
 

@@ -2540,18 +2540,15 @@ static int run_planes(const Job& J, cudaStream_t st) {
       DPN_CUDA_OK(cudaMemsetAsync(c.dov, 0, rows * Kn * 4, st));
       DPN_CUDA_OK(cudaMemsetAsync(c.dod, 0, rows * Kn * 12, st));
     }
-    if (pde) {
-      for (int b = 0; b < B; ++b) {
-        const size_t r0 = (size_t)b * T * TP, q0 = (size_t)b * N + p0;
-        if ((rc = f32::launch_residual(J.dc, P, c.o + r0 * 6, c.od + r0 * 18, J.pts->f + q0, inv_n, seed_scale,
-                                       J.out->loss_terms + (size_t)b * 6, c.dov + r0 * 6, c.dod + r0 * 18,
-                                       J.out->vals ? J.out->vals + q0 * 6 : nullptr,
-                                       J.out->jac ? J.out->jac + q0 * 18 : nullptr, st)))
-          return rc;
-        if (J.margin && (rc = f32::launch_margin(P, c.o + r0 * 6, J.margin->target + q0 * 6, *J.margin, inv_n, seed_scale,
-                                                 J.margin->loss + b, c.dov + r0 * 6, J.margin->o ? J.margin->o + q0 * 6 : nullptr, st)))
-          return rc;
-      }
+    if (pde) {                                                        // all samples in one launch (blockIdx.y = sample)
+      const size_t srow = (size_t)T * TP, q0 = (size_t)p0;
+      if ((rc = f32::launch_residual(J.dc, B, P, srow, (size_t)N, c.o, c.od, J.pts->f + q0, inv_n, seed_scale, J.out->loss_terms,
+                                     c.dov, c.dod, J.out->vals ? J.out->vals + q0 * 6 : nullptr,
+                                     J.out->jac ? J.out->jac + q0 * 18 : nullptr, st)))
+        return rc;
+      if (J.margin && (rc = f32::launch_margin(B, P, srow, (size_t)N, c.o, J.margin->target + q0 * 6, *J.margin, inv_n, seed_scale,
+                                               J.margin->loss, c.dov, J.margin->o ? J.margin->o + q0 * 6 : nullptr, st)))
+        return rc;
     } else {
       seed_copy_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(w, J.d_o, (float)seed_scale);
       DPN_LAUNCH_OK();
