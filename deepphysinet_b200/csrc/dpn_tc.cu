@@ -907,6 +907,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
     uint32_t s = 0, ph = 0, ae = 0;
+    long long t_full = 0, t_epi = 0;
+    const bool timed = w.phase_dbg != nullptr;
+    const long long t_begin = clock64();
     const uint32_t ring_addr = smem_u32(ring);
     const uint64_t a_base = smem_desc(ring_addr + ts::W_BYTES, CORE_STRIDE, 128);
     auto gemm = [&](const int nchunks, const int Nn, const bool a_in_tmem, const bool accumulate) {
@@ -914,7 +917,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint64_t b_base = smem_desc(ring_addr, Nn * 16, 128);
       const uint32_t b_lo = (uint32_t)(Nn * 32) >> 4;
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&pipe.full[s], ph);
+        if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
         tc_fence_after();
         const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
         const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
@@ -934,7 +937,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         if (++s == ts::NS) { s = 0; ph ^= 1; }
       }
     };
-    auto wait_epi = [&]() { mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
+    auto wait_epi = [&]() { if (timed) mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); else mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
     auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready); };
     for (int k = 0; k < w.Kn; ++k) {
       if (k > 0) wait_epi();                                               // the last epilogue of the previous net has drained the accumulator
@@ -953,6 +956,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           gemm(16, C, true, false); ready();                               // G6 (A = qm, N = 192)
         }
       }
+    }
+    if (timed && lane == 0) {
+      atomicAdd((unsigned long long*)w.phase_dbg + 0, (unsigned long long)(clock64() - t_begin));
+      atomicAdd((unsigned long long*)w.phase_dbg + 1, (unsigned long long)t_full);
+      atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)t_epi);
     }
   } else if (warp < Geo<PL>::EW) {
     // ---------------- epilogue: thread = (point r, column half) ----------------
@@ -988,7 +996,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       }
     };
     auto done = [&]() { tmem_st_wait(); tc_fence_before(); mbar_arrive(&pipe.a_epi); };
-    auto acc_wait = [&]() { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
+    long long t_acc = 0;
+    const long long t_begin = clock64();
+    const bool timed = w.phase_dbg != nullptr;
+    auto acc_wait = [&]() { if (timed) mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); else mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
     if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile<PL>(w, b, k, tl);
@@ -1160,6 +1171,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           rowsum[r * 4 + 1 + c] = 0.f;
         }
       }
+    }
+    if (timed && tid == 0) {
+      const long long tot = clock64() - t_begin;
+      atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)tot);
+      atomicAdd((unsigned long long*)w.phase_dbg + 5, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 7, (unsigned long long)(tot - t_acc));
+      atomicAdd((unsigned long long*)w.phase_dbg + 6, 1ull);
     }
   }
   tc_fence_before();
@@ -1518,6 +1536,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
     uint32_t s = 0, ph = 0, ae = 0;
+    long long t_full = 0, t_epi = 0;
+    const bool timed = w.phase_dbg != nullptr;
+    const long long t_begin = clock64();
     const uint32_t ring_addr = smem_u32(ring);
     const uint32_t idesc = idesc_16(F16, H, 0, 0, 128);
     const uint64_t b_base = smem_desc(ring_addr, H * 16, 128);
@@ -1525,7 +1546,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     constexpr uint32_t b_lo = (uint32_t)(H * 32) >> 4, zd_lo = BLOB_C >> 4, zd_step = (2 * CORE_STRIDE) >> 4;
     auto gemm = [&](const int nchunks, const bool a_in_tmem, const bool accumulate) {
       for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(&pipe.full[s], ph);
+        if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
         tc_fence_after();
         const uint64_t bd = b_base + s * (uint32_t)(p2z::W_BYTES >> 4), bl = bd + b_lo;
         const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
@@ -1545,7 +1566,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         if (++s == p2z::NS) { s = 0; ph ^= 1; }
       }
     };
-    auto wait_epi = [&]() { mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
+    auto wait_epi = [&]() { if (timed) mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); else mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
     auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready); };
     for (int k = 0; k < w.Kn; ++k) {
       wait_epi();                                                          // prologue: zp in tensor memory, zd in shared memory
@@ -1554,6 +1575,11 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       gemm(16, true, false); gemm(12, false, true); ready();               // G8' = zh W2^T + zd Wd^T
       wait_epi();
       gemm(16, true, false); ready();                                      // G9' = zc Wa^T
+    }
+    if (timed && lane == 0) {
+      atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
+      atomicAdd((unsigned long long*)w.phase_dbg + 9, (unsigned long long)t_full);
+      atomicAdd((unsigned long long*)w.phase_dbg + 10, (unsigned long long)t_epi);
     }
   } else if (warp < Geo<PL>::EW) {
     // ---------------- prologue + epilogues: thread = (point r, column half) ----------------
@@ -1567,7 +1593,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t ar = 0;
     auto done = [&]() { tmem_st_wait(); tc_fence_before(); fence_proxy_async(); mbar_arrive(&pipe.a_epi); };
-    auto acc_wait = [&]() { mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
+    long long t_acc = 0, t_pro = 0;
+    const long long t_begin = clock64();
+    const bool timed = w.phase_dbg != nullptr;
+    auto acc_wait = [&]() { if (timed) mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); else mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
     // 32 columns of this row, already scaled: split once -> workspace tile (wgrad operand) and / or the next A operand in TMEM
     auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a) {
       uint32_t hi[16], lo[16];
@@ -1634,6 +1663,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + gp_off(2, r, 1)), make_uint4(0u, 0u, 0u, 0u));
       }
       // ---- prologue: zp = dov PE + sum_c dod_c dPE_c -> A operand (TMEM) + workspace;  zd = dov PE6 -> shared memory + workspace ----
+      const long long t_p0 = timed ? clock64() : 0ll;
 #pragma unroll 1
       for (int it = half * NB; it < half * NB + NB; ++it) {          // 24 columns = 4 frequencies = 3 pieces = 12 packed words per plane
         float pe[24], zp[24];
@@ -1677,6 +1707,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         tmem_st8(lane_base + p2z::COL_AL + it * 12, lo); tmem_st4(lane_base + p2z::COL_AL + it * 12 + 8, lo + 8);
       }
       done();
+      if (timed) t_pro += clock64() - t_p0;
       // ---- epilogue 7: zh = m1 (acc + dov b1) ----
       acc_wait();
 #pragma unroll 1
@@ -1762,6 +1793,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         csum[i] = 0.f;
       }
       if (tid == 0) { atomicAdd(w.sdo + k, csum[2 * H]); csum[2 * H] = 0.f; }
+    }
+    if (timed && tid == 0) {
+      const long long tot = clock64() - t_begin;
+      atomicAdd((unsigned long long*)w.phase_dbg + 12, (unsigned long long)tot);
+      atomicAdd((unsigned long long*)w.phase_dbg + 13, (unsigned long long)t_acc);
+      atomicAdd((unsigned long long*)w.phase_dbg + 15, (unsigned long long)(tot - t_acc));
+      atomicAdd((unsigned long long*)w.phase_dbg + 11, (unsigned long long)t_pro);
+      atomicAdd((unsigned long long*)w.phase_dbg + 14, 1ull);
     }
   }
   tc_fence_before();
@@ -2601,7 +2640,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     fprintf(stderr, "[dpn phase] pass1 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f | wait A tile %.0f || "
                     "epilogue-thread total %.0f | wait accumulator %.0f | acc ready -> tile handed over %.0f\n", h[0] / n1, h[1] / n1, h[2] / n1, h[3] / n1, h[4] / n1, h[5] / n1, h[7] / n1);
     fprintf(stderr, "[dpn phase] pass2 per CTA (cycles): mma-thread total %.0f | wait weights %.0f | wait epilogue %.0f || "
-                    "epilogue-thread total %.0f | wait accumulator %.0f | compute %.0f\n", h[8] / n2, h[9] / n2, h[10] / n2, h[12] / n2, h[13] / n2, h[15] / n2);
+                    "epilogue-thread total %.0f | wait accumulator %.0f | compute %.0f (of which prologue %.0f)\n", h[8] / n2, h[9] / n2, h[10] / n2, h[12] / n2, h[13] / n2, h[15] / n2, h[11] / n2);
   }
 #endif
   if (want_bwd) {
