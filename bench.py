@@ -431,19 +431,22 @@ def main():
             # the same call captured once into a CUDA graph (deepphysinet_b200.graphed): pinned-host -> device copies, encoder,
             # fused operator and backward replay as ONE launch; the NCCL all-reduce and loss.item() stay outside the graph
             try:
-                from deepphysinet_b200.graphed import GraphedPlaceOneBatch
-                gstep = GraphedPlaceOneBatch(model, (hx, hy, ht, hf, hfield, hcd, hfh), crit, DEFAULT_LOSS_FACTOR, dev, rank=rank)
+                from deepphysinet_b200.graphed import PrefetchedPlaceOneBatch
+                gstep = PrefetchedPlaceOneBatch(model, (hx, hy, ht, hf, hfield, hcd, hfh), crit, DEFAULT_LOSS_FACTOR, dev, rank=rank)
+                gstep.prefetch()                                               # the first batch; every step below issues the next one
 
                 def graphed_step():
-                    loss = gstep()
-                    reducer()
+                    loss = gstep()                                             # graph replay on the batch prefetched last
+                    gstep.prefetch()                                           # this step's H2D (all inputs, pinned host -> device): runs
+                    reducer()                                                  # on the copy stream underneath the compute just enqueued
                     return loss.item()
                 ref_loss = e2e_step()
                 got_loss = graphed_step()
                 if abs(got_loss - ref_loss) > 1e-3 * abs(ref_loss):
                     raise RuntimeError("graphed step loss %r != eager loss %r" % (got_loss, ref_loss))
                 step_fn = graphed_step
-                api = "GraphedPlaceOneBatch (CUDA graph of place_one_batch(pinned host tensors) + backward) + grad all-reduce + loss.item()"
+                api = ("PrefetchedPlaceOneBatch (CUDA graph of place_one_batch + backward; the step's pinned-host -> device copies "
+                       "double-buffered on a copy stream) + grad all-reduce + loss.item()")
             except Exception as ex:                                            # host-side orchestration only: report and time the eager call
                 print("[rank %d] CUDA-graph capture of the e2e step failed (%s): timing the eager call" % (rank, ex), file=sys.stderr)
         ms_e = timed(step_fn, e_steps, max(5, args.warmup))

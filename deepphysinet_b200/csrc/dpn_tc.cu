@@ -1664,16 +1664,30 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       }
       // ---- prologue: zp = dov PE + sum_c dod_c dPE_c -> A operand (TMEM) + workspace;  zd = dov PE6 -> shared memory + workspace ----
       const long long t_p0 = timed ? clock64() : 0ll;
+      // the loads of column group it + 1 are in flight while group it is processed (they come from L2: the tile's features are
+      // re-read for every net)
+      float pe_n[24];
+      uint4 p6_n[3][PL];
+      auto fetch = [&](const int it) {
+#pragma unroll
+        for (int j = 0; j < 24; ++j) pe_n[j] = ldg_f32_hint(pet + (size_t)(it * 24 + j) * TP, pol_keep);
+#pragma unroll
+        for (int qd = 0; qd < 3; ++qd)
+#pragma unroll
+          for (int p = 0; p < PL; ++p) p6_n[qd][p] = ldg_v4_hint(pe6 + p * BLOB_C + piece_off(r, it * 3 + qd), pol_keep);
+      };
+      fetch(half * NB);
 #pragma unroll 1
       for (int it = half * NB; it < half * NB + NB; ++it) {          // 24 columns = 4 frequencies = 3 pieces = 12 packed words per plane
         float pe[24], zp[24];
         uint4 p6[3][PL];
 #pragma unroll
-        for (int j = 0; j < 24; ++j) pe[j] = ldg_f32_hint(pet + (size_t)(it * 24 + j) * TP, pol_keep);
+        for (int j = 0; j < 24; ++j) pe[j] = pe_n[j];
 #pragma unroll
         for (int qd = 0; qd < 3; ++qd)
 #pragma unroll
-          for (int p = 0; p < PL; ++p) p6[qd][p] = ldg_v4_hint(pe6 + p * BLOB_C + piece_off(r, it * 3 + qd), pol_keep);
+          for (int p = 0; p < PL; ++p) p6[qd][p] = p6_n[qd][p];
+        if (it + 1 < half * NB + NB) fetch(it + 1);
 #pragma unroll
         for (int j = 0; j < 24; ++j) {
           const int J = it * 24 + j;                                  // it*24 is a multiple of 6: the partner stays inside the block
@@ -1980,16 +1994,19 @@ static_assert(128 * (H * 4 + ROW_PAD) <= SMEM, "the staged [128 x 256] fp32 outp
 }  // namespace wg2
 
 template <bool F16>
-__global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
   constexpr int PL = 2;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2], acc_ready;
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  // the two CTAs of a cluster are the two output halves (mh) of one (sample, net, layer, split): they contract against the SAME Z
+  // half-tiles, so each fetches half of every Z plane (and of the seed tile) and multicasts it to both - one L2 / DRAM read
+  // instead of two (ncu, round 2: 27 GB of DRAM reads per launch for 20 GB of distinct tiles without the multicast)
   int item = blockIdx.x;
+  const int mh = item & 1; item >>= 1;                               // == cluster rank
   const int split = item % w.splits; item /= w.splits;
-  const int mh = item & 1; item >>= 1;
   const int layer = item & 3; item >>= 2;
   const int k = item % w.Kn, b = item / w.Kn;
   const int Nn = (layer == 0 || layer == 3) ? C : H;
@@ -2000,13 +2017,14 @@ __global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
   const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
   const int nst = 2 * (t1 - t0);                                      // half-tiles
   if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 1); mbar_init(&empty[1], 1); mbar_init(&acc_ready, 1);
+    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 2); mbar_init(&empty[1], 2); mbar_init(&acc_ready, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(&tmem_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cluster_sync_all();                                                // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem = tmem_s;
   constexpr uint32_t COL_X = 256;                                     // seed-product columns
   if (nst > 0) {
@@ -2021,15 +2039,16 @@ __global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
         const uint8_t* xsrc = nt + off_aux<PL>() + (size_t)ph * wg2::X_BYTES;
         const int s = i & 1;
         uint8_t* st = smem + s * wg2::STAGE;
-        mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);                     // BOTH CTAs are done with the previous occupant (multicast commits)
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], 2 * wg2::J_PLANE + 2 * zplane + (aux ? wg2::X_BYTES : 0));
+          mbar_arrive_expect_tx(&full[s], 2 * wg2::J_PLANE + 2 * zplane + (aux ? wg2::X_BYTES : 0));   // my J + both halves of Z / seeds
+          const uint32_t zh = zplane / 2, xh = wg2::X_BYTES / 2;
 #pragma unroll
           for (int p = 0; p < PL; ++p) {
             bulk_g2s(st + p * wg2::J_PLANE, jsrc + (size_t)p * BLOB_H, wg2::J_PLANE, &full[s]);
-            bulk_g2s(st + 2 * wg2::J_PLANE + p * wg2::Z_PLANE, zsrc + (size_t)p * zstride, zplane, &full[s]);
+            bulk_g2s_mc(st + 2 * wg2::J_PLANE + p * wg2::Z_PLANE + mh * zh, zsrc + (size_t)p * zstride + mh * zh, zh, &full[s], (uint16_t)3);
           }
-          if (aux) bulk_g2s(st + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE, xsrc, wg2::X_BYTES, &full[s]);
+          if (aux) bulk_g2s_mc(st + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE + mh * xh, xsrc + mh * xh, xh, &full[s], (uint16_t)3);
         }
       }
     } else if (warp == 5) {
@@ -2062,7 +2081,7 @@ __global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
               mma_f16_c<A_LAST>(tmem, ad, bd, idesc, 1u);
             }
           }
-          mma_commit(&empty[s]);
+          mma_commit_mc(&empty[s], (uint16_t)3);                      // the stage is free in BOTH CTAs' eyes only when both have read it
         }
       }
       if (elect_one()) mma_commit(&acc_ready);
@@ -2115,6 +2134,7 @@ __global__ void __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                                // nobody leaves while the peer's commits may still arrive on its barriers
   if (warp == 5) tmem_dealloc(tmem, 512);
 }
 
