@@ -69,9 +69,10 @@ constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
 constexpr int GEN_IMG = 2 * IMG_HC + 4 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T, P, PT  (P = Wa W2, see FOLD below)
 constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
-// Workspace tile of one (net, point tile).  bf16 mode: H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX.  Split modes: UM YT QM ZH ZC | ZP ZD | AUX |
+// Workspace tile of one (net, point tile).  bf16 mode: H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX.  Split modes: YT QM ZH ZC | ZP ZD | AUX |
 // MASK - pass 2 runs as the forward pass of the combined row and needs only the two ReLU masks of pass 1
-// (2 x 256 bits per point) instead of the h1 / c / g tiles (3 x 1 KB per point).
+// (2 x 256 bits per point) instead of the h1 / c / g tiles (3 x 1 KB per point), and the weight-gradient kernel rebuilds its
+// J operand um = u [a3 > 0] from the same mask bits instead of reading a stored tile.
 constexpr int NBLOB_H = 8, NBLOB_C = 2;
 enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
 constexpr int MASK_BYTES = 2 * TP * 32;       // [m1 | m3][128 rows][8 words]
@@ -84,7 +85,7 @@ struct Geo {
   static constexpr int ACT = BLOB_H * PL;                        // activation buffer: plane p at p * BLOB_H
   static constexpr int BH = BLOB_H * PL, BC = BLOB_C * PL;       // workspace blobs: plane p at p * BLOB_H (p * BLOB_C)
   static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
-  static constexpr int NBH = PL == 2 ? 5 : NBLOB_H;              // [128 x 256] tiles kept per (net, tile)
+  static constexpr int NBH = PL == 2 ? 4 : NBLOB_H;              // [128 x 256] tiles kept per (net, tile)
   static constexpr size_t NET_TILE = (size_t)NBH * BH + (size_t)NBLOB_C * BC + AUX_BYTES + (PL == 2 ? MASK_BYTES : 0);
   static constexpr int CTAS_PER_SM = PL == 1 ? 2 : 1;
   // FOLD (one CTA per SM, all 512 TMEM columns): two GEMMs that share their A operand run back to back into TWO accumulators and
@@ -146,7 +147,7 @@ template <int PL>
 __device__ __forceinline__ uint8_t* net_tile(const Work& w, int b, int k, int tl) {
   return w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * Geo<PL>::NET_TILE;
 }
-template <int PL> __host__ __device__ constexpr size_t off_h(int which) { return (size_t)(which - (PL == 2 ? (int)B_UM : 0)) * Geo<PL>::BH; }
+template <int PL> __host__ __device__ constexpr size_t off_h(int which) { return (size_t)(which - (PL == 2 ? (int)B_YT : 0)) * Geo<PL>::BH; }
 template <int PL> __host__ __device__ constexpr size_t off_zp() { return (size_t)Geo<PL>::NBH * Geo<PL>::BH; }
 template <int PL> __host__ __device__ constexpr size_t off_zd() { return off_zp<PL>() + Geo<PL>::BC; }
 template <int PL> __host__ __device__ constexpr size_t off_aux() { return off_zp<PL>() + 2 * Geo<PL>::BC; }
@@ -1091,7 +1092,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) m3w[i] = (cb == i) ? bits : m3w[i];
-        if (sweep) emit(cg, v, blob_h<PL>(nt, B_UM), true);
+        if (sweep) emit(cg, v, nullptr, true);                        // um = u [a3 > 0] is rebuilt from the mask by wgrad2_kernel
       }
       if (sweep) {                                                     // the two ReLU masks of this (net, tile): all pass 2 needs of h1 / c / g
         uint4* mk = reinterpret_cast<uint4*>(blob_mask<PL>(nt));
@@ -1834,6 +1835,7 @@ struct WgradWork {
   int B, Kn, T, splits;
   const uint8_t* blobs;
   const NetScales* sc;
+  const float* uvec;       // [Kn][H] u = Wb^T wo (split modes: the J operand of dWa is rebuilt from u and the m3 mask)
   float *gW1, *gW2, *gWa, *gWd;
   float *gb1, *gb2, *ge, *gbd, *gba;
 };
@@ -1999,6 +2001,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2], acc_ready;
   __shared__ uint32_t tmem_s;
+  __shared__ uint32_t su_hi[64], su_lo[64];                          // layer 2: u sUM of this out-half as packed 16-bit pairs, hi / lo plane
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   // the two CTAs of a cluster are the two output halves (mh) of one (sample, net, layer, split): they contract against the SAME Z
@@ -2013,14 +2016,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
   const int KCz = Nn / 8;                                             // k-cores of the Z tile
   const bool aux = layer != 1;                                        // layer 1 shares its J operand (y) with layer 3, which delivers db2
   const uint32_t zplane = (uint32_t)wg2::PT * Nn * 2;                 // bytes of one plane of a Z half-tile
-  const int jsel = layer == 0 ? B_QM : (layer == 2 ? B_UM : B_YT);
+  const int jsel = layer == 0 ? B_QM : B_YT;                          // layer 2: J = u [a3 > 0] is built in shared memory from the m3 mask
+  const bool build_j = layer == 2;
   const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
   const int nst = 2 * (t1 - t0);                                      // half-tiles
   if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_init(&empty[0], 2); mbar_init(&empty[1], 2); mbar_init(&acc_ready, 1);
+    mbar_init(&full[0], build_j ? 129 : 1); mbar_init(&full[1], build_j ? 129 : 1); mbar_init(&empty[0], 2); mbar_init(&empty[1], 2); mbar_init(&acc_ready, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(&tmem_s, 512);
+  if (build_j && tid < 64) {                                         // the same split pass 1 applied to um before it stopped storing it
+    const float s_um = F16 ? w.sc[(size_t)b * w.Kn + k].sUM : 1.f;
+    float u2[8] = {__ldg(w.uvec + (size_t)k * H + mh * TP + 2 * tid) * s_um, __ldg(w.uvec + (size_t)k * H + mh * TP + 2 * tid + 1) * s_um,
+                   0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint4 pq[PL];
+    split8<PL, F16>(u2, pq);
+    su_hi[tid] = pq[0].x; su_lo[tid] = pq[1].x;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -2041,11 +2053,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
         uint8_t* st = smem + s * wg2::STAGE;
         mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);                     // BOTH CTAs are done with the previous occupant (multicast commits)
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], 2 * wg2::J_PLANE + 2 * zplane + (aux ? wg2::X_BYTES : 0));   // my J + both halves of Z / seeds
+          mbar_arrive_expect_tx(&full[s], (build_j ? 0 : 2 * wg2::J_PLANE) + 2 * zplane + (aux ? wg2::X_BYTES : 0));   // my J + both halves of Z / seeds
           const uint32_t zh = zplane / 2, xh = wg2::X_BYTES / 2;
 #pragma unroll
           for (int p = 0; p < PL; ++p) {
-            bulk_g2s(st + p * wg2::J_PLANE, jsrc + (size_t)p * BLOB_H, wg2::J_PLANE, &full[s]);
+            if (!build_j) bulk_g2s(st + p * wg2::J_PLANE, jsrc + (size_t)p * BLOB_H, wg2::J_PLANE, &full[s]);
             bulk_g2s_mc(st + 2 * wg2::J_PLANE + p * wg2::Z_PLANE + mh * zh, zsrc + (size_t)p * zstride + mh * zh, zh, &full[s], (uint16_t)3);
           }
           if (aux) bulk_g2s_mc(st + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE + mh * xh, xsrc + mh * xh, xh, &full[s], (uint16_t)3);
@@ -2086,6 +2098,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
       }
       if (elect_one()) mma_commit(&acc_ready);
     } else if (warp < 4) {
+      if (build_j) {
+        // J half-tile = [16 k-cores][64 points][8 features]: thread = (point, 64-feature group g): 8 pieces per plane from 64 mask bits
+        const int pt = tid & 63, gq = tid >> 6;
+        for (int i = 0; i < nst; ++i) {
+          const int t = t0 + (i >> 1), ph = i & 1, s = i & 1;
+          const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
+          const uint2 mw = __ldg(reinterpret_cast<const uint2*>(nt + off_mask<PL>() + MASK_BYTES / 2) + (size_t)(ph * wg2::PT + pt) * 4 + mh * 2 + gq);
+          uint8_t* st = smem + s * wg2::STAGE;
+          mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);                   // both CTAs' MMAs are done with the previous occupant of the stage
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t bits = ((j < 4 ? mw.x : mw.y) >> ((j & 3) * 8)) & 0xFFu;
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t m = (((bits >> (2 * e)) & 1u) ? 0x0000FFFFu : 0u) | (((bits >> (2 * e + 1)) & 1u) ? 0xFFFF0000u : 0u);
+              hi[e] = su_hi[gq * 32 + j * 4 + e] & m;
+              lo[e] = su_lo[gq * 32 + j * 4 + e] & m;
+            }
+            const uint32_t off = (uint32_t)(gq * 8 + j) * (wg2::PT * 16) + (uint32_t)pt * 16;
+            *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(st + wg2::J_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async();                                         // generic-proxy stores -> visible to the tensor core's reads
+          mbar_arrive(&full[s]);
+        }
+      }
       mbar_wait(&acc_ready, 0);                                        // every MMA has completed: both stages are idle
       tc_fence_after();
       const size_t gk = ((size_t)b * w.Kn + k);
@@ -2625,7 +2664,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     else pass2_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
     DPN_LAUNCH_OK();
     WgradWork ww;
-    ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc;
+    ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc; ww.uvec = c.uvec;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd; ww.gba = G.ba;
     const int items = B * Kn * 8;
