@@ -30,7 +30,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 ALGO_FLOP_PER_POINT = 31.89e6      # fwd + Jacobian + bwd, GEMM work only
-EXEC_FLOP_PER_POINT = 6 * 2 * (407040 + 179200 + 228352)   # contraction FLOPs of the executed algorithm
+# contraction FLOPs of the executed algorithm: pass 1 + pass 2 + weight gradients, 6 nets, 2 FLOP per MAC;
+# the split modes run pass 2 as the forward pass of the combined row (229 376 MACs), the bf16 mode as the tangent chain (179 200)
+EXEC_FLOP = {m: 6 * 2 * (407040 + p2 + 228352) for m, p2 in (('f16x3', 229376), ('bf16x3', 229376), ('bf16', 179200), ('fp32', 179200))}
 MMA_PASSES = {"bf16": 1, "bf16x3": 3, "f16x3": 3, "fp32": 1}   # tensor-core MMAs issued per contraction (split operands: 3)
 DTYPE = {"bf16": "bf16", "bf16x3": "bf16 hi+lo (3 MMAs), fp32 accumulate", "f16x3": "fp16 hi+lo scaled (3 MMAs), fp32 accumulate", "fp32": "f32"}
 METRIC = "pde_residual_query_points_per_sec_fwd_jacobian_bwd"
@@ -541,12 +543,12 @@ def main():
             traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved / pk["bf16"],
                 "traffic": traffic,
-                "kernel": "dpn_pde_fwd_bwd: all kernels of one call (pass1 / pass2 / wgrad tcgen05 kernels + encode, residual, scale plan)",
+                "kernel": "dpn_pde_fwd_bwd: all kernels of one call (pass1_ts / pass2z / wgrad2 tcgen05 kernels + encode, residual, scale plan)",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % pk["source"],
-                "algorithmic_flop_per_point": ALGO_FLOP_PER_POINT, "executed_flop_per_point": EXEC_FLOP_PER_POINT,
-                "executed_tflops": EXEC_FLOP_PER_POINT * per_gpu_pts / 1e12,
+                "algorithmic_flop_per_point": ALGO_FLOP_PER_POINT, "executed_flop_per_point": EXEC_FLOP[args.mode],
+                "executed_tflops": EXEC_FLOP[args.mode] * per_gpu_pts / 1e12,
                 "mma_passes_per_contraction": MMA_PASSES[args.mode],
-                "tensor_pipe_tflops": MMA_PASSES[args.mode] * EXEC_FLOP_PER_POINT * per_gpu_pts / 1e12}
+                "tensor_pipe_tflops": MMA_PASSES[args.mode] * EXEC_FLOP[args.mode] * per_gpu_pts / 1e12}
 
     # ---- the reference's own way of running this path on the same GPU: PyTorch eager autograd (double backward) ----
     eager_gpu = None
