@@ -819,23 +819,36 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 // Pass 1 with the activation tile in TENSOR MEMORY (split modes; opt-in: DPN_TS=1).
 // The A operand of every GEMM but G1 / G2b is written by the epilogues with tcgen05.st and read by the TS form of tcgen05.mma; the
 // PE / PE6 tiles of G1 / G2b travel through the ring as K = 16 slices next to their weight chunks; tiles kept for the backward pass
-// leave with streaming 16-byte stores from registers.  No activation buffer in shared memory -> the ring holds 9 stages of 24 KB
-// instead of 5 of 16 KB (the weight stream paces today's kernel, section 9).  TMEM is full (accumulator [0,256) | A_hi [256,384) |
-// A_lo [384,512); K-chunk c of a plane = columns base + 8c .. 8c+7), so there is no FOLD: q = y W2 runs as its own round.
+// leave with streaming 16-byte stores from registers.  No activation buffer in shared memory -> the ring holds 9 stages of 24 KB.
+//
+// Tensor memory = two 256-column regions R0 | R1 used as PING-PONG accumulators with IN-PLACE conversion: the epilogue of GEMM j
+// reads a 32-column block of the fp32 accumulator (32 outputs of this row) and writes the two 16-bit planes of the same 32 values
+// back into the SAME 32 columns (hi -> columns +0..15, lo -> +16..31; K-chunk c of the next contraction = columns 32 (c / 2) +
+// 8 (c % 2), lo 16 further).  GEMM j + 1 accumulates into the OTHER region and starts on a K-chunk as soon as the epilogue has
+// converted that block (one mbarrier per block, weights streamed in block order), so the tensor pipe runs under the epilogue of
+// the previous GEMM instead of after it; the K-chunks without a dependence on the epilogue (PE6 Wd^T of G2, G1 of the next net)
+// are issued first.  tcgen05.mma executes in issue order, so a region that was the A operand of GEMM j is safe to be the
+// accumulator of GEMM j + 1.
 // ------------------------------------------------------------------------------------------------
 namespace ts {
 constexpr int NS = 9;
 constexpr int W_BYTES = 2 * STAGE_BYTES;        // weight chunk [256 x 16] : hi 8 KB | lo 8 KB   ([192 x 16]: 6 KB | 6 KB)
 constexpr int A_PLANE = 2 * CORE_STRIDE;        // A slice [128 x 16] of one plane: 4 KB
 constexpr int STAGE = W_BYTES + 2 * A_PLANE;    // 24 KB
-constexpr uint32_t COL_AH = 256, COL_AL = 384;
+constexpr uint32_t REGION = 256;               // TMEM columns of one ping-pong region
 constexpr int SMEM = NS * STAGE + NVEC * H * 4 + TP * 4 * 4;
 struct PipeTS {
-  uint64_t full[NS], empty[NS], a_epi, acc_ready;
+  uint64_t full[NS], empty[NS];
+  uint64_t blk[4];          // block cb of BOTH column halves of the next A operand is in tensor memory (one arrival per epilogue warp)
+  uint64_t acc_ready[2];    // the GEMM accumulating into region 0 / 1 has completed
+  uint64_t drained;         // the last epilogue of a net (which hands no operand on) has read its accumulator
   uint32_t tmem_base;
 };
 static_assert(SMEM + (int)sizeof(PipeTS) + 1024 <= 227 * 1024, "pass1_ts_kernel: ring + vectors + row sums + barriers must fit one SM's 227 KB");
-static_assert(COL_AL + 128 == 512 && COL_AH + 128 == COL_AL && COL_AH == H, "TMEM map: accumulator | A_hi | A_lo fills the 512 columns");
+static_assert(2 * REGION == 512 && REGION == H, "TMEM map: two [128 x 256] fp32 accumulators, each converted in place into 2 x 16-bit planes");
+// K-chunk order of a TS-form GEMM: the two epilogue warp groups finish block cb of their column halves together, i.e. chunks
+// 2cb, 2cb+1 (half 0) and 8+2cb, 9+2cb (half 1)
+__host__ __device__ constexpr int block_order(int i) { return ((i >> 2) << 1) + (i & 1) + ((i >> 1) & 1) * 8; }
 }  // namespace ts
 
 template <bool F16>
@@ -852,8 +865,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   const size_t g = blockIdx.x;
   if (tid == 0) {
     for (int s = 0; s < ts::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
-    mbar_init(&pipe.a_epi, Geo<PL>::ET);
-    mbar_init(&pipe.acc_ready, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&pipe.blk[i], Geo<PL>::EW);
+    mbar_init(&pipe.acc_ready[0], 1); mbar_init(&pipe.acc_ready[1], 1);
+    mbar_init(&pipe.drained, Geo<PL>::EW);
     fence_barrier_init();
   }
   if (warp == Geo<PL>::W_MMA) tmem_alloc(&pipe.tmem_base, 512);
@@ -894,68 +908,80 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
       const uint8_t *iW1 = gen, *iW1T = gen + PL * IMG_HC, *iW2 = gen + PL * 2 * IMG_HC, *iW2T = gen + PL * (2 * IMG_HC + IMG_HH);
       const uint8_t *iWd = sta, *iWa = sta + PL * IMG_HC, *iWaT = sta + PL * (IMG_HC + IMG_HH);
+      // the MMA warp's order: G1 | G2b (PE6 slices: no dependence on an epilogue, issued first) | TS-form GEMMs in block order
       for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe_src + (size_t)c * ts::A_PLANE);
-      for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
       for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE);
-      for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
+      for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
+      for (int i = 0; i < 16; ++i) put(iWa + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
       if (sweep) {
-        for (int c = 0; c < 16; ++c) put(iWaT + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
-        for (int c = 0; c < 16; ++c) put(iW2T + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr);
+        for (int i = 0; i < 16; ++i) put(iWaT + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
+        for (int i = 0; i < 16; ++i) put(iW2T + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
         if (sweep > 1)
-          for (int c = 0; c < 16; ++c) put(iW1T + (size_t)c * (PL * 6144), PL * 6144, nullptr);
+          for (int i = 0; i < 16; ++i) put(iW1T + (size_t)ts::block_order(i) * (PL * 6144), PL * 6144, nullptr);
       }
     }
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
-    uint32_t s = 0, ph = 0, ae = 0;
+    uint32_t s = 0, ph = 0, bp = 0, dr = 0, cur = 0;
     long long t_full = 0, t_epi = 0;
     const bool timed = w.phase_dbg != nullptr;
     const long long t_begin = clock64();
     const uint32_t ring_addr = smem_u32(ring);
     const uint64_t a_base = smem_desc(ring_addr + ts::W_BYTES, CORE_STRIDE, 128);
-    auto gemm = [&](const int nchunks, const int Nn, const bool a_in_tmem, const bool accumulate) {
+    // one K = 16 chunk: lo*hi + hi*lo + hi*hi into the accumulator at column d; A planes from tensor memory (a_hi) or from the stage
+    auto chunk = [&](const uint32_t d, const int Nn, const bool a_in_tmem, const uint32_t a_hi, const uint32_t first) {
       const uint32_t idesc = idesc_16(F16, Nn, 0, 0, 128);
       const uint64_t b_base = smem_desc(ring_addr, Nn * 16, 128);
       const uint32_t b_lo = (uint32_t)(Nn * 32) >> 4;
-      for (int c = 0; c < nchunks; ++c) {
-        if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
-        tc_fence_after();
-        const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
-        const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
-        if (elect_one()) {
-          if (a_in_tmem) {                               // lo*hi + hi*lo + hi*hi, A planes from tensor memory
-            mma_ts(tmem, tmem + ts::COL_AL + 8 * c, bd, idesc, first);
-            mma_ts(tmem, tmem + ts::COL_AH + 8 * c, bl, idesc, 1u);
-            mma_ts(tmem, tmem + ts::COL_AH + 8 * c, bd, idesc, 1u);
-          } else {                                       // the A slice of this chunk sits behind the weights in the same stage
-            const uint64_t ad = a_base + s * (uint32_t)(ts::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
-            mma_bf16(tmem, al, bd, idesc, first);
-            mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bl, idesc, 1u);
-            mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem, ad, bd, idesc, 1u);
-          }
-          if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
+      if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
+      tc_fence_after();
+      const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
+      if (elect_one()) {
+        if (a_in_tmem) {
+          mma_ts(d, a_hi + 16, bd, idesc, first);
+          mma_ts(d, a_hi, bl, idesc, 1u);
+          mma_ts(d, a_hi, bd, idesc, 1u);
+        } else {                                         // the A slice of this chunk sits behind the weights in the same stage
+          const uint64_t ad = a_base + s * (uint32_t)(ts::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
+          mma_bf16(d, al, bd, idesc, first);
+          mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
+          mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
         }
-        if (++s == ts::NS) { s = 0; ph ^= 1; }
+        if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
       }
+      if (++s == ts::NS) { s = 0; ph ^= 1; }
     };
-    auto wait_epi = [&]() { if (timed) mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); else mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
-    auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready); };
-    for (int k = 0; k < w.Kn; ++k) {
-      if (k > 0) wait_epi();                                               // the last epilogue of the previous net has drained the accumulator
-      gemm(12, H, false, false); ready();                                  // G1
-      wait_epi();
-      gemm(16, H, true, false); gemm(12, H, false, true); ready();         // G2a (A = h1 in TMEM) + G2b (A = PE6 slices)
-      wait_epi();
-      gemm(16, H, true, false); ready();                                   // G3 (A = c)
-      if (sweep) {
-        wait_epi();
-        gemm(16, H, true, false); ready();                                 // G4 (A = um)
-        wait_epi();
-        gemm(16, H, true, false); ready();                                 // G5 (A = y)
-        if (sweep > 1) {
-          wait_epi();
-          gemm(16, C, true, false); ready();                               // G6 (A = qm, N = 192)
+    // G over the PE / PE6 slices of the ring into region `cur`
+    auto gemm_ss = [&](const int nchunks) {
+      for (int c = 0; c < nchunks; ++c) chunk(tmem + cur * ts::REGION, H, false, 0u, c > 0 ? 1u : 0u);
+    };
+    // G whose A operand is the other region, converted in place by the running epilogue: block by block
+    auto gemm_ts = [&](const int Nn, const bool accumulate) {
+      const uint32_t d = tmem + cur * ts::REGION, a = tmem + (cur ^ 1u) * ts::REGION;
+      for (int cb = 0; cb < 4; ++cb) {
+        if (timed) mbar_wait_t(&pipe.blk[cb], bp, t_epi); else mbar_wait(&pipe.blk[cb], bp);
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 2 * cb + (j & 1) + (j >> 1) * 8;
+          chunk(d, Nn, true, a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1), (accumulate || cb > 0 || j > 0) ? 1u : 0u);
         }
+      }
+      bp ^= 1u;
+    };
+    auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready[cur]); cur ^= 1u; };
+    for (int k = 0; k < w.Kn; ++k) {
+      gemm_ss(12); ready();                                                // G1 (A = PE slices); its region was the A operand of the previous GEMM
+      if (k > 0) {                                                         // the last epilogue of the previous net has drained this region
+        if (timed) mbar_wait_t(&pipe.drained, dr & 1, t_epi); else mbar_wait(&pipe.drained, dr & 1);
+        ++dr; tc_fence_after();
+      }
+      gemm_ss(12); gemm_ts(H, true); ready();                              // G2b (A = PE6 slices) + G2a (A = h1)
+      gemm_ts(H, false); ready();                                          // G3 (A = c)
+      if (sweep) {
+        gemm_ts(H, false); ready();                                        // G4 (A = um)
+        gemm_ts(H, false); ready();                                        // G5 (A = y)
+        if (sweep > 1) { gemm_ts(C, false); ready(); }                     // G6 (A = qm, N = 192)
       }
     }
     if (timed && lane == 0) {
@@ -968,16 +994,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     constexpr int NB = Geo<PL>::NB;
     const int half = warp >> 2, r = (warp & 3) * 32 + lane, c0 = half * NB;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t tl_addr = lane_base + half * (NB * 32);
     const int p_local = tl * TP + r;
     const bool valid = p_local < w.P;
     const size_t q = (size_t)b * w.N + w.p0 + p_local;
     const size_t row = g * TP + r;
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     const uint64_t pol_keep = l2_policy_evict_last();
-    uint32_t ar = 0;
-    // 32 columns of this row: split into the two planes once, then -> workspace tile (if any) and / or the next A operand in TMEM
-    auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a) {
+    uint32_t arc0 = 0u, arc1 = 0u, cur = 0u;
+    // 32 columns of this row: split into the two planes once, then -> workspace tile (if any) and / or IN PLACE over the accumulator
+    // block they came from (blk_addr): the next A operand
+    auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a, const uint32_t blk_addr) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) {
@@ -992,15 +1018,26 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
       }
       if (to_a) {
-        tmem_st16(lane_base + ts::COL_AH + cg * 16, hi);
-        tmem_st16(lane_base + ts::COL_AL + cg * 16, lo);
+        tmem_st16(blk_addr, hi);
+        tmem_st16(blk_addr + 16, lo);
       }
     };
-    auto done = [&]() { tmem_st_wait(); tc_fence_before(); mbar_arrive(&pipe.a_epi); };
+    // this warp's part of block cb is in tensor memory / this warp has read the last accumulator of the net: one arrival per warp
+    auto blk_done = [&](const int cb) { tmem_st_wait(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&pipe.blk[cb]); };
+    auto net_done = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&pipe.drained); };
     long long t_acc = 0;
     const long long t_begin = clock64();
     const bool timed = w.phase_dbg != nullptr;
-    auto acc_wait = [&]() { if (timed) mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); else mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
+    // waits for the GEMM into the current region; returns this thread's lane address of that region and flips the region
+    auto acc_wait = [&]() -> uint32_t {
+      const uint32_t par = (cur ? arc1 : arc0) & 1u;
+      if (timed) mbar_wait_t(&pipe.acc_ready[cur], par, t_acc); else mbar_wait(&pipe.acc_ready[cur], par);
+      if (cur) ++arc1; else ++arc0;
+      tc_fence_after();
+      const uint32_t a = lane_base + cur * ts::REGION;
+      cur ^= 1u;
+      return a;
+    };
     if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile<PL>(w, b, k, tl);
@@ -1018,12 +1055,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
       for (int i = 0; i < NB; ++i) m1w[i] = 0u;
       // ---- epilogue 1: h1 = relu(a1 + b1) ----
-      acc_wait();
+      uint32_t ra = acc_wait();
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(ra + cg * 32, v);
         uint32_t bits = 0;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -1038,17 +1075,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
-        emit(cg, v, nullptr, true);                                   // h1 itself is not kept: pass 2 needs only its mask
+        emit(cg, v, nullptr, true, ra + cg * 32);                     // h1 itself is not kept: pass 2 needs only its mask
+        blk_done(cb);
       }
-      done();
       // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
       float os0 = 0.f, os1 = 0.f;
-      acc_wait();
+      ra = acc_wait();
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(ra + cg * 32, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cg * 32 + j4 * 4);
@@ -1061,19 +1098,19 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
             v[j4 * 4 + e] = F16 ? cc * sC : cc;
           }
         }
-        emit(cg, v, nullptr, true);
+        emit(cg, v, nullptr, true, ra + cg * 32);
+        blk_done(cb);
       }
-      done();
       // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
       uint32_t m3w[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) m3w[i] = 0u;
-      acc_wait();
+      ra = acc_wait();
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(ra + cg * 32, v);
         uint32_t bits = 0u;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
@@ -1092,8 +1129,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) m3w[i] = (cb == i) ? bits : m3w[i];
-        if (sweep) emit(cg, v, nullptr, true);                        // um = u [a3 > 0] is rebuilt from the mask by wgrad2_kernel
+        if (sweep) { emit(cg, v, nullptr, true, ra + cg * 32); blk_done(cb); }   // (wgrad2_kernel rebuilds um from the mask: not stored)
       }
+      if (!sweep) net_done();
       if (sweep) {                                                     // the two ReLU masks of this (net, tile): all pass 2 needs of h1 / c / g
         uint4* mk = reinterpret_cast<uint4*>(blob_mask<PL>(nt));
         static_assert(NB == 4, "one uint4 of mask words per thread");
@@ -1101,7 +1139,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         mk[(TP + r) * 2 + half] = make_uint4(m3w[0], m3w[1], m3w[2], m3w[3]);
       }
       atomicAdd(rowsum + r * 4, os0 + os1);
-      done();
       epi_bar<PL>();
       if (half == 0) {
         if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + (w.ref ? __ldg(w.ref + q * w.Kn + k) : __ldg(w.coord_data + q * 6 + k));
@@ -1109,12 +1146,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       }
       if (!sweep) continue;
       // ---- epilogue 4: y = acc + 2wo ----
-      acc_wait();
+      ra = acc_wait();
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(ra + cg * 32, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
@@ -1122,30 +1159,30 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
           for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = F16 ? fmaf(v[j4 * 4 + e], i4, ww[e]) * sY : v[j4 * 4 + e] + ww[e];
         }
-        emit(cg, v, blob_h<PL>(nt, B_YT), true);
+        emit(cg, v, blob_h<PL>(nt, B_YT), true, ra + cg * 32);
+        blk_done(cb);
       }
-      done();
       // ---- epilogue 5: qm = acc * m1 ----
-      acc_wait();
+      ra = acc_wait();
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(ra + cg * 32, v);
         uint32_t bits = 0u;
 #pragma unroll
         for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
-        emit(cg, v, blob_h<PL>(nt, B_QM), sweep > 1);
+        emit(cg, v, blob_h<PL>(nt, B_QM), sweep > 1, ra + cg * 32);
+        if (sweep > 1) blk_done(cb);
       }
-      done();
-      if (sweep < 2) continue;
+      if (sweep < 2) { net_done(); continue; }
       // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
-      acc_wait();
+      ra = acc_wait();
       float dz[3] = {0.f, 0.f, 0.f};
       {
-        const uint32_t a6 = lane_base + half * 96;
+        const uint32_t a6 = ra + half * 96;
         const float bsel = half ? 1.f : 0.f;
 #pragma unroll
         for (int ib = 0; ib < 3; ++ib) {
@@ -1163,7 +1200,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, F16 ? dz[c] * i6 : dz[c]);
-      done();
+      net_done();
       epi_bar<PL>();
       if (half == 0) {
 #pragma unroll
@@ -1462,8 +1499,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 // i.e. pass 2 is pass 1's value chain applied to the row zp with the FROZEN masks and dov-scaled biases.  It needs from pass 1
 // two bit masks per point (64 bytes) instead of the h1 / c / g tiles (3 KB), no separate tangent row, and every tile it produces
 // is at once the next A operand and the stored wgrad operand (one split instead of two).
-// Structure = pass1_ts_kernel: accumulator TMEM [0,256), A planes [256,384) | [384,512), TS-form MMAs; the zd tile is staged in
-// shared memory (96 KB, layout (*)) as the A operand of the K = 192 accumulate of G8; 7 x 16 KB weight ring.
+// Structure = pass1_ts_kernel: two 256-column TMEM regions as ping-pong accumulators, converted in place into the next A operand,
+// the next GEMM starting block by block under the running epilogue.  Per net: the prologue writes zp into R1 (hi planes columns
+// [0,96), lo [96,192)) while G7' (-> R0) consumes it; epilogue 7 converts R0 into zh while G8' (-> R1, first the K = 192 part whose
+// A operand zd is staged in shared memory, 96 KB, layout (*)) consumes it; epilogue 8 converts R1 into zc under G9' (-> R0);
+// epilogue 9 reads R0 and the next net's prologue follows in the same threads (so G7' of the next net cannot start before the
+// accumulator is drained).  7 x 16 KB weight ring.
 // ------------------------------------------------------------------------------------------------
 namespace p2z {
 constexpr int NS = 7;
@@ -1471,11 +1512,16 @@ constexpr int W_BYTES = 2 * STAGE_BYTES;         // one K = 16 chunk of a [256 x
 constexpr int ZD_BYTES = 2 * BLOB_C;             // zd staging: plane hi | plane lo, [128 x 192] each, layout (*)
 enum { V2_B1 = 0, V2_BSUM, V2_BA, NV2 };
 constexpr int SMEM = NS * W_BYTES + ZD_BYTES + NV2 * H * 4 + 2 * H * 4 + 16;      // + column sums [zc | gz] + sum of dov
-constexpr uint32_t COL_AH = 256, COL_AL = 384;
+constexpr uint32_t REGION = 256, ZP_LO = 96;   // TMEM: regions R0 | R1; zp planes inside R1: hi [0,96) | lo [96,192)
 struct PipeZ {
-  uint64_t full[NS], empty[NS], a_epi, acc_ready;
+  uint64_t full[NS], empty[NS];
+  uint64_t blk[4];          // block i of both column halves of the next A operand is in tensor memory (one arrival per epilogue warp)
+  uint64_t acc_ready[2];    // the GEMM accumulating into region 0 / 1 has completed
   uint32_t tmem_base;
 };
+// K-chunks of zp (K = 192) complete after prologue iteration i of both halves: a half writes 24 columns = 1.5 chunks per iteration
+__host__ __device__ constexpr int zp_first(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 3 : 4; }
+__host__ __device__ constexpr int zp_count(int i) { return (i & 1) ? 2 : 1; }
 static_assert(SMEM + (int)sizeof(PipeZ) + 1024 <= 227 * 1024, "pass2z_kernel: ring + zd tile + vectors must fit one SM's 227 KB");
 }  // namespace p2z
 
@@ -1494,8 +1540,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   const size_t g = blockIdx.x;
   if (tid == 0) {
     for (int s = 0; s < p2z::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
-    mbar_init(&pipe.a_epi, Geo<PL>::ET);
-    mbar_init(&pipe.acc_ready, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&pipe.blk[i], Geo<PL>::EW);
+    mbar_init(&pipe.acc_ready[0], 1); mbar_init(&pipe.acc_ready[1], 1);
     fence_barrier_init();
   }
   if (warp == Geo<PL>::W_MMA) tmem_alloc(&pipe.tmem_base, 512);
@@ -1529,14 +1575,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
       const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
       const uint8_t *iW1 = gen, *iW2 = gen + PL * 2 * IMG_HC, *iWd = sta, *iWa = sta + PL * IMG_HC;
-      for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * p2z::W_BYTES);
-      for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * p2z::W_BYTES);
+      // the MMA warp's order: G7' in prologue-block order | zd Wd^T (no dependence on an epilogue) | G8', G9' in block order
+      for (int i = 0; i < 4; ++i)
+        for (int h = 0; h < 2; ++h)
+          for (int j = 0; j < p2z::zp_count(i); ++j) put(iW1 + (size_t)(6 * h + p2z::zp_first(i) + j) * p2z::W_BYTES);
       for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * p2z::W_BYTES);
-      for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * p2z::W_BYTES);
+      for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * p2z::W_BYTES);
+      for (int i = 0; i < 16; ++i) put(iWa + (size_t)ts::block_order(i) * p2z::W_BYTES);
     }
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
-    uint32_t s = 0, ph = 0, ae = 0;
+    uint32_t s = 0, ph = 0, bp = 0;
     long long t_full = 0, t_epi = 0;
     const bool timed = w.phase_dbg != nullptr;
     const long long t_begin = clock64();
@@ -1545,37 +1594,56 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     const uint64_t b_base = smem_desc(ring_addr, H * 16, 128);
     const uint64_t zd_base = smem_desc(smem_u32(zdt), CORE_STRIDE, 128);
     constexpr uint32_t b_lo = (uint32_t)(H * 32) >> 4, zd_lo = BLOB_C >> 4, zd_step = (2 * CORE_STRIDE) >> 4;
-    auto gemm = [&](const int nchunks, const bool a_in_tmem, const bool accumulate) {
-      for (int c = 0; c < nchunks; ++c) {
-        if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
-        tc_fence_after();
-        const uint64_t bd = b_base + s * (uint32_t)(p2z::W_BYTES >> 4), bl = bd + b_lo;
-        const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
-        if (elect_one()) {
-          if (a_in_tmem) {                               // lo*hi + hi*lo + hi*hi, A planes from tensor memory
-            mma_ts(tmem, tmem + p2z::COL_AL + 8 * c, bd, idesc, first);
-            mma_ts(tmem, tmem + p2z::COL_AH + 8 * c, bl, idesc, 1u);
-            mma_ts(tmem, tmem + p2z::COL_AH + 8 * c, bd, idesc, 1u);
-          } else {                                       // A = K-slice c of the zd tile in shared memory
-            const uint64_t ad = zd_base + (uint32_t)c * zd_step, al = ad + zd_lo;
-            mma_bf16(tmem, al, bd, idesc, first);
-            mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bl, idesc, 1u);
-            mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem, ad, bd, idesc, 1u);
-          }
-          if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
+    const uint32_t R0 = tmem, R1 = tmem + p2z::REGION;
+    // one K = 16 chunk: lo*hi + hi*lo + hi*hi into the accumulator at d; A planes from tensor memory (a_hi / a_lo) or K-slice zc of the zd tile
+    auto chunk = [&](const uint32_t d, const bool a_in_tmem, const uint32_t a_hi, const uint32_t a_lo, const int zc, const uint32_t first) {
+      if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
+      tc_fence_after();
+      const uint64_t bd = b_base + s * (uint32_t)(p2z::W_BYTES >> 4), bl = bd + b_lo;
+      if (elect_one()) {
+        if (a_in_tmem) {
+          mma_ts(d, a_lo, bd, idesc, first);
+          mma_ts(d, a_hi, bl, idesc, 1u);
+          mma_ts(d, a_hi, bd, idesc, 1u);
+        } else {
+          const uint64_t ad = zd_base + (uint32_t)zc * zd_step, al = ad + zd_lo;
+          mma_bf16(d, al, bd, idesc, first);
+          mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
+          mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
         }
-        if (++s == p2z::NS) { s = 0; ph ^= 1; }
+        if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
       }
+      if (++s == p2z::NS) { s = 0; ph ^= 1; }
     };
-    auto wait_epi = [&]() { if (timed) mbar_wait_t(&pipe.a_epi, ae & 1, t_epi); else mbar_wait(&pipe.a_epi, ae & 1); ++ae; tc_fence_after(); };
-    auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready); };
+    auto wait_blk = [&](const int i) { if (timed) mbar_wait_t(&pipe.blk[i], bp, t_epi); else mbar_wait(&pipe.blk[i], bp); tc_fence_after(); };
+    // K = 256 GEMM whose A operand is region a, converted in place by the running epilogue
+    auto gemm_ts = [&](const uint32_t d, const uint32_t a, const bool accumulate) {
+      for (int cb = 0; cb < 4; ++cb) {
+        wait_blk(cb);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 2 * cb + (j & 1) + (j >> 1) * 8;
+          const uint32_t ah = a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1);
+          chunk(d, true, ah, ah + 16, 0, (accumulate || cb > 0 || j > 0) ? 1u : 0u);
+        }
+      }
+      bp ^= 1u;
+    };
+    auto ready = [&](const int region) { if (elect_one()) mma_commit(&pipe.acc_ready[region]); };
     for (int k = 0; k < w.Kn; ++k) {
-      wait_epi();                                                          // prologue: zp in tensor memory, zd in shared memory
-      gemm(12, true, false); ready();                                      // G7' = zp W1^T
-      wait_epi();
-      gemm(16, true, false); gemm(12, false, true); ready();               // G8' = zh W2^T + zd Wd^T
-      wait_epi();
-      gemm(16, true, false); ready();                                      // G9' = zc Wa^T
+      for (int i = 0; i < 4; ++i) {                                        // G7' = zp W1^T -> R0, under the prologue
+        wait_blk(i);
+        for (int h = 0; h < 2; ++h)
+          for (int j = 0; j < p2z::zp_count(i); ++j) {
+            const uint32_t c = 6 * h + p2z::zp_first(i) + j;
+            chunk(R0, true, R1 + 8u * c, R1 + p2z::ZP_LO + 8u * c, 0, (i > 0 || h > 0 || j > 0) ? 1u : 0u);
+          }
+      }
+      bp ^= 1u;
+      ready(0);
+      for (int c = 0; c < 12; ++c) chunk(R1, false, 0u, 0u, c, c > 0 ? 1u : 0u);   // G8' = zd Wd^T (zd: shared memory, complete with the prologue)
+      gemm_ts(R1, R0, true); ready(1);                                     //       + zh W2^T, under epilogue 7
+      gemm_ts(R0, R1, false); ready(0);                                    // G9' = zc Wa^T, under epilogue 8
     }
     if (timed && lane == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
@@ -1587,19 +1655,25 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     constexpr int NB = Geo<PL>::NB;
     const int half = warp >> 2, r = (warp & 3) * 32 + lane, c0 = half * NB;
     const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t tl_addr = lane_base + half * (NB * 32);
     const size_t row = g * TP + r;
     const float* pet = w.pet + g * (size_t)(C * TP) + r;
     const uint8_t* pe6 = w.pe6_blob + g * Geo<PL>::BC;
     const uint64_t pol_keep = l2_policy_evict_last();
-    uint32_t ar = 0;
-    auto done = [&]() { tmem_st_wait(); tc_fence_before(); fence_proxy_async(); mbar_arrive(&pipe.a_epi); };
+    uint32_t ar0 = 0u, ar1 = 0u;
+    const uint32_t R0 = lane_base, R1 = lane_base + p2z::REGION;
+    // this warp's part of block i is in tensor memory (and, for the prologue, in the zd tile in shared memory): one arrival per warp
+    auto blk_done = [&](const int i) { tmem_st_wait(); tc_fence_before(); fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(&pipe.blk[i]); };
     long long t_acc = 0, t_pro = 0;
     const long long t_begin = clock64();
     const bool timed = w.phase_dbg != nullptr;
-    auto acc_wait = [&]() { if (timed) mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); else mbar_wait(&pipe.acc_ready, ar & 1); ++ar; tc_fence_after(); };
+    auto acc_wait = [&](const int region) {
+      const uint32_t par = (region ? ar1 : ar0) & 1u;
+      if (timed) mbar_wait_t(&pipe.acc_ready[region], par, t_acc); else mbar_wait(&pipe.acc_ready[region], par);
+      if (region) ++ar1; else ++ar0;
+      tc_fence_after();
+    };
     // 32 columns of this row, already scaled: split once -> workspace tile (wgrad operand) and / or the next A operand in TMEM
-    auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const bool to_a) {
+    auto emit = [&](const int cg, const float (&v)[32], uint8_t* blob, const uint32_t blk_addr) {
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int qd = 0; qd < 4; ++qd) {
@@ -1613,10 +1687,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
         lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
       }
-      if (to_a) {
-        tmem_st16(lane_base + p2z::COL_AH + cg * 16, hi);
-        tmem_st16(lane_base + p2z::COL_AL + cg * 16, lo);
-      }
+      tmem_st16(blk_addr, hi);                                         // in place: the planes replace the accumulator block they came from
+      tmem_st16(blk_addr + 16, lo);
     };
     for (int i = tid; i < 2 * H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
     for (int k = 0; k < w.Kn; ++k) {
@@ -1718,18 +1790,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           *reinterpret_cast<uint4*>(zdt + soff) = pq[0];
           *reinterpret_cast<uint4*>(zdt + BLOB_C + soff) = pq[1];
         }
-        tmem_st8(lane_base + p2z::COL_AH + it * 12, hi); tmem_st4(lane_base + p2z::COL_AH + it * 12 + 8, hi + 8);
-        tmem_st8(lane_base + p2z::COL_AL + it * 12, lo); tmem_st4(lane_base + p2z::COL_AL + it * 12 + 8, lo + 8);
+        tmem_st8(R1 + it * 12, hi); tmem_st4(R1 + it * 12 + 8, hi + 8);
+        tmem_st8(R1 + p2z::ZP_LO + it * 12, lo); tmem_st4(R1 + p2z::ZP_LO + it * 12 + 8, lo + 8);
+        blk_done(it - half * NB);
       }
-      done();
       if (timed) t_pro += clock64() - t_p0;
       // ---- epilogue 7: zh = m1 (acc + dov b1) ----
-      acc_wait();
+      acc_wait(0);
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(R0 + cg * 32, v);
         uint32_t bits = 0u;
 #pragma unroll
         for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
@@ -1744,16 +1816,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
             v[j] = ((bits >> j) & 1u) ? (F16 ? z * sZH : z) : 0.f;
           }
         }
-        emit(cg, v, blob_h<PL>(nt, B_ZH), true);
+        emit(cg, v, blob_h<PL>(nt, B_ZH), R0 + cg * 32);
+        blk_done(cb);
       }
-      done();
       // ---- epilogue 8: zc = acc + dov (b2 + bd + e);  column sum -> vc ----
-      acc_wait();
+      acc_wait(1);
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32], z[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(R1 + cg * 32, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const float4 bv = *reinterpret_cast<const float4*>(svec + p2z::V2_BSUM * H + cg * 32 + j4 * 4);
@@ -1765,18 +1837,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
             v[j] = F16 ? z[j] * sZC : z[j];
           }
         }
-        emit(cg, v, blob_h<PL>(nt, B_ZC), true);
+        emit(cg, v, blob_h<PL>(nt, B_ZC), R1 + cg * 32);
+        blk_done(cb);                                                  // G9' goes on; the column sum runs under it
         const float cs = warp_colsum32(z, lane);
         atomicAdd(csum + cg * 32 + lane, cs);
       }
-      done();
       // ---- epilogue 9: gz = m3 (acc + dov ba);  column sum -> vg ----
-      acc_wait();
+      acc_wait(0);
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
         const int cg = c0 + cb;
         float v[32];
-        tmem_ld32(tl_addr + cb * 32, v);
+        tmem_ld32(R0 + cg * 32, v);
         uint32_t bits = 0u;
 #pragma unroll
         for (int i = 0; i < NB; ++i) bits = (cb == i) ? m3w[i] : bits;
