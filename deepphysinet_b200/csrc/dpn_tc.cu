@@ -227,6 +227,7 @@ __device__ __forceinline__ void stg8(uint8_t* tile, uint32_t plane, uint32_t off
 // ------------------------------------------------------------------------------------------------
 struct NetScales {                       // one per (sample, net)
   float sW1, sW2, sWd, sWa, sP;          // weight images (a matrix and its transpose share the factor); P = Wa W2
+  float sWaU;                            // split modes: the image of diag(u) Wa (B operand of G4, whose A operand is the bare m3 mask)
   float sH1, sC, sG, sUM, sY, sQ;        // tiles written by pass 1: h1, c, g, u*m3, y, q*m1
   float M1, Mc, l1W1, l1W12;             // bounds of |h1|, |c|; L1(W1), L1(W1) L1(W2)
   float rowB;                            // max(1, L1(W1), L1(W1) L1(W2)): growth of the pass-2 tangent row over its chain
@@ -929,7 +930,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     const uint32_t ring_addr = smem_u32(ring);
     const uint64_t a_base = smem_desc(ring_addr + ts::W_BYTES, CORE_STRIDE, 128);
     // one K = 16 chunk: lo*hi + hi*lo + hi*hi into the accumulator at column d; A planes from tensor memory (a_hi) or from the stage
-    auto chunk = [&](const uint32_t d, const int Nn, const bool a_in_tmem, const uint32_t a_hi, const uint32_t first) {
+    auto chunk = [&](const uint32_t d, const int Nn, const bool a_in_tmem, const uint32_t a_hi, const uint32_t first, const bool a_exact = false) {
       const uint32_t idesc = idesc_16(F16, Nn, 0, 0, 128);
       const uint64_t b_base = smem_desc(ring_addr, Nn * 16, 128);
       const uint32_t b_lo = (uint32_t)(Nn * 32) >> 4;
@@ -938,8 +939,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
       if (elect_one()) {
         if (a_in_tmem) {
-          mma_ts(d, a_hi + 16, bd, idesc, first);
-          mma_ts(d, a_hi, bl, idesc, 1u);
+          if (!a_exact) mma_ts(d, a_hi + 16, bd, idesc, first);            // (an exact 16-bit A operand - the 0 / 1 mask of G4 - has no lo plane)
+          mma_ts(d, a_hi, bl, idesc, a_exact ? first : 1u);
           mma_ts(d, a_hi, bd, idesc, 1u);
         } else {                                         // the A slice of this chunk sits behind the weights in the same stage
           const uint64_t ad = a_base + s * (uint32_t)(ts::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
@@ -956,7 +957,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int c = 0; c < nchunks; ++c) chunk(tmem + cur * ts::REGION, H, false, 0u, c > 0 ? 1u : 0u);
     };
     // G whose A operand is the other region, converted in place by the running epilogue: block by block
-    auto gemm_ts = [&](const int Nn, const bool accumulate) {
+    auto gemm_ts = [&](const int Nn, const bool accumulate, const bool a_exact = false) {
       const uint32_t d = tmem + cur * ts::REGION, a = tmem + (cur ^ 1u) * ts::REGION;
       for (int cb = 0; cb < 4; ++cb) {
         if (timed) mbar_wait_t(&pipe.blk[cb], bp, t_epi); else mbar_wait(&pipe.blk[cb], bp);
@@ -964,7 +965,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = 2 * cb + (j & 1) + (j >> 1) * 8;
-          chunk(d, Nn, true, a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1), (accumulate || cb > 0 || j > 0) ? 1u : 0u);
+          chunk(d, Nn, true, a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1), (accumulate || cb > 0 || j > 0) ? 1u : 0u, a_exact);
         }
       }
       bp ^= 1u;
@@ -979,7 +980,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       gemm_ss(12); gemm_ts(H, true); ready();                              // G2b (A = PE6 slices) + G2a (A = h1)
       gemm_ts(H, false); ready();                                          // G3 (A = c)
       if (sweep) {
-        gemm_ts(H, false); ready();                                        // G4 (A = um)
+        gemm_ts(H, false, true); ready();                                  // G4 (A = the m3 mask, B = diag(u) Wa: two MMAs per chunk)
         gemm_ts(H, false); ready();                                        // G5 (A = y)
         if (sweep > 1) { gemm_ts(C, false); ready(); }                     // G6 (A = qm, N = 192)
       }
@@ -1044,12 +1045,12 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       epi_bar<PL>();
       if (tid < H) load_vectors(svec, w, b, k, tid);
       epi_bar<PL>();
-      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sUM = 1.f, sY = 1.f;
+      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sY = 1.f;
       if (F16) {
         const NetScales t = w.sc[b * w.Kn + k];
-        i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / (t.sUM * t.sWa);
+        i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / t.sWaU;
         i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
-        sH1 = t.sH1; sC = t.sC; sUM = t.sUM; sY = t.sY;
+        sH1 = t.sH1; sC = t.sC; sY = t.sY;
       }
       uint32_t m1w[NB];
 #pragma unroll
@@ -1101,7 +1102,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         emit(cg, v, nullptr, true, ra + cg * 32);
         blk_done(cb);
       }
-      // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
+      // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  the mask m3 = [a3 > 0] is the A operand of G4 ----
       uint32_t m3w[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) m3w[i] = 0u;
@@ -1124,12 +1125,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
             const float gg = fmaxf(a, 0.f);
             if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
             bits |= (a > 0.f ? 1u : 0u) << j;
-            v[j] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;          // um replaces the accumulator value in place
           }
         }
 #pragma unroll
         for (int i = 0; i < NB; ++i) m3w[i] = (cb == i) ? bits : m3w[i];
-        if (sweep) { emit(cg, v, nullptr, true, ra + cg * 32); blk_done(cb); }   // (wgrad2_kernel rebuilds um from the mask: not stored)
+        if (sweep) {                                                  // the mask as ONE exact 16-bit plane (1.0 / 0) over the accumulator block
+          constexpr uint32_t ONE = F16 ? 0x3C00u : 0x3F80u;
+          uint32_t mk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mk[i] = (((bits >> (2 * i)) & 1u) ? ONE : 0u) | (((bits >> (2 * i + 1)) & 1u) ? (ONE << 16) : 0u);
+          tmem_st16(ra + cg * 32, mk);
+          blk_done(cb);
+        }
       }
       if (!sweep) net_done();
       if (sweep) {                                                     // the two ReLU masks of this (net, tile): all pass 2 needs of h1 / c / g
@@ -1497,21 +1504,24 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 //        zc = zh W2^T + zd Wd^T + dov bsum       zd = dov PE6       (the operand of dWd)
 //        gz = m3 ( zc Wa^T + dov ba )
 // i.e. pass 2 is pass 1's value chain applied to the row zp with the FROZEN masks and dov-scaled biases.  It needs from pass 1
-// two bit masks per point (64 bytes) instead of the h1 / c / g tiles (3 KB), no separate tangent row, and every tile it produces
+// one bit mask per point (32 bytes) instead of the h1 / c / g tiles (3 KB), no separate tangent row, and every tile it produces
 // is at once the next A operand and the stored wgrad operand (one split instead of two).
+// gz itself is never formed: it enters the gradients only through its column sum vg = sum_p gz (dWb, dwo), and
+//        vg[j] = sum_i Wa[j,i] S[j,i] + ba[j] sum_p m3[p,j] dov[p],     S = m3^T zc
+// where S is the contraction the weight-gradient kernel runs anyway for dWa = diag(u) S (wgrad2_kernel, layer 2) - so the third
+// GEMM of the chain (zc Wa^T, K = 256) and its epilogue are not executed at all.
 // Structure = pass1_ts_kernel: two 256-column TMEM regions as ping-pong accumulators, converted in place into the next A operand,
 // the next GEMM starting block by block under the running epilogue.  Per net: the prologue writes zp into R1 (hi planes columns
 // [0,96), lo [96,192)) while G7' (-> R0) consumes it; epilogue 7 converts R0 into zh while G8' (-> R1, first the K = 192 part whose
-// A operand zd is staged in shared memory, 96 KB, layout (*)) consumes it; epilogue 8 converts R1 into zc under G9' (-> R0);
-// epilogue 9 reads R0 and the next net's prologue follows in the same threads (so G7' of the next net cannot start before the
-// accumulator is drained).  7 x 16 KB weight ring.
+// A operand zd is staged in shared memory, 96 KB, layout (*)) consumes it; epilogue 8 reads R1 (zc -> workspace, column sums) and
+// the next net's prologue follows in the same threads.  7 x 16 KB weight ring.
 // ------------------------------------------------------------------------------------------------
 namespace p2z {
 constexpr int NS = 7;
 constexpr int W_BYTES = 2 * STAGE_BYTES;         // one K = 16 chunk of a [256 x K] image: hi 8 KB | lo 8 KB
 constexpr int ZD_BYTES = 2 * BLOB_C;             // zd staging: plane hi | plane lo, [128 x 192] each, layout (*)
-enum { V2_B1 = 0, V2_BSUM, V2_BA, NV2 };
-constexpr int SMEM = NS * W_BYTES + ZD_BYTES + NV2 * H * 4 + 2 * H * 4 + 16;      // + column sums [zc | gz] + sum of dov
+enum { V2_B1 = 0, V2_BSUM, NV2 };
+constexpr int SMEM = NS * W_BYTES + ZD_BYTES + NV2 * H * 4 + H * 4 + 16;          // + column sums of zc + sum of dov
 constexpr uint32_t REGION = 256, ZP_LO = 96;   // TMEM: regions R0 | R1; zp planes inside R1: hi [0,96) | lo [96,192)
 struct PipeZ {
   uint64_t full[NS], empty[NS];
@@ -1533,7 +1543,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   uint8_t* ring = smem;
   uint8_t* zdt = smem + p2z::NS * p2z::W_BYTES;
   float* svec = reinterpret_cast<float*>(zdt + p2z::ZD_BYTES);
-  float* csum = svec + p2z::NV2 * H;                               // [2][H] + sdo
+  float* csum = svec + p2z::NV2 * H;                               // [H] + sdo
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
@@ -1574,14 +1584,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     for (int k = 0; k < w.Kn; ++k) {
       const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
       const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
-      const uint8_t *iW1 = gen, *iW2 = gen + PL * 2 * IMG_HC, *iWd = sta, *iWa = sta + PL * IMG_HC;
-      // the MMA warp's order: G7' in prologue-block order | zd Wd^T (no dependence on an epilogue) | G8', G9' in block order
+      const uint8_t *iW1 = gen, *iW2 = gen + PL * 2 * IMG_HC, *iWd = sta;
+      // the MMA warp's order: G7' in prologue-block order | zd Wd^T (no dependence on an epilogue) | G8' in block order
       for (int i = 0; i < 4; ++i)
         for (int h = 0; h < 2; ++h)
           for (int j = 0; j < p2z::zp_count(i); ++j) put(iW1 + (size_t)(6 * h + p2z::zp_first(i) + j) * p2z::W_BYTES);
       for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * p2z::W_BYTES);
       for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * p2z::W_BYTES);
-      for (int i = 0; i < 16; ++i) put(iWa + (size_t)ts::block_order(i) * p2z::W_BYTES);
     }
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
@@ -1643,7 +1652,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       ready(0);
       for (int c = 0; c < 12; ++c) chunk(R1, false, 0u, 0u, c, c > 0 ? 1u : 0u);   // G8' = zd Wd^T (zd: shared memory, complete with the prologue)
       gemm_ts(R1, R0, true); ready(1);                                     //       + zh W2^T, under epilogue 7
-      gemm_ts(R0, R1, false); ready(0);                                    // G9' = zc Wa^T, under epilogue 8
     }
     if (timed && lane == 0) {
       atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
@@ -1690,15 +1698,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       tmem_st16(blk_addr, hi);                                         // in place: the planes replace the accumulator block they came from
       tmem_st16(blk_addr + 16, lo);
     };
-    for (int i = tid; i < 2 * H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
+    for (int i = tid; i < H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile<PL>(w, b, k, tl);
       epi_bar<PL>();                                                   // previous net's vectors / column sums are flushed
       if (tid < H) {
-        const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+        const size_t vb = ((size_t)b * w.Kn + k) * H;
         svec[p2z::V2_B1 * H + tid] = __ldg(w.b1 + vb + tid);
         svec[p2z::V2_BSUM * H + tid] = __ldg(w.bsum + vb + tid);
-        svec[p2z::V2_BA * H + tid] = __ldg(w.ba + vk + tid);
       }
       epi_bar<PL>();
       const float dv = w.dov[row * w.Kn + k];
@@ -1706,18 +1713,17 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
       for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];          // zero for the values-only backward
       const uint4 m1q = __ldg(reinterpret_cast<const uint4*>(blob_mask<PL>(nt)) + r * 2 + half);
-      const uint4 m3q = __ldg(reinterpret_cast<const uint4*>(blob_mask<PL>(nt)) + (TP + r) * 2 + half);
-      const uint32_t m1w[4] = {m1q.x, m1q.y, m1q.z, m1q.w}, m3w[4] = {m3q.x, m3q.y, m3q.z, m3q.w};
+      const uint32_t m1w[4] = {m1q.x, m1q.y, m1q.z, m1q.w};
       // fp16 variant: every tile carries one power-of-two scale per (sample, net) (zscale_kernel); accumulators carry
       // (A tile scale) x (weight image scale) and i7 / i8 / i9 undo that
       // zd exists twice: the stored tile (wgrad operand of dWd) with its own scale sZD, and the A operand of G8' whose scale is tied
       // to the accumulator it shares with zh W2^T: sZH sW2 = sZDa sWd, and plan_kernel made sH1 sW2 = S_PE sWd  =>  sZDa = sZH S_PE / sH1
-      float sZP = 1.f, sZH = 1.f, sZC = 1.f, sZD = 1.f, sZDa = 1.f, sDV = 1.f, i7 = 1.f, i8 = 1.f, i9 = 1.f;
+      float sZP = 1.f, sZH = 1.f, sZC = 1.f, sZD = 1.f, sZDa = 1.f, sDV = 1.f, i7 = 1.f, i8 = 1.f;
       if (F16) {
         const NetScales t = w.sc[b * w.Kn + k];
         sZP = t.sZP; sZH = t.sZH; sZC = t.sZC; sZD = t.sZD; sDV = t.sDV;
         sZDa = t.sZH * (S_PE / t.sH1);
-        i7 = (1.f / t.sZP) * (1.f / t.sW1); i8 = (1.f / t.sZH) * (1.f / t.sW2); i9 = (1.f / t.sZC) * (1.f / t.sWa);
+        i7 = (1.f / t.sZP) * (1.f / t.sW1); i8 = (1.f / t.sZH) * (1.f / t.sW2);
       }
       // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three 16-bit terms, rest 0
       if (half == 0) {
@@ -1819,7 +1825,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         emit(cg, v, blob_h<PL>(nt, B_ZH), R0 + cg * 32);
         blk_done(cb);
       }
-      // ---- epilogue 8: zc = acc + dov (b2 + bd + e);  column sum -> vc ----
+      // ---- epilogue 8: zc = acc + dov (b2 + bd + e) -> workspace (Z operand of dWa);  column sum -> vc ----
       acc_wait(1);
 #pragma unroll 1
       for (int cb = 0; cb < NB; ++cb) {
@@ -1837,49 +1843,31 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
             v[j] = F16 ? z[j] * sZC : z[j];
           }
         }
-        emit(cg, v, blob_h<PL>(nt, B_ZC), R1 + cg * 32);
-        blk_done(cb);                                                  // G9' goes on; the column sum runs under it
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          uint4 pq[PL];
+          split8<PL, F16>(v + qd * 8, pq);
+          const uint32_t off = gp_off(32, r, cg * 4 + qd);
+          __stcs(reinterpret_cast<uint4*>(blob_h<PL>(nt, B_ZC) + off), pq[0]);
+          __stcs(reinterpret_cast<uint4*>(blob_h<PL>(nt, B_ZC) + BLOB_H + off), pq[1]);
+        }
         const float cs = warp_colsum32(z, lane);
         atomicAdd(csum + cg * 32 + lane, cs);
       }
-      // ---- epilogue 9: gz = m3 (acc + dov ba);  column sum -> vg ----
-      acc_wait(0);
-#pragma unroll 1
-      for (int cb = 0; cb < NB; ++cb) {
-        const int cg = c0 + cb;
-        float v[32];
-        tmem_ld32(R0 + cg * 32, v);
-        uint32_t bits = 0u;
-#pragma unroll
-        for (int i = 0; i < NB; ++i) bits = (cb == i) ? m3w[i] : bits;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = *reinterpret_cast<const float4*>(svec + p2z::V2_BA * H + cg * 32 + j4 * 4);
-          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int j = j4 * 4 + e;
-            const float z = F16 ? fmaf(v[j], i9, dv * bb[e]) : fmaf(dv, bb[e], v[j]);
-            v[j] = ((bits >> j) & 1u) ? z : 0.f;
-          }
-        }
-        const float cs = warp_colsum32(v, lane);
-        atomicAdd(csum + H + cg * 32 + lane, cs);
-      }
+      tc_fence_before();                                                // my reads of R1 precede the prologue's tcgen05.st of the next net
       // ---- flush this net's column sums ----
       if (half == 0) {
         float sd = dv;
 #pragma unroll
         for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
-        if (lane == 0) atomicAdd(csum + 2 * H, sd);
+        if (lane == 0) atomicAdd(csum + H, sd);
       }
       epi_bar<PL>();
-      for (int i = tid; i < 2 * H; i += Geo<PL>::ET) {
-        float* dstv = i < H ? w.vc : w.vg;
-        atomicAdd(dstv + (size_t)k * H + (i % H), csum[i]);
+      for (int i = tid; i < H; i += Geo<PL>::ET) {
+        atomicAdd(w.vc + (size_t)k * H + i, csum[i]);
         csum[i] = 0.f;
       }
-      if (tid == 0) { atomicAdd(w.sdo + k, csum[2 * H]); csum[2 * H] = 0.f; }
+      if (tid == 0) { atomicAdd(w.sdo + k, csum[H]); csum[H] = 0.f; }
     }
     if (timed && tid == 0) {
       const long long tot = clock64() - t_begin;
@@ -1907,7 +1895,9 @@ struct WgradWork {
   int B, Kn, T, splits;
   const uint8_t* blobs;
   const NetScales* sc;
-  const float* uvec;       // [Kn][H] u = Wb^T wo (split modes: the J operand of dWa is rebuilt from u and the m3 mask)
+  const float* uvec;       // [Kn][H] u = Wb^T wo
+  const float *Wa, *ba;    // [Kn][H][H], [Kn][H] fp32 (split modes: vg = sum_p gz from the dWa contraction, see wgrad2_kernel)
+  float* vg;               // [Kn][H]
   float *gW1, *gW2, *gWa, *gWd;
   float *gb1, *gb2, *ge, *gbd, *gba;
 };
@@ -2050,8 +2040,10 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
 //   * tiles are stored [point half][k-core][64 rows][16 B] (gp_off), so a 64-point half of every operand is contiguous and a stage is
 //     98 KB: J half-columns 2 x 16 KB | Z 2 x 32 KB (24 KB for the 192-wide layers) | seed tile 2 KB.  TWO stages: the bulk loads of
 //     half-tile i+1 run under the 12 (+ seed) MMAs of half-tile i;
-//   * the dba column sum moves here: dba[out] = sum_p (u m3)[p,out] dov[p] is the seed-tile MMA of layer 2, exactly like db1 / db2
-//     (TMEM: 256 accumulator columns + 16 for the seed product);
+//   * layer 2 contracts the BARE mask: S = m3^T zc with J = [a3 > 0] as one exact 16-bit plane built from the mask bits of pass 1
+//     (two MMAs per step instead of three, no stored J tile).  Its epilogue derives three results from S and the seed product
+//     sm3 = sum_p m3 dov:  dWa = diag(u) S,  dba = u sm3,  and the column sum of the never-formed tile gz = m3 (zc Wa^T + dov ba):
+//     vg[j] = sum_i Wa[j,i] S[j,i] + ba[j] sm3[j]  - which is why pass 2 has no third GEMM;
 //   * epilogue: every thread owns one output row; it parks the scaled row in shared memory (the stages are free by then) and hands
 //     it to the TMA engine as ONE bulk fp32 reduction (cp.reduce.async.bulk ... add.f32, 768 / 1024 contiguous bytes) instead of
 //     192 / 256 scalar red.global.add whose 32 lanes hit 32 different rows.
@@ -2073,7 +2065,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t full[2], empty[2], acc_ready;
   __shared__ uint32_t tmem_s;
-  __shared__ uint32_t su_hi[64], su_lo[64];                          // layer 2: u sUM of this out-half as packed 16-bit pairs, hi / lo plane
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   // the two CTAs of a cluster are the two output halves (mh) of one (sample, net, layer, split): they contract against the SAME Z
@@ -2088,7 +2079,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
   const int KCz = Nn / 8;                                             // k-cores of the Z tile
   const bool aux = layer != 1;                                        // layer 1 shares its J operand (y) with layer 3, which delivers db2
   const uint32_t zplane = (uint32_t)wg2::PT * Nn * 2;                 // bytes of one plane of a Z half-tile
-  const int jsel = layer == 0 ? B_QM : B_YT;                          // layer 2: J = u [a3 > 0] is built in shared memory from the m3 mask
+  const int jsel = layer == 0 ? B_QM : B_YT;                          // layer 2: J = [a3 > 0] is built in shared memory from the m3 mask bits
   const bool build_j = layer == 2;
   const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
   const int nst = 2 * (t1 - t0);                                      // half-tiles
@@ -2097,14 +2088,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(&tmem_s, 512);
-  if (build_j && tid < 64) {                                         // the same split pass 1 applied to um before it stopped storing it
-    const float s_um = F16 ? w.sc[(size_t)b * w.Kn + k].sUM : 1.f;
-    float u2[8] = {__ldg(w.uvec + (size_t)k * H + mh * TP + 2 * tid) * s_um, __ldg(w.uvec + (size_t)k * H + mh * TP + 2 * tid + 1) * s_um,
-                   0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    uint4 pq[PL];
-    split8<PL, F16>(u2, pq);
-    su_hi[tid] = pq[0].x; su_lo[tid] = pq[1].x;
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -2153,7 +2136,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
           for (int ks = 0; ks < wg2::PT / 16; ++ks) {
             const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
             const uint64_t ad = a_hi + ks * 16, bd = b_hi + ks * 16, xd = x_d + ks * 16;
-            if (aux) {                                       // every J plane is fetched once per step for all MMAs that read it
+            if (build_j) {                                   // exact one-plane J (the mask): J Z_lo + J Z_hi + J seeds
+              mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, first);
+              mma_f16_c<A_USE>(tmem, ad, bd, idesc, 1u);
+              mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, first);
+            } else if (aux) {                                // every J plane is fetched once per step for all MMAs that read it
               mma_f16_c<A_FILL>(tmem, ad + a_lo, bd, idesc, first);
               mma_f16_c<A_LAST>(tmem + COL_X, ad + a_lo, xd, idesc_x, first);
               mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
@@ -2182,16 +2169,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const uint32_t bits = ((j < 4 ? mw.x : mw.y) >> ((j & 3) * 8)) & 0xFFu;
-            uint32_t hi[4], lo[4];
+            constexpr uint32_t ONE = F16 ? 0x3C00u : 0x3F80u;                 // 1.0 in the operand format
+            uint32_t hi[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t m = (((bits >> (2 * e)) & 1u) ? 0x0000FFFFu : 0u) | (((bits >> (2 * e + 1)) & 1u) ? 0xFFFF0000u : 0u);
-              hi[e] = su_hi[gq * 32 + j * 4 + e] & m;
-              lo[e] = su_lo[gq * 32 + j * 4 + e] & m;
-            }
+            for (int e = 0; e < 4; ++e) hi[e] = (((bits >> (2 * e)) & 1u) ? ONE : 0u) | (((bits >> (2 * e + 1)) & 1u) ? (ONE << 16) : 0u);
             const uint32_t off = (uint32_t)(gq * 8 + j) * (wg2::PT * 16) + (uint32_t)pt * 16;
             *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(st + wg2::J_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
           fence_proxy_async();                                         // generic-proxy stores -> visible to the tensor core's reads
           mbar_arrive(&full[s]);
@@ -2208,19 +2191,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
       float un = 1.f, un_x = 1.f;                                      // fp16 variant: undo (J tile scale) x (Z tile / seed scale)
       if (F16) {
         const NetScales t = w.sc[gk];
-        const float sj = layer == 0 ? t.sQ : (layer == 2 ? t.sUM : t.sY);
+        const float sj = layer == 0 ? t.sQ : (layer == 2 ? 1.f : t.sY);      // (the mask of layer 2 carries no scale)
         const float sz = layer == 0 ? t.sZP : (layer == 1 ? t.sZH : (layer == 2 ? t.sZC : t.sZD));
         un = (1.f / sj) * (1.f / sz); un_x = (1.f / sj) * (1.f / t.sDV);      // separately: sj * sz may leave the fp32 range
       }
+      const int out = mh * TP + tid;
+      // layer 2: this row of S = m3^T zc gives dWa[out,:] = u[out] S and the dot product with Wa[out,:] that vg needs
+      const float urow = build_j ? __ldg(w.uvec + (size_t)k * H + out) : 1.f;
+      const float* warow = w.Wa + ((size_t)k * H + out) * H;
+      float dot0 = 0.f, dot1 = 0.f;
       uint8_t* myrow = smem + (size_t)tid * (H * 4 + wg2::ROW_PAD);
       float v[32];
       for (int cb = 0; cb < Nn / 32; ++cb) {
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
+        if (build_j) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(warow + cb * 32) + j4);
+            dot0 = fmaf(v[j4 * 4], wv.x, dot0); dot1 = fmaf(v[j4 * 4 + 1], wv.y, dot1);
+            dot0 = fmaf(v[j4 * 4 + 2], wv.z, dot0); dot1 = fmaf(v[j4 * 4 + 3], wv.w, dot1);
+          }
+        }
+        const float sc = un * urow;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
           *reinterpret_cast<float4*>(myrow + cb * 128 + j4 * 16) =
-              make_float4(F16 ? v[j4 * 4] * un : v[j4 * 4], F16 ? v[j4 * 4 + 1] * un : v[j4 * 4 + 1],
-                          F16 ? v[j4 * 4 + 2] * un : v[j4 * 4 + 2], F16 ? v[j4 * 4 + 3] * un : v[j4 * 4 + 3]);
+              (F16 || build_j) ? make_float4(v[j4 * 4] * sc, v[j4 * 4 + 1] * sc, v[j4 * 4 + 2] * sc, v[j4 * 4 + 3] * sc)
+                               : make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
       }
       fence_proxy_async();                                             // my generic-proxy row -> visible to the bulk engine
       bulk_red_add_f32(dst, myrow, (uint32_t)Nn * 4u);
@@ -2229,11 +2226,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
         float x[16];
         tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_X, x);
         const float bsum = (x[0] + x[1] + x[2]) * un_x;                // the three 16-bit terms of the seed
-        const int out = mh * TP + tid;
         if (layer == 0) {
           atomicAdd(w.gb1 + gk * H + out, bsum);
-        } else if (layer == 2) {
-          atomicAdd(w.gba + (size_t)k * H + out, bsum);
+        } else if (layer == 2) {                                       // bsum = sum_p m3[p,out] dov[p]
+          atomicAdd(w.gba + (size_t)k * H + out, urow * bsum);
+          atomicAdd(w.vg + (size_t)k * H + out, fmaf(__ldg(w.ba + (size_t)k * H + out), bsum, (dot0 + dot1) * un));
         } else {
           atomicAdd(w.gb2 + gk * H + out, bsum);
           atomicAdd(w.ge + gk * H + out, bsum);
@@ -2334,6 +2331,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
   const float mP = block_max256(mp, red);
   const float mBs = block_max256(fabsf(bsum[(size_t)bk * H + j]), red), mBa = block_max256(fabsf(ba[(size_t)k * H + j]), red);
   const float Mu = block_max256(fabsf(uvec[(size_t)k * H + j]), red), mWo2 = block_max256(fabsf(wo2[(size_t)k * H + j]), red);
+  const float mWaU = block_max256(fabsf(uvec[(size_t)k * H + j]) * ma, red);       // max |u_j Wa_ji|
   if (j == 0) {
     NetScales t;
     const float Mc = l1W2 * M1 + l1Wd + mBs, Mg = l1Wa * Mc + mBa;
@@ -2341,6 +2339,7 @@ __global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __rest
     t.sW1 = scale_for(mW1 * 32.f);                   // weights: maximum -> 2^10
     t.sWa = scale_for(mWa * 32.f);
     t.sP = scale_for(mP * 32.f);
+    t.sWaU = scale_for(mWaU * 32.f);
     t.sWd = scale_for(mWd * 32.f);                   // preliminary: plan_kernel couples sWd, sH1 and sW2
     t.sW2 = scale_for(mW2);                          // preliminary: the LARGEST admissible factor
     t.sH1 = scale_for(M1); t.sC = scale_for(Mc); t.sG = scale_for(Mg);
@@ -2409,7 +2408,8 @@ __global__ void zscale_kernel(int n, const int* __restrict__ seedmax, NetScales*
 // [hi plane | lo plane], so the producer still fetches one contiguous block per chunk.
 template <int PL, bool F16>
 __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, uint8_t* __restrict__ dst,
-                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which) {
+                             size_t dst_stride, int rows, int kd, int transpose, const NetScales* __restrict__ tab, int which,
+                             const float* __restrict__ kscale) {        // kscale [batch][kd]: image of S diag(kscale) (or nullptr)
   const float* S = src + blockIdx.y * src_stride;
   uint8_t* D = dst + blockIdx.y * dst_stride;
   const int q = blockIdx.x * blockDim.x + threadIdx.x;             // 16-byte piece index
@@ -2418,9 +2418,13 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = transpose ? S[(size_t)(kc * 8 + e) * rows + r] : S[(size_t)r * kd + kc * 8 + e];
+  if (kscale) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= kscale[(size_t)blockIdx.y * kd + kc * 8 + e];
+  }
   if (F16) {                                                         // entry blockIdx.y: (sample, net) for generated weights, (0, net) for static ones
     const NetScales& t = tab[blockIdx.y];
-    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : (which == 3 ? t.sWa : t.sP)));
+    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : (which == 3 ? t.sWa : (which == 5 ? t.sWaU : t.sP))));
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] *= sc;
   }
@@ -2584,21 +2588,23 @@ size_t workspace_bytes(int chunk, int Kn, int B, int planes) { return carve(null
 
 template <int PL, bool F16>
 static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
-  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; };
+  struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; const float* kscale; };
+  // split modes: the transposed Wa image carries u (G4: y = m3 (diag(u) Wa) + 2wo with the bare mask as A operand)
+  const float* ku = PL == 2 ? c.uvec : nullptr;
   const Spec specs[] = {
-      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0},                       // W1  : rows = out, k = in
-      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0},                  // W1T : rows = in,  k = out
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1},
-      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen, 1},
-      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta, 2},
-      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta, 3},
-      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta, 3},
+      {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0, nullptr},              // W1  : rows = out, k = in
+      {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0, nullptr},         // W1T : rows = in,  k = out
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC, GEN_IMG, H, H, 0, B * Kn, c.img_gen, 1, nullptr},
+      {Wt.W2, (size_t)H * H, 2 * IMG_HC + IMG_HH, GEN_IMG, H, H, 1, B * Kn, c.img_gen, 1, nullptr},
+      {Wt.Wd, (size_t)H * C, 0, STA_IMG, H, C, 0, Kn, c.img_sta, 2, nullptr},
+      {Wt.Wa, (size_t)H * H, IMG_HC, STA_IMG, H, H, 0, Kn, c.img_sta, 3, nullptr},
+      {Wt.Wa, (size_t)H * H, IMG_HC + IMG_HH, STA_IMG, H, H, 1, Kn, c.img_sta, ku ? 5 : 3, ku},
   };
   for (const Spec& s : specs) {
     if (s.batches == 0) continue;
     const int pieces = s.rows * s.kd / 8;
     image_kernel<PL, F16><<<dim3((pieces + 255) / 256, s.batches), 256, 0, st>>>(s.src, s.sstride, s.dst + s.doff * PL, s.dstride * PL,
-                                                                                 s.rows, s.kd, s.tr, c.sc, s.which);
+                                                                                 s.rows, s.kd, s.tr, c.sc, s.which, s.kscale);
     DPN_LAUNCH_OK();
   }
   return 0;
@@ -2737,6 +2743,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc; ww.uvec = c.uvec;
+    ww.Wa = Wt.Wa; ww.ba = Wt.ba; ww.vg = c.vg;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd; ww.gba = G.ba;
     const int items = B * Kn * 8;

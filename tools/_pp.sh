@@ -1,9 +1,11 @@
 #!/bin/bash
-# ping-pong pipelined pass 1 / pass 2 against the previous commit's library
+# quick parity (split modes) + step time + in-situ kernel times of the in-tree library [and of a previous build]
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_f16x3.py tests/test_gpu_bf16x3.py tests/test_gpu_decoder.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/r02j_pytest_quick.txt
-for lib in "" "$PWD/tools/bin/libdpn_prev.so"; do
+T=${1:-quick}
+timeout 400 python -m pytest tests/test_gpu_f16x3.py tests/test_gpu_bf16x3.py tests/test_gpu_decoder.py tests/test_gpu_parity.py tests/test_gpu_margin_fused.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${T}_pytest_quick.txt
+for lib in "" ${PREV:+$PWD/tools/bin/libdpn_prev.so}; do
   echo "== library: ${lib:-in-tree}"
   DPN_LIB_OVERRIDE=$lib timeout 120 python tools/step_jitter.py f16x3 16 2>&1 | grep -E "per-step" | cut -c1-200
-done 2>&1 | tee gpurun_out/r02j_ab.txt
+done 2>&1 | tee gpurun_out/${T}_ab.txt
+timeout 200 python tools/insitu_kernels.py 2>&1 | grep -v Warn | tail -8 | tee gpurun_out/${T}_insitu.txt
