@@ -191,15 +191,28 @@ __device__ __forceinline__ void unpack8f(const uint4& q, float* v) {
     unpack8(q, v);
   }
 }
-// 8 fp32 values -> one 16-byte piece per plane: hi = rn16(v), lo = rn16(v - hi)  (v - hi is exact in fp32)
+// v - h for a 16-bit h (fp16 / bf16) without unpacking it: one mixed-precision FMA, h * (-1) + v (SASS: FHFMA with a half selector).
+// Exact: h is v rounded to 11 / 8 significant bits, so the difference fits fp32.
+template <bool F16>
+__device__ __forceinline__ float resid16(const uint32_t h, const float v) {
+  float d;
+  if (F16) asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"((uint16_t)h), "h"((uint16_t)0xBC00), "f"(v));
+  else asm("fma.rn.f32.bf16 %0, %1, %2, %3;" : "=f"(d) : "h"((uint16_t)h), "h"((uint16_t)0xBF80), "f"(v));
+  return d;
+}
+// 8 fp32 values -> one 16-byte piece per plane: hi = rn16(v), lo = rn16(v - hi)  (v - hi is exact in fp32).
+// Per pair of values: pack, two mixed-precision FMAs, pack - the epilogues of the split modes spend a third of their instructions here.
 template <int PL, bool F16 = false>
 __device__ __forceinline__ void split8(const float* v, uint4 (&q)[PL]) {
   q[0] = pack8f<F16>(v);
   if (PL == 2) {
-    float h[8], l[8];
-    unpack8f<F16>(q[0], h);
+    const uint32_t hw[4] = {q[0].x, q[0].y, q[0].z, q[0].w};
+    float l[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) l[e] = v[e] - h[e];
+    for (int i = 0; i < 4; ++i) {
+      l[2 * i] = resid16<F16>(hw[i] & 0xFFFFu, v[2 * i]);
+      l[2 * i + 1] = resid16<F16>(hw[i] >> 16, v[2 * i + 1]);
+    }
     q[PL - 1] = pack8f<F16>(l);
   }
 }
@@ -938,7 +951,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       tc_fence_after();
       const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
       if (elect_one()) {
-        if (a_in_tmem) {
+        if (DPN_DBG(w, 1)) {                             // (debug builds: no MMAs, barrier protocol intact)
+        } else if (a_in_tmem) {
           if (!a_exact) mma_ts(d, a_hi + 16, bd, idesc, first);            // (an exact 16-bit A operand - the 0 / 1 mask of G4 - has no lo plane)
           mma_ts(d, a_hi, bl, idesc, a_exact ? first : 1u);
           mma_ts(d, a_hi, bd, idesc, 1u);
@@ -1010,7 +1024,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       for (int qd = 0; qd < 4; ++qd) {
         uint4 pq[PL];
         split8<PL, F16>(v + qd * 8, pq);
-        if (blob) {
+        if (blob && !DPN_DBG(w, 4)) {
           const uint32_t off = gp_off(32, r, cg * 4 + qd);
           __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
           __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
@@ -1042,16 +1056,28 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
     for (int k = 0; k < w.Kn; ++k) {
       uint8_t* nt = net_tile<PL>(w, b, k, tl);
-      epi_bar<PL>();
-      if (tid < H) load_vectors(svec, w, b, k, tid);
-      epi_bar<PL>();
-      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sY = 1.f;
+      // fp16 variant: an accumulator carries (A tile scale) x (weight image scale); k1 .. k6 undo that AND apply the scale of the tile
+      // the epilogue produces, and the bias vectors are staged pre-multiplied by the same power of two (exact), so that
+      // value -> next operand is ONE FMA per element:  h1 sH1 = max(acc k1 + b1 sH1, 0),  c sC = acc k2 + bsum sC,  y sY = acc k4 + 2wo sY
+      float k1 = 1.f, k2 = 1.f, i3 = 1.f, k4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sY = 1.f;
       if (F16) {
         const NetScales t = w.sc[b * w.Kn + k];
-        i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / t.sWaU;
-        i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
         sH1 = t.sH1; sC = t.sC; sY = t.sY;
+        k1 = sH1 / (S_PE * t.sW1); k2 = sC / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); k4 = sY / t.sWaU;
+        i5 = t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
       }
+      epi_bar<PL>();
+      if (tid < H) {                                                   // V_B1: b1 sH1 | V_BSUM: bsum sC | V_BA, V_U | V_WO2: 2wo / sC (epilogue 2) | V_C2: 2wo sY (epilogue 4)
+        const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
+        const float wo2 = __ldg(w.wo2 + vk + tid);
+        svec[V_B1 * H + tid] = __ldg(w.b1 + vb + tid) * sH1;
+        svec[V_BSUM * H + tid] = __ldg(w.bsum + vb + tid) * sC;
+        svec[V_BA * H + tid] = __ldg(w.ba + vk + tid);
+        svec[V_U * H + tid] = __ldg(w.uvec + vk + tid);
+        svec[V_WO2 * H + tid] = wo2 * (1.f / sC);
+        svec[V_C2 * H + tid] = wo2 * sY;
+      }
+      epi_bar<PL>();
       uint32_t m1w[NB];
 #pragma unroll
       for (int i = 0; i < NB; ++i) m1w[i] = 0u;
@@ -1069,9 +1095,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = F16 ? fmaf(v[j4 * 4 + e], i1, bb[e]) : v[j4 * 4 + e] + bb[e];
+            const float a = F16 ? fmaf(v[j4 * 4 + e], k1, bb[e]) : v[j4 * 4 + e] + bb[e];      // a1 sH1
             bits |= (a > 0.f ? 1u : 0u) << (j4 * 4 + e);
-            v[j4 * 4 + e] = F16 ? fmaxf(a, 0.f) * sH1 : fmaxf(a, 0.f);
+            v[j4 * 4 + e] = fmaxf(a, 0.f);
           }
         }
 #pragma unroll
@@ -1094,9 +1120,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float cc = F16 ? fmaf(v[j4 * 4 + e], i2, bb[e]) : v[j4 * 4 + e] + bb[e];
+            const float cc = F16 ? fmaf(v[j4 * 4 + e], k2, bb[e]) : v[j4 * 4 + e] + bb[e];     // c sC; ww = 2wo / sC
             if (e & 1) os1 = fmaf(ww[e], cc, os1); else os0 = fmaf(ww[e], cc, os0);
-            v[j4 * 4 + e] = F16 ? cc * sC : cc;
+            v[j4 * 4 + e] = cc;
           }
         }
         emit(cg, v, nullptr, true, ra + cg * 32);
@@ -1161,10 +1187,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         tmem_ld32(ra + cg * 32, v);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
+          const float4 wv = *reinterpret_cast<const float4*>(svec + V_C2 * H + cg * 32 + j4 * 4);      // 2wo sY
           const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = F16 ? fmaf(v[j4 * 4 + e], i4, ww[e]) * sY : v[j4 * 4 + e] + ww[e];
+          for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = F16 ? fmaf(v[j4 * 4 + e], k4, ww[e]) : v[j4 * 4 + e] + ww[e];
         }
         emit(cg, v, blob_h<PL>(nt, B_YT), true, ra + cg * 32);
         blk_done(cb);
@@ -1725,6 +1751,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         sZDa = t.sZH * (S_PE / t.sH1);
         i7 = (1.f / t.sZP) * (1.f / t.sW1); i8 = (1.f / t.sZH) * (1.f / t.sW2);
       }
+      // the scale of the tile an epilogue produces is folded into its FMA (powers of two: exact): zh sZH = m1 (acc k7 + (dov sZH) b1), ...
+      const float k7 = i7 * sZH, k8 = i8 * sZC, dvH = dv * sZH, dvC = dv * sZC, dvP = dv * sZP, inv_sZC = 1.f / sZC;
+      const float ddP[3] = {dd[0] * sZP, dd[1] * sZP, dd[2] * sZP};
       // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three 16-bit terms, rest 0
       if (half == 0) {
         float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1767,13 +1796,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
           for (int p = 0; p < PL; ++p) p6[qd][p] = p6_n[qd][p];
         if (it + 1 < half * NB + NB) fetch(it + 1);
+        float kb[4][3];                                               // (dod_c sZP) band_f: one product per (frequency, component) of this group
 #pragma unroll
-        for (int j = 0; j < 24; ++j) {
-          const int J = it * 24 + j;                                  // it*24 is a multiple of 6: the partner stays inside the block
-          const float xt = dd[j % 3] * (DPE_SIGN(j) * w.band[J / 6]) * pe[DPE_PARTNER(j)];
-          zp[j] = fmaf(dv, pe[j], xt);
-          if (F16) zp[j] *= sZP;
-        }
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) kb[f][c] = ddP[c] * w.band[it * 4 + f];
+#pragma unroll
+        for (int j = 0; j < 24; ++j)                                  // it*24 is a multiple of 6: the partner stays inside the block
+          zp[j] = fmaf(dvP, pe[j], (DPE_SIGN(j) * kb[j / 6][j % 3]) * pe[DPE_PARTNER(j)]);
         uint32_t hi[12], lo[12];
 #pragma unroll
         for (int qd = 0; qd < 3; ++qd) {
@@ -1818,8 +1848,8 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = j4 * 4 + e;
-            const float z = F16 ? fmaf(v[j], i7, dv * bb[e]) : fmaf(dv, bb[e], v[j]);
-            v[j] = ((bits >> j) & 1u) ? (F16 ? z * sZH : z) : 0.f;
+            const float z = F16 ? fmaf(v[j], k7, dvH * bb[e]) : fmaf(dv, bb[e], v[j]);      // zh sZH
+            v[j] = ((bits >> j) & 1u) ? z : 0.f;
           }
         }
         emit(cg, v, blob_h<PL>(nt, B_ZH), R0 + cg * 32);
@@ -1839,8 +1869,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int j = j4 * 4 + e;
-            z[j] = F16 ? fmaf(v[j], i8, dv * bb[e]) : fmaf(dv, bb[e], v[j]);
-            v[j] = F16 ? z[j] * sZC : z[j];
+            z[j] = v[j] = F16 ? fmaf(v[j], k8, dvC * bb[e]) : fmaf(dv, bb[e], v[j]);           // zc sZC
           }
         }
 #pragma unroll
@@ -1852,7 +1881,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           __stcs(reinterpret_cast<uint4*>(blob_h<PL>(nt, B_ZC) + BLOB_H + off), pq[1]);
         }
         const float cs = warp_colsum32(z, lane);
-        atomicAdd(csum + cg * 32 + lane, cs);
+        atomicAdd(csum + cg * 32 + lane, cs * inv_sZC);
       }
       tc_fence_before();                                                // my reads of R1 precede the prologue's tcgen05.st of the next net
       // ---- flush this net's column sums ----

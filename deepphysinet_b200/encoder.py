@@ -40,7 +40,15 @@ class _TokenConv(nn.Module):
         nn.init.kaiming_normal_(self.tokenConv.weight, mode="fan_in", nonlinearity="leaky_relu")
 
     def forward(self, x):                      # x [B, tokens, c_in]
-        return self.tokenConv(x.transpose(1, 2)).transpose(1, 2)
+        # The circular k = 3 convolution as ONE GEMM over the three neighbouring tokens: out[l] = sum_k W[:, :, k] x[(l + k - 1) % L].
+        # Same arithmetic as F.conv1d (fp32 products, different summation order); cuDNN's implicit-GEMM kernel for this shape
+        # (c_in = 2405, 159 tokens) needs 0.62 ms forward + 0.20 ms weight gradient per step, 4 % of an end-to-end step.
+        conv = self.tokenConv
+        if conv.kernel_size != (3,) or conv.padding_mode != "circular":
+            return conv(x.transpose(1, 2)).transpose(1, 2)
+        x3 = torch.cat([x.roll(1, dims=1), x, x.roll(-1, dims=1)], dim=-1)               # [B, L, 3 c_in]
+        wm = conv.weight.permute(2, 1, 0).reshape(3 * conv.in_channels, conv.out_channels)
+        return torch.addmm(conv.bias, x3.reshape(-1, x3.shape[-1]), wm).view(x.shape[0], x.shape[1], -1)
 
 
 class _FieldEmbedding(nn.Module):
