@@ -31,9 +31,12 @@ if ROOT not in sys.path:
 
 ALGO_FLOP_PER_POINT = 31.89e6      # fwd + Jacobian + bwd, GEMM work only
 # contraction FLOPs of the executed algorithm: pass 1 + pass 2 + weight gradients, 6 nets, 2 FLOP per MAC;
-# the split modes run pass 2 as the forward pass of the combined row (229 376 MACs), the bf16 mode as the tangent chain (179 200)
-EXEC_FLOP = {m: 6 * 2 * (407040 + p2 + 228352) for m, p2 in (('f16x3', 229376), ('bf16x3', 229376), ('bf16', 179200), ('fp32', 179200))}
+# the split modes run pass 2 as the forward pass of the combined row WITHOUT its third GEMM (163 840 MACs: the column sum of gz comes
+# out of the dWa contraction), the bf16 mode as the tangent chain (179 200)
+EXEC_FLOP = {m: 6 * 2 * (407040 + p2 + 228352) for m, p2 in (('f16x3', 163840), ('bf16x3', 163840), ('bf16', 179200), ('fp32', 179200))}
 MMA_PASSES = {"bf16": 1, "bf16x3": 3, "f16x3": 3, "fp32": 1}   # tensor-core MMAs issued per contraction (split operands: 3)
+# ... except the two contractions whose A operand is the exact 0 / 1 ReLU mask (G4 of pass 1, dWa): 2 MMAs.  FLOPs as ISSUED to the pipe:
+ISSUED_FLOP = {m: MMA_PASSES[m] * EXEC_FLOP[m] - (6 * 2 * 2 * 65536 if m in ("f16x3", "bf16x3") else 0) for m in EXEC_FLOP}
 DTYPE = {"bf16": "bf16", "bf16x3": "bf16 hi+lo (3 MMAs), fp32 accumulate", "f16x3": "fp16 hi+lo scaled (3 MMAs), fp32 accumulate", "fp32": "f32"}
 METRIC = "pde_residual_query_points_per_sec_fwd_jacobian_bwd"
 UNIT = "points/s"
@@ -483,6 +486,14 @@ def main():
             torch.cuda.synchronize()
             ms_m = e0.elapsed_time(e1) / n_m
             modes[m] = {"value": B * Np / (ms_m * 1e-3), "unit": UNIT, "ms_per_step": ms_m, "note": notes[m]}
+            if m == "fp32":                                  # CUDA-core mode: executed FLOPs against the MEASURED FP32 FFMA peak (tools/ffma_peak.cu)
+                try:
+                    ffma = json.load(open(os.path.join(ROOT, "profiles", "ffma_peak.json")))["fp32_ffma_tflops_sustained"]
+                    ex = EXEC_FLOP[m] * modes[m]["value"] / 1e12
+                    modes[m]["roofline"] = {"bound": "fp32 FFMA", "achieved": ex, "peak": ffma, "unit": "TFLOP/s", "frac": ex / ffma,
+                                            "note": "executed contraction FLOPs (%.2f MFLOP/point)" % (EXEC_FLOP[m] / 1e6)}
+                except Exception:
+                    pass
 
     # ---- the other single-GPU configurations of BASELINE.json, a few steps each ----
     configs = {}
@@ -548,7 +559,7 @@ def main():
                 "algorithmic_flop_per_point": ALGO_FLOP_PER_POINT, "executed_flop_per_point": EXEC_FLOP[args.mode],
                 "executed_tflops": EXEC_FLOP[args.mode] * per_gpu_pts / 1e12,
                 "mma_passes_per_contraction": MMA_PASSES[args.mode],
-                "tensor_pipe_tflops": MMA_PASSES[args.mode] * EXEC_FLOP[args.mode] * per_gpu_pts / 1e12}
+                "tensor_pipe_tflops": ISSUED_FLOP[args.mode] * per_gpu_pts / 1e12}
 
     # ---- the reference's own way of running this path on the same GPU: PyTorch eager autograd (double backward) ----
     eager_gpu = None

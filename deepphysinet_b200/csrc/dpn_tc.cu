@@ -897,7 +897,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     // ---------------- producer: weight chunks (multicast slices) + this tile's PE slices ----------------
     uint32_t s = 0, ph = 0;
     const uint64_t pol = l2_policy_evict_last();
-    auto put = [&](const uint8_t* wsrc, const uint32_t wbytes, const uint8_t* asrc) {
+    auto put = [&](const uint8_t* wsrc, uint32_t wbytes, const uint8_t* asrc) {
+#ifdef DPN_EXP_HALFSTREAM
+      wbytes /= 2;                                     // TIMING EXPERIMENT ONLY (wrong results): half of every weight chunk is fetched
+#endif
       mbar_wait(&pipe.empty[s], ph ^ 1);
       if (elect_one()) {
         uint8_t* stg = ring + s * ts::STAGE;
