@@ -9,7 +9,7 @@ Parity pinning: the reference ships no tests or golden vectors (SURVEY.md sectio
 oracle is pinned by running the UNMODIFIED reference in the build container
 (oracle/ref_harness.py + oracle/make_golden.py) and committing the resulting vectors under
 tests/golden/; tests/test_oracle_golden.py checks this file against them on every run, and
-tests/test_oracle_vs_reference.py re-runs the live comparison when /root/reference is mounted.
+oracle/make_golden.py re-generates the vectors (and with them the live comparison) when /root/reference is mounted.
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
 It keeps the reference's structure on purpose - six separate coordinate nets, one
