@@ -262,11 +262,11 @@ __host__ __device__ __forceinline__ float pow2_floor(float x) {           // lar
 __device__ __forceinline__ float scale_for(float bound) { return pow2_floor(F16_TOP / fmaxf(bound, 1e-30f)); }
 // element (r, 8*kc .. 8*kc+7) of a 128-row blob
 __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)kc * CORE_STRIDE + (uint32_t)r * 16; }
-// byte offset of the 16-byte piece (row r, k-core kc) of a workspace tile of the split modes: [point half][k-core][64 rows][16 B],
-// KC k-cores per tile.  A 64-point half of a tile is contiguous, which is what lets the weight-gradient kernel double-buffer
-// half tiles (wgrad2_kernel); a warp (32 consecutive rows) still writes 512 contiguous bytes per 16-byte store.
+// byte offset of the 16-byte piece (row r, k-core kc) of a workspace tile of the split modes: [point quarter][k-core][32 rows][16 B],
+// KC k-cores per tile.  A 32-point quarter of a tile is contiguous, which is what lets the weight-gradient kernel stream quarter
+// tiles through three stages (wgrad2_kernel); a warp (32 consecutive rows) still writes 512 contiguous bytes per 16-byte store.
 __device__ __forceinline__ uint32_t gp_off(const int KC, const int r, const int kc) {
-  return (uint32_t)(r >> 6) * (uint32_t)(KC * 1024) + (uint32_t)kc * 1024u + (uint32_t)(r & 63) * 16u;
+  return (uint32_t)(r >> 5) * (uint32_t)(KC * 512) + (uint32_t)kc * 512u + (uint32_t)(r & 31) * 16u;
 }
 template <int PL>
 __device__ __forceinline__ uint32_t blob_off(const int KC, const int r, const int kc) { return PL == 2 ? gp_off(KC, r, kc) : piece_off(r, kc); }
@@ -2068,55 +2068,62 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradients of the split modes: same contraction, restructured around what limited wgrad_kernel<2> (one 200 KB stage per SM:
-// load and MMA strictly alternate, 3.8 TB/s where the same access pattern reaches 5.5 TB/s with two resident CTAs):
-//   * tiles are stored [point half][k-core][64 rows][16 B] (gp_off), so a 64-point half of every operand is contiguous and a stage is
-//     98 KB: J half-columns 2 x 16 KB | Z 2 x 32 KB (24 KB for the 192-wide layers) | seed tile 2 KB.  TWO stages: the bulk loads of
-//     half-tile i+1 run under the 12 (+ seed) MMAs of half-tile i;
-//   * layer 2 contracts the BARE mask: S = m3^T zc with J = [a3 > 0] as one exact 16-bit plane built from the mask bits of pass 1
-//     (two MMAs per step instead of three, no stored J tile).  Its epilogue derives three results from S and the seed product
-//     sm3 = sum_p m3 dov:  dWa = diag(u) S,  dba = u sm3,  and the column sum of the never-formed tile gz = m3 (zc Wa^T + dov ba):
+// load and MMA strictly alternate, 3.8 TB/s where the same access pattern reaches 5.5 TB/s with two resident CTAs).  The kernel is
+// HBM-bound (it reads every operand tile pass 1 / pass 2 wrote), so the structure follows the bytes:
+//   * tiles are stored [point quarter][k-core][32 rows][16 B] (gp_off), so a 32-point quarter of every operand is contiguous; THREE
+//     stages of 73 KB: the bulk loads of quarter-tiles i+1, i+2 run under the MMAs of quarter-tile i;
+//   * three kinds of work item per (sample, net):  0: dW1 = qm^T zp (+ db1);  1: dW2 = y^T zh AND dWd = y^T zd (+ db2) - the two layers
+//     that share J = y run in ONE item with a 256 + 192 column accumulator, so the y tile is read once (-15 % of the kernel's bytes);
+//     2: S = m3^T zc with J = [a3 > 0] as one exact 16-bit plane built from the mask bits of pass 1 (two MMAs per step instead of
+//     three, no stored J tile).  Its epilogue derives three results from S and the seed product sm3 = sum_p m3 dov:
+//     dWa = diag(u) S,  dba = u sm3,  and the column sum of the never-formed tile gz = m3 (zc Wa^T + dov ba):
 //     vg[j] = sum_i Wa[j,i] S[j,i] + ba[j] sm3[j]  - which is why pass 2 has no third GEMM;
+//   * bias gradients are seed-tile products (an N = 16 MMA of the same J planes against the three 16-bit terms of dov);
+//   * the two CTAs of a cluster are the two output halves of one item: they contract against the SAME Z quarter-tiles, each fetches
+//     half of every Z plane (and of the seed tile) and multicasts it to both - one L2 / DRAM read instead of two;
 //   * epilogue: every thread owns one output row; it parks the scaled row in shared memory (the stages are free by then) and hands
 //     it to the TMA engine as ONE bulk fp32 reduction (cp.reduce.async.bulk ... add.f32, 768 / 1024 contiguous bytes) instead of
 //     192 / 256 scalar red.global.add whose 32 lanes hit 32 different rows.
 // ------------------------------------------------------------------------------------------------
 namespace wg2 {
-constexpr int PT = 64;                              // points per stage
-constexpr int J_PLANE = PT * 128 * 2;               // 16384: [16 k-cores of this out-half][64][16 B]
-constexpr int Z_PLANE = PT * H * 2;                 // 32768 (24576 used by the 192-wide layers)
-constexpr int X_BYTES = PT * 16 * 2;                // 2048 seed tile
-constexpr int STAGE = 2 * J_PLANE + 2 * Z_PLANE + X_BYTES;   // 100352
-constexpr int SMEM = 2 * STAGE;                     // 200704
+constexpr int PT = 32;                              // points per stage
+constexpr int NSTG = 3;
+constexpr int J_PLANE = PT * 128 * 2;               // 8192: [16 k-cores of this out-half][32][16 B]
+constexpr int ZH_PLANE = PT * H * 2;                // 16384
+constexpr int ZC_PLANE = PT * C * 2;                // 12288
+constexpr int X_BYTES = PT * 16 * 2;                // 1024 seed tile
+constexpr int OFF_Z1 = 2 * J_PLANE, OFF_Z2 = OFF_Z1 + 2 * ZH_PLANE, OFF_X = OFF_Z2 + 2 * ZC_PLANE;
+constexpr int STAGE = OFF_X + X_BYTES;              // 74752
+constexpr int SMEM = NSTG * STAGE;                  // 224256
 constexpr int ROW_PAD = 16;                         // bytes between staged output rows: 1040-byte pitch -> conflict-free 16-byte stores
-static_assert(128 * (H * 4 + ROW_PAD) <= SMEM, "the staged [128 x 256] fp32 output must fit the two (idle) stages");
+constexpr int ITEMS = 3;                            // work-item kinds per (sample, net)
+static_assert(128 * (H * 4 + ROW_PAD) <= SMEM, "the staged [128 x 256] fp32 output must fit the (idle) stages");
+static_assert(SMEM + 1024 <= 227 * 1024, "three stages must fit one SM's 227 KB");
 }  // namespace wg2
 
 template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
   constexpr int PL = 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[2], empty[2], acc_ready;
+  __shared__ uint64_t full[wg2::NSTG], empty[wg2::NSTG], acc_ready;
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  // the two CTAs of a cluster are the two output halves (mh) of one (sample, net, layer, split): they contract against the SAME Z
-  // half-tiles, so each fetches half of every Z plane (and of the seed tile) and multicasts it to both - one L2 / DRAM read
-  // instead of two (ncu, round 2: 27 GB of DRAM reads per launch for 20 GB of distinct tiles without the multicast)
   int item = blockIdx.x;
-  const int mh = item & 1; item >>= 1;                               // == cluster rank
+  const int mh = item & 1; item >>= 1;                               // output half == cluster rank
   const int split = item % w.splits; item /= w.splits;
-  const int layer = item & 3; item >>= 2;
+  const int kind = item % wg2::ITEMS; item /= wg2::ITEMS;            // 0: dW1   1: dW2 + dWd   2: dWa (mask)
   const int k = item % w.Kn, b = item / w.Kn;
-  const int Nn = (layer == 0 || layer == 3) ? C : H;
-  const int KCz = Nn / 8;                                             // k-cores of the Z tile
-  const bool aux = layer != 1;                                        // layer 1 shares its J operand (y) with layer 3, which delivers db2
-  const uint32_t zplane = (uint32_t)wg2::PT * Nn * 2;                 // bytes of one plane of a Z half-tile
-  const int jsel = layer == 0 ? B_QM : B_YT;                          // layer 2: J = [a3 > 0] is built in shared memory from the m3 mask bits
-  const bool build_j = layer == 2;
+  const int N1 = kind == 0 ? C : H;                                   // columns of the first Z tile (zp | zh | zc)
+  const bool two = kind == 1;                                         // second Z tile: zd, N = 192
+  const bool build_j = kind == 2;
+  const uint32_t z1plane = (uint32_t)wg2::PT * N1 * 2;                // bytes of one plane of a Z1 quarter-tile
+  const int jsel = kind == 0 ? B_QM : B_YT;
   const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
-  const int nst = 2 * (t1 - t0);                                      // half-tiles
+  const int nst = 4 * (t1 - t0);                                      // quarter-tiles
   if (tid == 0) {
-    mbar_init(&full[0], build_j ? 129 : 1); mbar_init(&full[1], build_j ? 129 : 1); mbar_init(&empty[0], 2); mbar_init(&empty[1], 2); mbar_init(&acc_ready, 1);
+    for (int s = 0; s < wg2::NSTG; ++s) { mbar_init(&full[s], build_j ? 129 : 1); mbar_init(&empty[s], 2); }
+    mbar_init(&acc_ready, 1);
     fence_barrier_init();
   }
   if (warp == 5) tmem_alloc(&tmem_s, 512);
@@ -2125,63 +2132,70 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
   tc_fence_after();
   cluster_sync_all();                                                // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem = tmem_s;
-  constexpr uint32_t COL_X = 256;                                     // seed-product columns
+  constexpr uint32_t COL_D2 = 256, COL_X = 448;                       // TMEM: D1 [0,256) | D2 (dWd) [256,448) | seed product [448,464)
   if (nst > 0) {
     if (warp == 4) {
       for (int i = 0; i < nst; ++i) {
-        const int t = t0 + (i >> 1), ph = i & 1;                      // tile, point half
+        const int t = t0 + (i >> 2), pq = i & 3;                      // tile, point quarter
         const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
-        const uint8_t* jsrc = nt + off_h<PL>(jsel) + (size_t)ph * (BLOB_H / 2) + (size_t)mh * wg2::J_PLANE;
-        const uint8_t* zsrc = (layer == 0 ? nt + off_zp<PL>() : layer == 3 ? nt + off_zd<PL>()
-                             : nt + off_h<PL>(layer == 1 ? B_ZH : B_ZC)) + (size_t)ph * zplane;
-        const uint32_t zstride = (layer == 0 || layer == 3) ? BLOB_C : BLOB_H;     // plane stride of the Z tile in the workspace
-        const uint8_t* xsrc = nt + off_aux<PL>() + (size_t)ph * wg2::X_BYTES;
-        const int s = i & 1;
+        const uint8_t* jsrc = nt + off_h<PL>(jsel) + (size_t)pq * (BLOB_H / 4) + (size_t)mh * wg2::J_PLANE;
+        const uint8_t* z1src = (kind == 0 ? nt + off_zp<PL>() : nt + off_h<PL>(kind == 1 ? B_ZH : B_ZC)) + (size_t)pq * z1plane;
+        const uint32_t z1stride = kind == 0 ? BLOB_C : BLOB_H;          // plane stride of the Z1 tile in the workspace
+        const uint8_t* z2src = nt + off_zd<PL>() + (size_t)pq * wg2::ZC_PLANE;
+        const uint8_t* xsrc = nt + off_aux<PL>() + (size_t)pq * wg2::X_BYTES;
+        const int s = i % wg2::NSTG;
         uint8_t* st = smem + s * wg2::STAGE;
-        mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);                     // BOTH CTAs are done with the previous occupant (multicast commits)
+        mbar_wait(&empty[s], ((i / wg2::NSTG) & 1) ^ 1);              // BOTH CTAs are done with the previous occupant (multicast commits)
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], (build_j ? 0 : 2 * wg2::J_PLANE) + 2 * zplane + (aux ? wg2::X_BYTES : 0));   // my J + both halves of Z / seeds
-          const uint32_t zh = zplane / 2, xh = wg2::X_BYTES / 2;
+          mbar_arrive_expect_tx(&full[s], (build_j ? 0 : 2 * wg2::J_PLANE) + 2 * z1plane + (two ? 2 * wg2::ZC_PLANE : 0) + wg2::X_BYTES);
+          const uint32_t zh = z1plane / 2, z2h = wg2::ZC_PLANE / 2, xh = wg2::X_BYTES / 2;
 #pragma unroll
           for (int p = 0; p < PL; ++p) {
             if (!build_j) bulk_g2s(st + p * wg2::J_PLANE, jsrc + (size_t)p * BLOB_H, wg2::J_PLANE, &full[s]);
-            bulk_g2s_mc(st + 2 * wg2::J_PLANE + p * wg2::Z_PLANE + mh * zh, zsrc + (size_t)p * zstride + mh * zh, zh, &full[s], (uint16_t)3);
+            bulk_g2s_mc(st + wg2::OFF_Z1 + p * wg2::ZH_PLANE + mh * zh, z1src + (size_t)p * z1stride + mh * zh, zh, &full[s], (uint16_t)3);
+            if (two) bulk_g2s_mc(st + wg2::OFF_Z2 + p * wg2::ZC_PLANE + mh * z2h, z2src + (size_t)p * BLOB_C + mh * z2h, z2h, &full[s], (uint16_t)3);
           }
-          if (aux) bulk_g2s_mc(st + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE + mh * xh, xsrc + mh * xh, xh, &full[s], (uint16_t)3);
+          bulk_g2s_mc(st + wg2::OFF_X + mh * xh, xsrc + mh * xh, xh, &full[s], (uint16_t)3);
         }
       }
     } else if (warp == 5) {
-      const uint32_t idesc = idesc_16(F16, Nn, 1, 1), idesc_x = idesc_16(F16, 16, 1, 1);
-      // MN-major operands: 8-element groups of the M / N dimension are one k-core block of [64 points][16 B] = 1024 bytes apart,
+      const uint32_t idesc1 = idesc_16(F16, N1, 1, 1), idesc2 = idesc_16(F16, C, 1, 1), idesc_x = idesc_16(F16, 16, 1, 1);
+      // MN-major operands: 8-element groups of the M / N dimension are one k-core block of [32 points][16 B] = 512 bytes apart,
       // 8-point groups of the K dimension 128 bytes; a K = 16-point step adds 256 bytes (>> 4) to the address field
       constexpr uint32_t SBO = wg2::PT * 16;
+      constexpr uint32_t a_lo = wg2::J_PLANE >> 4, b1_lo = wg2::ZH_PLANE >> 4, b2_lo = wg2::ZC_PLANE >> 4;
       for (int i = 0; i < nst; ++i) {
-        const int s = i & 1;
+        const int s = i % wg2::NSTG;
         const uint32_t base = smem_u32(smem + s * wg2::STAGE);
-        const uint64_t a_hi = smem_desc(base, 128, SBO), b_hi = smem_desc(base + 2 * wg2::J_PLANE, 128, SBO);
-        const uint64_t x_d = smem_desc(base + 2 * wg2::J_PLANE + 2 * wg2::Z_PLANE, 128, SBO);
-        constexpr uint32_t a_lo = wg2::J_PLANE >> 4, b_lo = wg2::Z_PLANE >> 4;
-        mbar_wait(&full[s], (i >> 1) & 1);
+        const uint64_t a_hi = smem_desc(base, 128, SBO), b1_hi = smem_desc(base + wg2::OFF_Z1, 128, SBO), b2_hi = smem_desc(base + wg2::OFF_Z2, 128, SBO);
+        const uint64_t x_d = smem_desc(base + wg2::OFF_X, 128, SBO);
+        mbar_wait(&full[s], (i / wg2::NSTG) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < wg2::PT / 16; ++ks) {
             const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-            const uint64_t ad = a_hi + ks * 16, bd = b_hi + ks * 16, xd = x_d + ks * 16;
+            const uint64_t ad = a_hi + ks * 16, b1 = b1_hi + ks * 16, b2 = b2_hi + ks * 16, xd = x_d + ks * 16;
+            // every J plane is fetched from shared memory once per step for all MMAs that read it (A collector)
             if (build_j) {                                   // exact one-plane J (the mask): J Z_lo + J Z_hi + J seeds
-              mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, first);
-              mma_f16_c<A_USE>(tmem, ad, bd, idesc, 1u);
+              mma_f16_c<A_FILL>(tmem, ad, b1 + b1_lo, idesc1, first);
+              mma_f16_c<A_USE>(tmem, ad, b1, idesc1, 1u);
               mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, first);
-            } else if (aux) {                                // every J plane is fetched once per step for all MMAs that read it
-              mma_f16_c<A_FILL>(tmem, ad + a_lo, bd, idesc, first);
+            } else if (two) {                                // J = y against zh (D1) and zd (D2)
+              mma_f16_c<A_FILL>(tmem, ad + a_lo, b1, idesc1, first);
+              mma_f16_c<A_USE>(tmem + COL_D2, ad + a_lo, b2, idesc2, first);
               mma_f16_c<A_LAST>(tmem + COL_X, ad + a_lo, xd, idesc_x, first);
-              mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
-              mma_f16_c<A_USE>(tmem, ad, bd, idesc, 1u);
+              mma_f16_c<A_FILL>(tmem, ad, b1 + b1_lo, idesc1, 1u);
+              mma_f16_c<A_USE>(tmem, ad, b1, idesc1, 1u);
+              mma_f16_c<A_USE>(tmem + COL_D2, ad, b2 + b2_lo, idesc2, 1u);
+              mma_f16_c<A_USE>(tmem + COL_D2, ad, b2, idesc2, 1u);
               mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, 1u);
             } else {
-              mma_bf16(tmem, ad + a_lo, bd, idesc, first);
-              mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
-              mma_f16_c<A_LAST>(tmem, ad, bd, idesc, 1u);
+              mma_f16_c<A_FILL>(tmem, ad + a_lo, b1, idesc1, first);
+              mma_f16_c<A_LAST>(tmem + COL_X, ad + a_lo, xd, idesc_x, first);
+              mma_f16_c<A_FILL>(tmem, ad, b1 + b1_lo, idesc1, 1u);
+              mma_f16_c<A_USE>(tmem, ad, b1, idesc1, 1u);
+              mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, 1u);
             }
           }
           mma_commit_mc(&empty[s], (uint16_t)3);                      // the stage is free in BOTH CTAs' eyes only when both have read it
@@ -2190,79 +2204,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
       if (elect_one()) mma_commit(&acc_ready);
     } else if (warp < 4) {
       if (build_j) {
-        // J half-tile = [16 k-cores][64 points][8 features]: thread = (point, 64-feature group g): 8 pieces per plane from 64 mask bits
-        const int pt = tid & 63, gq = tid >> 6;
+        // J quarter-tile = [16 k-cores][32 points][8 features], one plane: thread = (point, 32-feature group gq): 4 pieces from one mask word
+        const int pt = tid & 31, gq = tid >> 5;
         for (int i = 0; i < nst; ++i) {
-          const int t = t0 + (i >> 1), ph = i & 1, s = i & 1;
+          const int t = t0 + (i >> 2), pq = i & 3, s = i % wg2::NSTG;
           const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
-          const uint2 mw = __ldg(reinterpret_cast<const uint2*>(nt + off_mask<PL>() + MASK_BYTES / 2) + (size_t)(ph * wg2::PT + pt) * 4 + mh * 2 + gq);
+          const uint32_t mw = __ldg(reinterpret_cast<const uint32_t*>(nt + off_mask<PL>() + MASK_BYTES / 2) + (size_t)(pq * wg2::PT + pt) * 8 + mh * 4 + gq);
           uint8_t* st = smem + s * wg2::STAGE;
-          mbar_wait(&empty[s], ((i >> 1) & 1) ^ 1);                   // both CTAs' MMAs are done with the previous occupant of the stage
+          mbar_wait(&empty[s], ((i / wg2::NSTG) & 1) ^ 1);            // both CTAs' MMAs are done with the previous occupant of the stage
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t bits = ((j < 4 ? mw.x : mw.y) >> ((j & 3) * 8)) & 0xFFu;
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t bits = (mw >> (j * 8)) & 0xFFu;
             constexpr uint32_t ONE = F16 ? 0x3C00u : 0x3F80u;                 // 1.0 in the operand format
             uint32_t hi[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) hi[e] = (((bits >> (2 * e)) & 1u) ? ONE : 0u) | (((bits >> (2 * e + 1)) & 1u) ? (ONE << 16) : 0u);
-            const uint32_t off = (uint32_t)(gq * 8 + j) * (wg2::PT * 16) + (uint32_t)pt * 16;
+            const uint32_t off = (uint32_t)(gq * 4 + j) * (wg2::PT * 16) + (uint32_t)pt * 16;
             *reinterpret_cast<uint4*>(st + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           }
           fence_proxy_async();                                         // generic-proxy stores -> visible to the tensor core's reads
           mbar_arrive(&full[s]);
         }
       }
-      mbar_wait(&acc_ready, 0);                                        // every MMA has completed: both stages are idle
+      mbar_wait(&acc_ready, 0);                                        // every MMA has completed: all stages are idle
       tc_fence_after();
       const size_t gk = ((size_t)b * w.Kn + k);
-      float* dst = layer == 0 ? w.gW1 + gk * H * C
-                 : layer == 1 ? w.gW2 + gk * H * H
-                 : layer == 2 ? w.gWa + (size_t)k * H * H
-                 : w.gWd + (size_t)k * H * C;
-      dst += (size_t)(mh * TP + tid) * Nn;
-      float un = 1.f, un_x = 1.f;                                      // fp16 variant: undo (J tile scale) x (Z tile / seed scale)
+      const int out = mh * TP + tid;
+      float un1 = 1.f, un2 = 1.f, un_x = 1.f;                          // fp16 variant: undo (J tile scale) x (Z tile / seed scale)
       if (F16) {
         const NetScales t = w.sc[gk];
-        const float sj = layer == 0 ? t.sQ : (layer == 2 ? 1.f : t.sY);      // (the mask of layer 2 carries no scale)
-        const float sz = layer == 0 ? t.sZP : (layer == 1 ? t.sZH : (layer == 2 ? t.sZC : t.sZD));
-        un = (1.f / sj) * (1.f / sz); un_x = (1.f / sj) * (1.f / t.sDV);      // separately: sj * sz may leave the fp32 range
+        const float sj = kind == 0 ? t.sQ : (kind == 2 ? 1.f : t.sY);        // (the mask carries no scale)
+        const float sz1 = kind == 0 ? t.sZP : (kind == 1 ? t.sZH : t.sZC);
+        un1 = (1.f / sj) * (1.f / sz1); un2 = (1.f / sj) * (1.f / t.sZD); un_x = (1.f / sj) * (1.f / t.sDV);   // separately: sj * sz may leave the fp32 range
       }
-      const int out = mh * TP + tid;
-      // layer 2: this row of S = m3^T zc gives dWa[out,:] = u[out] S and the dot product with Wa[out,:] that vg needs
+      // kind 2: this row of S = m3^T zc gives dWa[out,:] = u[out] S and the dot product with Wa[out,:] that vg needs
       const float urow = build_j ? __ldg(w.uvec + (size_t)k * H + out) : 1.f;
       const float* warow = w.Wa + ((size_t)k * H + out) * H;
       float dot0 = 0.f, dot1 = 0.f;
       uint8_t* myrow = smem + (size_t)tid * (H * 4 + wg2::ROW_PAD);
+      const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
       float v[32];
-      for (int cb = 0; cb < Nn / 32; ++cb) {
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
-        if (build_j) {
+      {
+        float* dst = (kind == 0 ? w.gW1 + gk * H * C : kind == 1 ? w.gW2 + gk * H * H : w.gWa + (size_t)k * H * H) + (size_t)out * N1;
+        const float sc = un1 * urow;
+        for (int cb = 0; cb < N1 / 32; ++cb) {
+          tmem_ld32(lane_base + cb * 32, v);
+          if (build_j) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(warow + cb * 32) + j4);
-            dot0 = fmaf(v[j4 * 4], wv.x, dot0); dot1 = fmaf(v[j4 * 4 + 1], wv.y, dot1);
-            dot0 = fmaf(v[j4 * 4 + 2], wv.z, dot0); dot1 = fmaf(v[j4 * 4 + 3], wv.w, dot1);
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 wv = __ldg(reinterpret_cast<const float4*>(warow + cb * 32) + j4);
+              dot0 = fmaf(v[j4 * 4], wv.x, dot0); dot1 = fmaf(v[j4 * 4 + 1], wv.y, dot1);
+              dot0 = fmaf(v[j4 * 4 + 2], wv.z, dot0); dot1 = fmaf(v[j4 * 4 + 3], wv.w, dot1);
+            }
           }
-        }
-        const float sc = un * urow;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<float4*>(myrow + cb * 128 + j4 * 16) =
-              (F16 || build_j) ? make_float4(v[j4 * 4] * sc, v[j4 * 4 + 1] * sc, v[j4 * 4 + 2] * sc, v[j4 * 4 + 3] * sc)
-                               : make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(myrow + cb * 128 + j4 * 16) =
+                (F16 || build_j) ? make_float4(v[j4 * 4] * sc, v[j4 * 4 + 1] * sc, v[j4 * 4 + 2] * sc, v[j4 * 4 + 3] * sc)
+                                 : make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        fence_proxy_async();                                           // my generic-proxy row -> visible to the bulk engine
+        bulk_red_add_f32(dst, myrow, (uint32_t)N1 * 4u);
+        bulk_commit();
       }
-      fence_proxy_async();                                             // my generic-proxy row -> visible to the bulk engine
-      bulk_red_add_f32(dst, myrow, (uint32_t)Nn * 4u);
-      bulk_commit();
-      if (aux) {
+      if (two) {                                                       // second output of the merged item: dWd rows (the staging row is reused)
+        float* dst = w.gWd + (size_t)k * H * C + (size_t)out * C;
+        bulk_wait_read_all();
+        for (int cb = 0; cb < C / 32; ++cb) {
+          tmem_ld32(lane_base + COL_D2 + cb * 32, v);
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(myrow + cb * 128 + j4 * 16) =
+                F16 ? make_float4(v[j4 * 4] * un2, v[j4 * 4 + 1] * un2, v[j4 * 4 + 2] * un2, v[j4 * 4 + 3] * un2)
+                    : make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+        }
+        fence_proxy_async();
+        bulk_red_add_f32(dst, myrow, (uint32_t)C * 4u);
+        bulk_commit();
+      }
+      {
         float x[16];
-        tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + COL_X, x);
+        tmem_ld16(lane_base + COL_X, x);
         const float bsum = (x[0] + x[1] + x[2]) * un_x;                // the three 16-bit terms of the seed
-        if (layer == 0) {
+        if (kind == 0) {
           atomicAdd(w.gb1 + gk * H + out, bsum);
-        } else if (layer == 2) {                                       // bsum = sum_p m3[p,out] dov[p]
+        } else if (kind == 2) {                                        // bsum = sum_p m3[p,out] dov[p]
           atomicAdd(w.gba + (size_t)k * H + out, urow * bsum);
-          atomicAdd(w.vg + (size_t)k * H + out, fmaf(__ldg(w.ba + (size_t)k * H + out), bsum, (dot0 + dot1) * un));
+          atomicAdd(w.vg + (size_t)k * H + out, fmaf(__ldg(w.ba + (size_t)k * H + out), bsum, (dot0 + dot1) * un1));
         } else {
           atomicAdd(w.gb2 + gk * H + out, bsum);
           atomicAdd(w.ge + gk * H + out, bsum);
@@ -2778,7 +2806,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     ww.Wa = Wt.Wa; ww.ba = Wt.ba; ww.vg = c.vg;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd; ww.gba = G.ba;
-    const int items = B * Kn * 8;
+    const int items = B * Kn * (PL == 2 ? 2 * wg2::ITEMS : 8);            // x 2 output halves
     // point-splits per (sample, net, layer, out-half): fill whole waves of resident CTAs (148 SMs x CTAs per SM); every split
     // adds one fp32 red.add pass over the gradient tile, so prefer the smallest count within 2 % of the best wave efficiency
     int splits = 1;
