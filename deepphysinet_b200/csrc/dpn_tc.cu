@@ -51,11 +51,7 @@ constexpr bool PAIR = DPN_PAIR != 0;
 #ifndef DPN_REUSE_A
 #define DPN_REUSE_A 1
 #endif
-constexpr bool REUSE_A = DPN_REUSE_A != 0;
-#ifndef DPN_DEFAULT_TS
-#define DPN_DEFAULT_TS 1
-#endif
-constexpr bool DEFAULT_TS = DPN_DEFAULT_TS != 0;         // split modes: pass 1 keeps its activation tile in tensor memory (pass1_ts_kernel)               // split modes: consecutive MMAs on the same A tile share one shared-memory fetch
+constexpr bool REUSE_A = DPN_REUSE_A != 0;               // split modes: consecutive MMAs on the same A tile share one shared-memory fetch
 #ifndef DPN_NSTAGE
 #define DPN_NSTAGE (DPN_PAIR ? 10 : 5)
 #endif
@@ -830,7 +826,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 }
 
 // ------------------------------------------------------------------------------------------------
-// Pass 1 with the activation tile in TENSOR MEMORY (split modes; opt-in: DPN_TS=1).
+// Pass 1 of the split modes: A operands in TENSOR MEMORY.
 // The A operand of every GEMM but G1 / G2b is written by the epilogues with tcgen05.st and read by the TS form of tcgen05.mma; the
 // PE / PE6 tiles of G1 / G2b travel through the ring as K = 16 slices next to their weight chunks; tiles kept for the backward pass
 // leave with streaming 16-byte stores from registers.  No activation buffer in shared memory -> the ring holds 9 stages of 24 KB.
