@@ -140,3 +140,39 @@ def test_predict_grid_matches_oracle_pipeline():
         vals = torch.cat(O.inverse_norm(O.physics_net_decode(meta, pe, cd, fh.cpu(), sp), with_clip=False), 1)
         got = out[ti].reshape(-1, 6).cpu().double()
         assert H.rel(got, vals.detach()) < 1e-4
+
+
+@pytest.mark.parametrize("K", [6, 1])
+def test_pre_encoded_surface_honours_mode(K):
+    """PhysicsNet.forward / VariableNet.forward hand the library an already encoded coordinate [N,192] (reference
+    model/physics_net.py:41-55, variable_net.py:49) and, for one net, an explicit `ref`.  Round 1 silently ran this surface on the
+    CUDA cores whatever `mode` said; now the requested mode runs: both modes agree with the oracle within their own tolerance, the
+    results differ in the last bits, and the kernel sequences differ (dpn_last_launch_count)."""
+    from deepphysinet_b200 import functional as Fn, testing as T, _native as N
+    from deepphysinet_b200.config import PhysicsConsts
+    from oracle import dpn_oracle as O
+    consts = PhysicsConsts()
+    W, pts = T.random_decoder_weights(B=1, N=500, seed=5, device="cuda")
+    if K == 1:                                                     # one net with its own skip input, like VariableNet.forward
+        W = Fn.DecoderWeights(*[(w[:, 2:3] if n in ("W1", "b1", "W2", "b2", "e") else w[2:3]).clone() for n, w in zip(Fn.DecoderWeights._fields, W)])
+    col = lambda k: pts[k][0].double().cpu().reshape(-1, 1)
+    pe64 = O.encoding_coord(col("x"), col("y"), col("t"), consts.dx, consts.dy, consts.lat_size, consts.lon_size, consts.pred_t_span)
+    cd = pts["coord_data"][0]
+    ref_in = cd[:, 2:3].contiguous() if K == 1 else None
+    names = Fn.DecoderWeights._fields
+    Wb = {n: (w[0] if n in ("W1", "b1", "W2", "b2", "e") else w).double().cpu() for n, w in zip(names, W)}
+    if K == 1:                                                     # variable_net.py:67-87 with the explicit skip input
+        want = O.decoder_net(pe64, cd.double().cpu(), ref_in.double().cpu(), Wb["W1"][0], Wb["b1"][0], Wb["W2"][0], Wb["b2"][0],
+                             Wb["e"][0], O._net_params(Wb, 0))
+    else:
+        want = torch.cat(O.decode_generated(pe64, cd.double().cpu(), Wb), 1)
+    pe32 = pe64.float().cuda()
+    got, launches = {}, {}
+    for mode in ("fp32", "f16x3"):
+        got[mode] = Fn.decoder_values(pe32, cd, W, ref=ref_in, mode=mode).detach().cpu()
+        launches[mode] = N.lib().dpn_last_launch_count()
+        assert got[mode].shape == (500, K)
+        assert H.rel(got[mode], want) < (1e-5 if mode == "fp32" else 2e-5), (mode, H.rel(got[mode], want))
+    assert H.rel(got["f16x3"], got["fp32"]) < 2e-5
+    assert not torch.equal(got["f16x3"], got["fp32"])              # different arithmetic actually ran
+    assert launches["fp32"] != launches["f16x3"], launches         # CUDA-core kernel sequence vs tcgen05 kernel sequence
