@@ -421,25 +421,34 @@ __global__ void prep_kernel(int B, int Kn, const float* __restrict__ Wb, const f
 
 // Gradients of the folded layer from the column sums: dWb = wo (x) vg ; dwo = 2 vc + Wb vg + bb sdo ;
 // dbb = wo sdo ; dbo = sdo.
-__global__ void finalize_kernel(const float* __restrict__ Wb, const float* __restrict__ bb, const float* __restrict__ wo,
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ Wb, const float* __restrict__ bb, const float* __restrict__ wo,
                                 const float* __restrict__ vc, const float* __restrict__ vg,
                                 const float* __restrict__ sdo, float* __restrict__ gWb, float* __restrict__ gbb,
                                 float* __restrict__ gwo, float* __restrict__ gbo) {
-  const int k = blockIdx.x, i = threadIdx.x;  // 256 threads; i = output row of Wb
+  // grid (Kn, 8): block y handles 32 rows of Wb, one warp per row at a time, lanes along the row (coalesced)
+  const int k = blockIdx.x, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   __shared__ float vgs[H];
-  vgs[i] = vg[k * H + i];
+  vgs[threadIdx.x] = vg[k * H + threadIdx.x];
   __syncthreads();
-  const float* W = Wb + ((size_t)k * H + i) * H;
-  float* G = gWb + ((size_t)k * H + i) * H;
-  const float w = wo[k * H + i], sd = sdo[k];
-  float s = 0.f;
-  for (int j = 0; j < H; ++j) {
-    s = fmaf(W[j], vgs[j], s);
-    G[j] = w * vgs[j];
+  const float sd = sdo[k];
+  for (int i = blockIdx.y * 32 + wrp; i < blockIdx.y * 32 + 32; i += 8) {
+    const float* W = Wb + ((size_t)k * H + i) * H;
+    float* G = gWb + ((size_t)k * H + i) * H;
+    const float w = wo[k * H + i];
+    float s = 0.f;
+#pragma unroll
+    for (int j = lane; j < H; j += 32) {
+      s = fmaf(W[j], vgs[j], s);
+      G[j] = w * vgs[j];
+    }
+#pragma unroll
+    for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(0xffffffffu, s, m);
+    if (lane == 0) {
+      gwo[k * H + i] = 2.f * vc[k * H + i] + s + bb[k * H + i] * sd;
+      gbb[k * H + i] = w * sd;
+    }
   }
-  gwo[k * H + i] = 2.f * vc[k * H + i] + s + bb[k * H + i] * sd;
-  gbb[k * H + i] = w * sd;
-  if (i == 0) gbo[k] = sd;
+  if (blockIdx.y == 0 && threadIdx.x == 0) gbo[k] = sd;
 }
 
 __global__ void copy_seed_kernel(size_t n, const float* __restrict__ src, float scale, float* __restrict__ dst) {
@@ -637,7 +646,7 @@ int run(const Job& J, cudaStream_t st) {
   }
   if (want_bwd) {
     const DpnGrads& G = *J.grads;
-    finalize_kernel<<<Kn, 256, 0, st>>>(Wt.Wb, Wt.bb, Wt.wo, w.vc, w.vg, w.sdo, G.Wb, G.bb, G.wo, G.bo);
+    finalize_kernel<<<dim3(Kn, 8), 256, 0, st>>>(Wt.Wb, Wt.bb, Wt.wo, w.vc, w.vg, w.sdo, G.Wb, G.bb, G.wo, G.bo);
     DPN_LAUNCH_OK();
   }
   return 0;
@@ -667,7 +676,7 @@ int launch_margin(int B, int P, size_t srow, size_t sq, const float* o, const fl
 
 int launch_finalize(int Kn, const DpnWeights& Wt, const float* vc, const float* vg, const float* sdo, const DpnGrads& G,
                     cudaStream_t st) {
-  finalize_kernel<<<Kn, 256, 0, st>>>(Wt.Wb, Wt.bb, Wt.wo, vc, vg, sdo, G.Wb, G.bb, G.wo, G.bo);
+  finalize_kernel<<<dim3(Kn, 8), 256, 0, st>>>(Wt.Wb, Wt.bb, Wt.wo, vc, vg, sdo, G.Wb, G.bb, G.wo, G.bo);
   DPN_LAUNCH_OK();
   return 0;
 }

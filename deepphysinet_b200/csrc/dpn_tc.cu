@@ -2356,30 +2356,62 @@ __device__ __forceinline__ float block_max256(float v, float* red) {      // 256
 }
 
 // One block per (sample, net): L1 norms / maxima of its matrices -> activation bounds and tile scales.
-__global__ void __launch_bounds__(256) bounds_kernel(int Kn, const float* __restrict__ W1, const float* __restrict__ b1,
+__global__ void __launch_bounds__(1024) bounds_kernel(int Kn, const float* __restrict__ W1, const float* __restrict__ b1,
                                                      const float* __restrict__ W2, const float* __restrict__ Wd,
                                                      const float* __restrict__ Wa, const float* __restrict__ ba,
                                                      const float* __restrict__ bsum, const float* __restrict__ uvec,
                                                      const float* __restrict__ wo2, const float* __restrict__ P,
                                                      NetScales* __restrict__ tab) {
   __shared__ float red[8];
-  const int bk = blockIdx.x, k = bk % Kn, j = threadIdx.x;
-  const float* w1 = W1 + ((size_t)bk * H + j) * C;
+  __shared__ float srow[8][H];                                       // per matrix row: L1 norm / maximum of W1, Wd, W2, Wa
+  // 1024 threads: the block reads ~1.4 MB and one SM's memory-level parallelism is what bounds it (48 blocks on 148 SMs)
+  __shared__ float scol[2][4][H];                                    // partial column L1 norms of W2, Wa
+  const int bk = blockIdx.x, k = bk % Kn, j = threadIdx.x & 255, part = threadIdx.x >> 8, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const float* w1m = W1 + (size_t)bk * H * C;
   const float* w2 = W2 + (size_t)bk * H * H;
-  const float* wd = Wd + ((size_t)k * H + j) * C;
+  const float* wdm = Wd + (size_t)k * H * C;
   const float* wa = Wa + (size_t)k * H * H;
-  float r1 = 0.f, m1 = 0.f, rd = 0.f, md = 0.f;
-  for (int i = 0; i < C; ++i) {
-    const float a = fabsf(w1[i]), d = fabsf(wd[i]);
-    r1 += a; m1 = fmaxf(m1, a); rd += d; md = fmaxf(md, d);
+  // row-wise quantities: one warp per row, lanes along the row (coalesced), shuffle reduction
+  for (int row = wrp; row < H; row += 32) {
+    float a1 = 0.f, x1 = 0.f, ad = 0.f, xd = 0.f, a2 = 0.f, x2 = 0.f, aa = 0.f, xa = 0.f;
+    for (int i = lane; i < C; i += 32) {
+      const float a = fabsf(w1m[(size_t)row * C + i]), d = fabsf(wdm[(size_t)row * C + i]);
+      a1 += a; x1 = fmaxf(x1, a); ad += d; xd = fmaxf(xd, d);
+    }
+    for (int i = lane; i < H; i += 32) {
+      const float a = fabsf(w2[(size_t)row * H + i]), c = fabsf(wa[(size_t)row * H + i]);
+      a2 += a; x2 = fmaxf(x2, a); aa += c; xa = fmaxf(xa, c);
+    }
+#pragma unroll
+    for (int m = 16; m; m >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, m); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, m));
+      ad += __shfl_xor_sync(0xffffffffu, ad, m); xd = fmaxf(xd, __shfl_xor_sync(0xffffffffu, xd, m));
+      a2 += __shfl_xor_sync(0xffffffffu, a2, m); x2 = fmaxf(x2, __shfl_xor_sync(0xffffffffu, x2, m));
+      aa += __shfl_xor_sync(0xffffffffu, aa, m); xa = fmaxf(xa, __shfl_xor_sync(0xffffffffu, xa, m));
+    }
+    if (lane == 0) {
+      srow[0][row] = a1; srow[1][row] = x1; srow[2][row] = ad; srow[3][row] = xd;
+      srow[4][row] = a2; srow[5][row] = x2; srow[6][row] = aa; srow[7][row] = xa;
+    }
   }
-  float r2 = 0.f, c2 = 0.f, m2 = 0.f, ra = 0.f, ca = 0.f, ma = 0.f, mp = 0.f;
-  for (int i = 0; i < H; ++i) {
-    if (P) mp = fmaxf(mp, fabsf(P[((size_t)bk * H + j) * H + i]));
-    const float x2 = fabsf(w2[(size_t)j * H + i]), y2 = fabsf(w2[(size_t)i * H + j]);
-    const float xa = fabsf(wa[(size_t)j * H + i]), ya = fabsf(wa[(size_t)i * H + j]);
-    r2 += x2; c2 += y2; m2 = fmaxf(m2, x2); ra += xa; ca += ya; ma = fmaxf(ma, xa);
+  // column-wise L1 norms: thread (part, j) walks down a quarter of column j (coalesced across the block)
+  float c2 = 0.f, ca = 0.f, mp = 0.f;
+  for (int i0 = part * 64; i0 < part * 64 + 64; i0 += 16) {          // 32 independent loads in flight per thread
+    float t2[16], ta[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { t2[u] = __ldg(w2 + (size_t)(i0 + u) * H + j); ta[u] = __ldg(wa + (size_t)(i0 + u) * H + j); }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) { c2 += fabsf(t2[u]); ca += fabsf(ta[u]); }
   }
+  scol[0][part][j] = c2; scol[1][part][j] = ca;
+  __syncthreads();
+  if (threadIdx.x >= H) return;                                      // (exited threads do not take part in later barriers)
+  c2 = (scol[0][0][j] + scol[0][1][j]) + (scol[0][2][j] + scol[0][3][j]);
+  ca = (scol[1][0][j] + scol[1][1][j]) + (scol[1][2][j] + scol[1][3][j]);
+  const float r1 = srow[0][j], m1 = srow[1][j], rd = srow[2][j], md = srow[3][j];
+  const float r2 = srow[4][j], m2 = srow[5][j], ra = srow[6][j], ma = srow[7][j];
+  if (P)
+    for (int i = 0; i < H; ++i) mp = fmaxf(mp, fabsf(P[((size_t)bk * H + j) * H + i]));
   const float l1W1 = block_max256(r1, red), M1 = block_max256(r1 + fabsf(b1[(size_t)bk * H + j]), red);
   const float l1W2 = block_max256(r2, red), l1Wd = block_max256(rd, red), l1Wa = block_max256(ra, red);
   const float cW2 = block_max256(c2, red), cWa = block_max256(ca, red);
@@ -2710,7 +2742,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     DPN_LAUNCH_OK();
   }
   if (F16) {                                                          // scaling plan before anything is converted to fp16
-    bounds_kernel<<<B * Kn, 256, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, Geo<PL>::FOLD ? c.P : nullptr, c.sc);
+    bounds_kernel<<<B * Kn, 1024, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, Geo<PL>::FOLD ? c.P : nullptr, c.sc);
     DPN_LAUNCH_OK();
     plan_kernel<<<1, 32, 0, st>>>(B, Kn, c.sc);
     DPN_LAUNCH_OK();
