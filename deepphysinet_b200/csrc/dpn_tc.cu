@@ -1,25 +1,32 @@
-// DPN_MODE_BF16: the hot path on the 5th-generation tensor cores (tcgen05.mma kind::f16, bf16 operands,
-// fp32 accumulators in TMEM), weights streamed through shared memory with cp.async.bulk (UBLKCP) on mbarriers.
+// The hot path on the 5th-generation tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM), weights streamed through
+// shared memory with cp.async.bulk (UBLKCP) on mbarriers.  Two kernel families live in this file:
+//
+//   * the SPLIT MODES (DPN_MODE_F16X3 - the default - and DPN_MODE_BF16X3): pass1_ts_kernel / pass2z_kernel / wgrad2_kernel.  Every
+//     operand - weight images, activation tiles, workspace tiles - is kept as TWO 16-bit planes, hi = rn16(v) and lo = rn16(v - hi)
+//     (22 / 16 mantissa bits together; fp16 tiles carry exact power-of-two scales), and a contraction issues three MMAs into the same
+//     fp32 accumulator: lo*hi + hi*lo + hi*hi (two where one operand is the exact 0 / 1 ReLU mask).  A operands live in TENSOR MEMORY:
+//     two 256-column regions used as ping-pong accumulators that the epilogues convert IN PLACE into the next A operand while the next
+//     GEMM already runs on the converted blocks.
+//   * DPN_MODE_BF16 (one bf16 plane): pass1_kernel / pass2_kernel / wgrad_kernel, the round-1 structure (activation tile in shared
+//     memory, MMA -> epilogue -> MMA in turn, 2 CTAs per SM).
 //
 // Executed algorithm, per tile of 128 query points and per coordinate net:
 //   pass 1  G1 a1 = PE W1^T            -> h1 = relu(a1+b1), mask m1
 //           G2 c  = h1 W2^T + PE6 Wd^T -> c + (b2+bd+e);  o += 2wo.c
-//           G3 a3 = c Wa^T             -> g = relu(a3+ba), o += u.g (u = Wb^T wo: out_fc folded through cat_fc1.fc.2)
-//           G4 y  = (u*m3) Wa + 2wo    reverse sweep of the scalar output: do/dc
+//           G3 a3 = c Wa^T             -> g = relu(a3+ba), o += u.g (u = Wb^T wo: out_fc folded through cat_fc1.fc.2), mask m3
+//           G4 y  = (u*m3) Wa + 2wo    reverse sweep of the scalar output: do/dc   (split modes: m3 (diag(u) Wa), the bare mask as operand)
 //           G5 q  = y W2, qm = q*m1    do/da1
 //           G6 jin = qm W1             do/dPE  -> do/dz_c = jin . dPE_c   (the 3 Jacobian columns)
 //   residual kernel (fp64, shared with the fp32 mode) -> loss terms + seeds dL/do, dL/d(do/dz_c)
-//   pass 2  ONE combined tangent row: xt = sum_c seed_c dPE_c;  G7 ht = (xt W1^T)*m1;  G8 ct = ht W2^T;  G9 gt = (ct Wa^T)*m3
-//           Z-side rows  zp = dov PE + xt, zh = dov h1 + ht, zc = dov c + ct, gz = dov g + gt, zd = dov PE6
+//   pass 2  bf16 mode: ONE combined tangent row xt = sum_c seed_c dPE_c;  G7 ht = (xt W1^T)*m1;  G8 ct = ht W2^T;  G9 gt = (ct Wa^T)*m3;
+//                      Z-side rows  zp = dov PE + xt, zh = dov h1 + ht, zc = dov c + ct, gz = dov g + gt, zd = dov PE6
+//           split modes: the same rows as the FORWARD pass of the combined row zp with frozen masks and dov-scaled biases (G7', G8');
+//                      gz is never formed - its column sum comes out of the dWa contraction
 //   wgrad   dW1 = qm^T zp, dW2 = y^T zh, dWa = (u*m3)^T zc, dWd = y^T zd  : K = points contractions, MN-major operands
 //   colsum  bias gradients and the two vectors the folded output layer needs (vc, vg)
 //
-// DPN_MODE_BF16X3 (template parameter PL = 2): every operand - weight images, activation tiles, workspace blobs - is kept
-// as TWO bf16 planes, hi = bf16(v) and lo = bf16(v - hi) (16 mantissa bits together), and every contraction issues three
-// MMAs into the same fp32 accumulator: lo*hi + hi*lo + hi*hi.  Same kernels, same pipeline, 1 CTA per SM.
-//
-// Every [128 x Kd] bf16 operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh, in shared memory and in
-// the workspace alike, so a tile written once by an epilogue is (a) the K-major A operand of the next GEMM and
+// Every [128 x Kd] 16-bit operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh in shared memory (and, 32 points at a
+// time, in the workspace), so a tile written once by an epilogue is (a) the K-major A operand of the next GEMM and
 // (b) an MN-major operand of the weight-gradient contraction, and moves with plain 1-D bulk copies.
 #include <math.h>
 #include <stdlib.h>
@@ -1740,7 +1747,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint4 m1q = __ldg(reinterpret_cast<const uint4*>(blob_mask<PL>(nt)) + r * 2 + half);
       const uint32_t m1w[4] = {m1q.x, m1q.y, m1q.z, m1q.w};
       // fp16 variant: every tile carries one power-of-two scale per (sample, net) (zscale_kernel); accumulators carry
-      // (A tile scale) x (weight image scale) and i7 / i8 / i9 undo that
+      // (A tile scale) x (weight image scale) and i7 / i8 undo that
       // zd exists twice: the stored tile (wgrad operand of dWd) with its own scale sZD, and the A operand of G8' whose scale is tied
       // to the accumulator it shares with zh W2^T: sZH sW2 = sZDa sWd, and plan_kernel made sH1 sW2 = S_PE sWd  =>  sZDa = sZH S_PE / sH1
       float sZP = 1.f, sZH = 1.f, sZC = 1.f, sZD = 1.f, sZDa = 1.f, sDV = 1.f, i7 = 1.f, i8 = 1.f;
