@@ -10,8 +10,8 @@ from .config import PhysicsConsts
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DPN_LIB_OVERRIDE") or os.path.join(_HERE, "_lib", "libdpn_b200.so")   # override: kernel experiments only
 
-MODE_FP32, MODE_BF16, MODE_BF16X3, MODE_F16X3 = 0, 1, 2, 3
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "bf16x3": MODE_BF16X3, "f16x3": MODE_F16X3}
+MODE_FP32, MODE_BF16, MODE_BF16X3, MODE_F16X3, MODE_F16X3A = 0, 1, 2, 3, 4
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "bf16x3": MODE_BF16X3, "f16x3": MODE_F16X3, "f16x3a": MODE_F16X3A}
 WEIGHT_FIELDS = ("W1", "b1", "W2", "b2", "e", "Wd", "bd", "Wa", "ba", "Wb", "bb", "wo", "bo")
 
 

@@ -29,7 +29,7 @@ static int f32_chunk(const DpnShape& s) {
   return c < s.N ? c : s.N;
 }
 
-static int planes(const DpnShape& s) { return (s.mode == DPN_MODE_BF16X3 || s.mode == DPN_MODE_F16X3) ? 2 : 1; }
+static int planes(const DpnShape& s) { return (s.mode == DPN_MODE_BF16X3 || s.mode == DPN_MODE_F16X3 || s.mode == DPN_MODE_F16X3A) ? 2 : 1; }
 
 static int tc_chunk(const DpnShape& s) {
   int c = s.chunk > 0 ? (s.chunk + 127) / 128 * 128 : tc::default_chunk(s.B, planes(s));
@@ -43,7 +43,7 @@ static int check_shape(const DpnShape* s) {
     set_error("bad shape B=%d N=%d K=%d (need B>0, N>0, 1<=K<=6)", s->B, s->N, s->K);
     return DPN_E_INVALID;
   }
-  if (s->mode < DPN_MODE_FP32 || s->mode > DPN_MODE_F16X3) {
+  if (s->mode < DPN_MODE_FP32 || s->mode > DPN_MODE_F16X3A) {
     set_error("unknown mode %d", s->mode);
     return DPN_E_INVALID;
   }

@@ -142,6 +142,7 @@ struct Work {
   float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
   const NetScales* sc;         // [B][Kn] scaling plan (fp16 variant only)
   long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (debug builds with DPN_PHASE_DEBUG=1), summed over CTAs
+  int xfirst;                  // split modes: cross-first accumulation of G1 - G3 (DPN_MODE_F16X3A)
   int dbg_flags;               // DEBUG BUILDS ONLY (tools/build_debug.sh, DPN_DEBUG_FLAGS): 1 = no MMAs, 2 = empty epilogues, 4 = no tile stores
   float band[NF];
 };
@@ -895,19 +896,27 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   const uint32_t tmem = pipe.tmem_base;
   const uint32_t rank = cluster_ctarank();
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CLUSTER) - 1);
+  // DPN_MODE_F16X3A: CROSS-FIRST accumulation of the three GEMMs that decide the ReLU masks (G1 -> m1; G2, G3 -> m3).  The tensor core adds every MMA
+  // into the fp32 accumulator with round-toward-zero at the accumulator's CURRENT magnitude, so the 2 x 16 cross-term MMAs of a split
+  // contraction cost as much accuracy as its 16 main-term MMAs when they are interleaved.  Issued FIRST - while the accumulator holds
+  // only the 2^-11-times-smaller cross sums - their truncations vanish, and a pre-activation carries 16 instead of 48 truncations:
+  // 4.6e-7 instead of 1.2e-6 rms relative error for K = 256 (a CUDA-core fp32 FMA chain: 2.9e-7).  The price is
+  // that the hi planes of these GEMMs' chunks are fetched twice and that their main terms cannot start under the running epilogue.
+  // Only when a Jacobian / backward pass follows (sweep > 0): the values themselves are continuous in the masks.
+  const bool xfirst = w.xfirst != 0 && sweep > 0;
 
   if (warp == Geo<PL>::W_PROD) {
     // ---------------- producer: weight chunks (multicast slices) + this tile's PE slices ----------------
     uint32_t s = 0, ph = 0;
     const uint64_t pol = l2_policy_evict_last();
-    auto put = [&](const uint8_t* wsrc, uint32_t wbytes, const uint8_t* asrc) {
-#ifdef DPN_EXP_HALFSTREAM
-      wbytes /= 2;                                     // TIMING EXPERIMENT ONLY (wrong results): half of every weight chunk is fetched
-#endif
+    // hi_only: the main-term phase of a cross-first GEMM needs only the hi plane of the chunk (first half) and of the A slice
+    auto put = [&](const uint8_t* wsrc, uint32_t wbytes, const uint8_t* asrc, const bool hi_only = false) {
+      if (hi_only) wbytes /= 2;
+      const int a_planes = hi_only ? 1 : PL;
       mbar_wait(&pipe.empty[s], ph ^ 1);
       if (elect_one()) {
         uint8_t* stg = ring + s * ts::STAGE;
-        mbar_arrive_expect_tx(&pipe.full[s], wbytes + (asrc ? 2 * ts::A_PLANE : 0));
+        mbar_arrive_expect_tx(&pipe.full[s], wbytes + (asrc ? a_planes * ts::A_PLANE : 0));
         if (CLUSTER == 1) {
           bulk_g2s_hint(stg, wsrc, wbytes, &pipe.full[s], pol);
         } else {
@@ -915,8 +924,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           bulk_g2s_mc_hint(stg + rank * slice, wsrc + rank * slice, slice, &pipe.full[s], MC_MASK, pol);
         }
         if (asrc) {
-#pragma unroll
-          for (int p = 0; p < PL; ++p) bulk_g2s_hint(stg + ts::W_BYTES + p * ts::A_PLANE, asrc + p * BLOB_C, ts::A_PLANE, &pipe.full[s], pol);
+          for (int p = 0; p < a_planes; ++p) bulk_g2s_hint(stg + ts::W_BYTES + p * ts::A_PLANE, asrc + p * BLOB_C, ts::A_PLANE, &pipe.full[s], pol);
         }
       }
       if (++s == ts::NS) { s = 0; ph ^= 1; }
@@ -928,11 +936,19 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
       const uint8_t *iW1 = gen, *iW1T = gen + PL * IMG_HC, *iW2 = gen + PL * 2 * IMG_HC, *iW2T = gen + PL * (2 * IMG_HC + IMG_HH);
       const uint8_t *iWd = sta, *iWa = sta + PL * IMG_HC, *iWaT = sta + PL * (IMG_HC + IMG_HH);
-      // the MMA warp's order: G1 | G2b (PE6 slices: no dependence on an epilogue, issued first) | TS-form GEMMs in block order
+      // the MMA warp's order: G1 | G2b (PE6 slices: no dependence on an epilogue, issued first) | TS-form GEMMs in block order.
+      // Cross-first GEMMs (G1 - G3 when masks matter, see the MMA warp) read every chunk twice: whole chunks for the cross terms,
+      // then the hi planes again for the main terms.
       for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe_src + (size_t)c * ts::A_PLANE);
+      if (xfirst) for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe_src + (size_t)c * ts::A_PLANE, true);
       for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE);
       for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
+      if (xfirst) {
+        for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE, true);
+        for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr, true);
+      }
       for (int i = 0; i < 16; ++i) put(iWa + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
+      if (xfirst) for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr, true);
       if (sweep) {
         for (int i = 0; i < 16; ++i) put(iWaT + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
         for (int i = 0; i < 16; ++i) put(iW2T + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
@@ -949,7 +965,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     const uint32_t ring_addr = smem_u32(ring);
     const uint64_t a_base = smem_desc(ring_addr + ts::W_BYTES, CORE_STRIDE, 128);
     // one K = 16 chunk: lo*hi + hi*lo + hi*hi into the accumulator at column d; A planes from tensor memory (a_hi) or from the stage
-    auto chunk = [&](const uint32_t d, const int Nn, const bool a_in_tmem, const uint32_t a_hi, const uint32_t first, const bool a_exact = false) {
+    // which of the products of a split contraction a chunk issues: all three | exact A operand (B_lo, B_hi) | the two cross terms | the main term
+    enum { P_ALL = 0, P_EXACT = 1, P_CROSS = 2, P_MAIN = 3 };
+    auto chunk = [&](const uint32_t d, const int Nn, const bool a_in_tmem, const uint32_t a_hi, const uint32_t first, const int part = P_ALL) {
       const uint32_t idesc = idesc_16(F16, Nn, 0, 0, 128);
       const uint64_t b_base = smem_desc(ring_addr, Nn * 16, 128);
       const uint32_t b_lo = (uint32_t)(Nn * 32) >> 4;
@@ -959,25 +977,33 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       if (elect_one()) {
         if (DPN_DBG(w, 1)) {                             // (debug builds: no MMAs, barrier protocol intact)
         } else if (a_in_tmem) {
-          if (!a_exact) mma_ts(d, a_hi + 16, bd, idesc, first);            // (an exact 16-bit A operand - the 0 / 1 mask of G4 - has no lo plane)
-          mma_ts(d, a_hi, bl, idesc, a_exact ? first : 1u);
-          mma_ts(d, a_hi, bd, idesc, 1u);
+          if (part == P_ALL || part == P_CROSS) mma_ts(d, a_hi + 16, bd, idesc, first);   // (an exact 16-bit A operand - the 0 / 1 mask of G4 - has no lo plane)
+          if (part != P_MAIN) mma_ts(d, a_hi, bl, idesc, part == P_EXACT ? first : 1u);
+          if (part != P_CROSS) mma_ts(d, a_hi, bd, idesc, part == P_MAIN ? first : 1u);
         } else {                                         // the A slice of this chunk sits behind the weights in the same stage
           const uint64_t ad = a_base + s * (uint32_t)(ts::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
-          mma_bf16(d, al, bd, idesc, first);
-          mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
-          mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
+          if (part == P_MAIN) {
+            mma_bf16(d, ad, bd, idesc, first);
+          } else {
+            mma_bf16(d, al, bd, idesc, first);
+            if (part == P_CROSS) {
+              mma_bf16(d, ad, bl, idesc, 1u);
+            } else {
+              mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
+              mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
+            }
+          }
         }
         if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
       }
       if (++s == ts::NS) { s = 0; ph ^= 1; }
     };
     // G over the PE / PE6 slices of the ring into region `cur`
-    auto gemm_ss = [&](const int nchunks) {
-      for (int c = 0; c < nchunks; ++c) chunk(tmem + cur * ts::REGION, H, false, 0u, c > 0 ? 1u : 0u);
+    auto gemm_ss = [&](const int nchunks, const int part = P_ALL, const bool accumulate = false) {
+      for (int c = 0; c < nchunks; ++c) chunk(tmem + cur * ts::REGION, H, false, 0u, (accumulate || c > 0) ? 1u : 0u, part);
     };
     // G whose A operand is the other region, converted in place by the running epilogue: block by block
-    auto gemm_ts = [&](const int Nn, const bool accumulate, const bool a_exact = false) {
+    auto gemm_ts = [&](const int Nn, const bool accumulate, const int part = P_ALL) {
       const uint32_t d = tmem + cur * ts::REGION, a = tmem + (cur ^ 1u) * ts::REGION;
       for (int cb = 0; cb < 4; ++cb) {
         if (timed) mbar_wait_t(&pipe.blk[cb], bp, t_epi); else mbar_wait(&pipe.blk[cb], bp);
@@ -985,22 +1011,33 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = 2 * cb + (j & 1) + (j >> 1) * 8;
-          chunk(d, Nn, true, a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1), (accumulate || cb > 0 || j > 0) ? 1u : 0u, a_exact);
+          chunk(d, Nn, true, a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1), (accumulate || cb > 0 || j > 0) ? 1u : 0u, part);
         }
       }
       bp ^= 1u;
     };
+    // main terms of a cross-first K = 256 GEMM: every block of the A operand has arrived (its cross terms are in), natural chunk order
+    auto gemm_ts_main = [&]() {
+      const uint32_t d = tmem + cur * ts::REGION, a = tmem + (cur ^ 1u) * ts::REGION;
+      for (int c = 0; c < 16; ++c) chunk(d, H, true, a + 32u * (uint32_t)(c >> 1) + 8u * (uint32_t)(c & 1), 1u, P_MAIN);
+    };
     auto ready = [&]() { if (elect_one()) mma_commit(&pipe.acc_ready[cur]); cur ^= 1u; };
     for (int k = 0; k < w.Kn; ++k) {
-      gemm_ss(12); ready();                                                // G1 (A = PE slices); its region was the A operand of the previous GEMM
+      if (xfirst) { gemm_ss(12, P_CROSS); gemm_ss(12, P_MAIN, true); } else gemm_ss(12);
+      ready();                                                             // G1 (A = PE slices); its region was the A operand of the previous GEMM
       if (k > 0) {                                                         // the last epilogue of the previous net has drained this region
         if (timed) mbar_wait_t(&pipe.drained, dr & 1, t_epi); else mbar_wait(&pipe.drained, dr & 1);
         ++dr; tc_fence_after();
       }
-      gemm_ss(12); gemm_ts(H, true); ready();                              // G2b (A = PE6 slices) + G2a (A = h1)
-      gemm_ts(H, false); ready();                                          // G3 (A = c)
+      if (xfirst) {                                                        // G2b (A = PE6 slices) + G2a (A = h1): all cross terms, then all main terms
+        gemm_ss(12, P_CROSS); gemm_ts(H, true, P_CROSS); gemm_ss(12, P_MAIN, true); gemm_ts_main(); ready();
+      } else {
+        gemm_ss(12); gemm_ts(H, true); ready();
+      }
+      if (xfirst) { gemm_ts(H, false, P_CROSS); gemm_ts_main(); } else gemm_ts(H, false);
+      ready();                                                             // G3 (A = c)
       if (sweep) {
-        gemm_ts(H, false, true); ready();                                  // G4 (A = the m3 mask, B = diag(u) Wa: two MMAs per chunk)
+        gemm_ts(H, false, P_EXACT); ready();                               // G4 (A = the m3 mask, B = diag(u) Wa: two MMAs per chunk)
         gemm_ts(H, false); ready();                                        // G5 (A = y)
         if (sweep > 1) { gemm_ts(C, false); ready(); }                     // G6 (A = qm, N = 192)
       }
@@ -2788,6 +2825,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
     w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
     w.sc = c.sc;
+    w.xfirst = J.shape.mode == DPN_MODE_F16X3A ? 1 : 0;
     w.phase_dbg = phase_debug ? c.dbg : nullptr;
 #ifdef DPN_DEBUG_BUILD
     w.dbg_flags = getenv("DPN_DEBUG_FLAGS") ? atoi(getenv("DPN_DEBUG_FLAGS")) : 0;
@@ -2889,7 +2927,7 @@ static int run_planes(const Job& J, cudaStream_t st) {
 int run(const Job& J, cudaStream_t st) {
   // (a single scaled fp16 plane - run_planes<1, true> - was measured too: 12.1 ms per call against 10.8 ms for bf16, Jacobian /
   //  gradient errors 1e-2..3e-2 against 5e-2: ReLU-mask flips dominate both, not worth a fifth mode)
-  if (J.shape.mode == DPN_MODE_F16X3) return run_planes<2, true>(J, st);
+  if (J.shape.mode == DPN_MODE_F16X3 || J.shape.mode == DPN_MODE_F16X3A) return run_planes<2, true>(J, st);
   if (J.shape.mode == DPN_MODE_BF16X3) return run_planes<2, false>(J, st);
   return run_planes<1, false>(J, st);
 }

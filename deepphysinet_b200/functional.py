@@ -202,6 +202,7 @@ _DEFAULT_MODE = "f16x3"
 def set_default_mode(mode: str):
     """Arithmetic of the dense contractions (include/dpn_b200.h):
     'f16x3'  tcgen05, scaled fp16 hi+lo operands, 3 MMAs per contraction - fp32-class accuracy (default)
+    'f16x3a' the same with cross-first accumulation of the mask-deciding GEMMs: 2.6x smaller pre-activation error, 6 % slower
     'bf16x3' tcgen05, bf16 hi+lo operands - ~1e-3 class          'bf16' tcgen05, plain bf16 - fastest, ~5e-2 class
     'fp32'   CUDA-core FMA - the reference arithmetic, slowest."""
     global _DEFAULT_MODE

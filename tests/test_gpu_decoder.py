@@ -24,7 +24,7 @@ def _oracle_values(W, pts, consts):
     return torch.stack(outs), leaves
 
 
-@pytest.mark.parametrize("mode,tol_v,tol_g", [("fp32", 1e-4, 1e-4), ("f16x3", 1e-5, 1e-4), ("bf16x3", 1e-5, 2e-3), ("bf16", 2e-2, 5e-2)])
+@pytest.mark.parametrize("mode,tol_v,tol_g", [("fp32", 1e-4, 1e-4), ("f16x3", 1e-5, 1e-4), ("f16x3a", 1e-5, 1e-4), ("bf16x3", 1e-5, 2e-3), ("bf16", 2e-2, 5e-2)])
 def test_decoder_values_and_backward_from_xyz(mode, tol_v, tol_g):
     from deepphysinet_b200 import functional as Fn, testing as T
     from deepphysinet_b200.config import PhysicsConsts
