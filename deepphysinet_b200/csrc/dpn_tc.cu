@@ -869,7 +869,7 @@ static_assert(2 * REGION == 512 && REGION == H, "TMEM map: two [128 x 256] fp32 
 __host__ __device__ constexpr int block_order(int i) { return ((i >> 2) << 1) + (i & 1) + ((i >> 1) & 1) * 8; }
 }  // namespace ts
 
-template <bool F16>
+template <bool F16, bool XF>                     // XF: cross-first accumulation of G1 - G3 (DPN_MODE_F16X3A)
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREADS, 1) pass1_ts_kernel(const Work w, const int sweep) {
   constexpr int PL = 2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -903,7 +903,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   // 4.6e-7 instead of 1.2e-6 rms relative error for K = 256 (a CUDA-core fp32 FMA chain: 2.9e-7).  The price is
   // that the hi planes of these GEMMs' chunks are fetched twice and that their main terms cannot start under the running epilogue.
   // Only when a Jacobian / backward pass follows (sweep > 0): the values themselves are continuous in the masks.
-  const bool xfirst = w.xfirst != 0 && sweep > 0;
+  const bool xfirst = XF && sweep > 0;
 
   if (warp == Geo<PL>::W_PROD) {
     // ---------------- producer: weight chunks (multicast slices) + this tile's PE slices ----------------
@@ -2753,7 +2753,8 @@ static int run_planes(const Job& J, cudaStream_t st) {
     DPN_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
       if constexpr (PL == 2) {
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
+        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
         DPN_CUDA_OK(cudaFuncSetAttribute(pass2z_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2z::SMEM));
         DPN_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM));
       } else {
@@ -2835,7 +2836,8 @@ static int run_planes(const Job& J, cudaStream_t st) {
     encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t, J.pts->coord_pe);
     DPN_LAUNCH_OK();
     if constexpr (PL == 2) {                      // split modes: the A operand lives in tensor memory
-      pass1_ts_kernel<F16><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
+      if (w.xfirst) pass1_ts_kernel<F16, true><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
+      else pass1_ts_kernel<F16, false><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
     } else {
       pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
     }
