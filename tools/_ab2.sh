@@ -1,4 +1,5 @@
 #!/bin/bash
+# in-situ kernel times of the in-tree library and of variant builds:  VARIANTS="tools/bin/a.so ..." bash tools/_ab2.sh <tag>
 cd "$(dirname "$0")/.."
 for lib in "" $VARIANTS; do
   echo "== library: ${lib:-in-tree}"

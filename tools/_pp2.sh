@@ -1,4 +1,5 @@
 #!/bin/bash
+# cycle counters of pass 1 / pass 2 from the debug build (tools/build_debug.sh):  bash tools/_pp2.sh <tag>
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 T=${1:-phase}
