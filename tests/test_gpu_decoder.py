@@ -176,3 +176,22 @@ def test_pre_encoded_surface_honours_mode(K):
     assert H.rel(got["f16x3"], got["fp32"]) < 2e-5
     assert not torch.equal(got["f16x3"], got["fp32"])              # different arithmetic actually ran
     assert launches["fp32"] != launches["f16x3"], launches         # CUDA-core kernel sequence vs tcgen05 kernel sequence
+
+
+def test_cross_first_mode_only_changes_the_masked_paths():
+    """DPN_MODE_F16X3A re-orders the accumulation of G1 - G3 only when a Jacobian / backward pass follows (the values are continuous
+    in the ReLU masks): the values-only forward is bit-identical to f16x3, the PDE call is not - and closer to the oracle in values."""
+    from deepphysinet_b200 import functional as Fn, testing as T
+    W, pts = T.random_decoder_weights(B=2, N=700, seed=23, device="cuda")
+    xyz = (pts["x"], pts["y"], pts["t"])
+    o1 = Fn.decoder_values(None, pts["coord_data"], W, xyz=xyz, mode="f16x3")
+    o2 = Fn.decoder_values(None, pts["coord_data"], W, xyz=xyz, mode="f16x3a")
+    assert torch.equal(o1, o2)
+    ref = T.oracle_reference(W, pts)
+    a = T.run_library(W, pts, mode="f16x3")
+    b = T.run_library(W, pts, mode="f16x3a")
+    assert not torch.equal(a["vals"], b["vals"])
+    ea = max(T._rel(a["vals"][..., k], ref["vals"][..., k]) for k in range(6))
+    eb = max(T._rel(b["vals"][..., k], ref["vals"][..., k]) for k in range(6))
+    print("values vs fp64 oracle: f16x3 %.2e, f16x3a %.2e" % (ea, eb))
+    assert eb < 3e-7 and eb < ea
