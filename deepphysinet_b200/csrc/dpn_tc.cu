@@ -1,28 +1,28 @@
 // The hot path on the 5th-generation tensor cores (tcgen05.mma kind::f16, fp32 accumulators in TMEM), weights streamed through
-// shared memory with cp.async.bulk (UBLKCP) on mbarriers.  Two kernel families live in this file:
+// shared memory with cp.async.bulk (UBLKCP) on mbarriers: pass1_ts_kernel / pass2z_kernel / wgrad2_kernel, templated on the number
+// of operand planes PL.
 //
-//   * the SPLIT MODES (DPN_MODE_F16X3 - the default - and DPN_MODE_BF16X3): pass1_ts_kernel / pass2z_kernel / wgrad2_kernel.  Every
-//     operand - weight images, activation tiles, workspace tiles - is kept as TWO 16-bit planes, hi = rn16(v) and lo = rn16(v - hi)
-//     (22 / 16 mantissa bits together; fp16 tiles carry exact power-of-two scales), and a contraction issues three MMAs into the same
-//     fp32 accumulator: lo*hi + hi*lo + hi*hi (two where one operand is the exact 0 / 1 ReLU mask).  A operands live in TENSOR MEMORY:
-//     two 256-column regions used as ping-pong accumulators that the epilogues convert IN PLACE into the next A operand while the next
-//     GEMM already runs on the converted blocks.
-//   * DPN_MODE_BF16 (one bf16 plane): pass1_kernel / pass2_kernel / wgrad_kernel, the round-1 structure (activation tile in shared
-//     memory, MMA -> epilogue -> MMA in turn, 2 CTAs per SM).
+//   * PL = 2, the SPLIT MODES (DPN_MODE_F16X3 - the default -, DPN_MODE_F16X3A, DPN_MODE_BF16X3): every operand - weight images,
+//     activation tiles, workspace tiles - is kept as TWO 16-bit planes, hi = rn16(v) and lo = rn16(v - hi) (22 / 16 mantissa bits
+//     together; fp16 tiles carry exact power-of-two scales), and a contraction issues three MMAs into the same fp32 accumulator:
+//     lo*hi + hi*lo + hi*hi (two where one operand is the exact 0 / 1 ReLU mask).
+//   * PL = 1, DPN_MODE_BF16: one bf16 plane, one MMA per contraction.
+//
+// A operands live in TENSOR MEMORY: two 256-column regions used as ping-pong accumulators that the epilogues convert IN PLACE into the
+// next A operand while the next GEMM already runs on the converted blocks.
 //
 // Executed algorithm, per tile of 128 query points and per coordinate net:
 //   pass 1  G1 a1 = PE W1^T            -> h1 = relu(a1+b1), mask m1
 //           G2 c  = h1 W2^T + PE6 Wd^T -> c + (b2+bd+e);  o += 2wo.c
 //           G3 a3 = c Wa^T             -> g = relu(a3+ba), o += u.g (u = Wb^T wo: out_fc folded through cat_fc1.fc.2), mask m3
-//           G4 y  = (u*m3) Wa + 2wo    reverse sweep of the scalar output: do/dc   (split modes: m3 (diag(u) Wa), the bare mask as operand)
+//           G4 y  = (u*m3) Wa + 2wo = m3 (diag(u) Wa) + 2wo    reverse sweep of the scalar output: do/dc   (the bare mask is the A operand)
 //           G5 q  = y W2, qm = q*m1    do/da1
 //           G6 jin = qm W1             do/dPE  -> do/dz_c = jin . dPE_c   (the 3 Jacobian columns)
 //   residual kernel (fp64, shared with the fp32 mode) -> loss terms + seeds dL/do, dL/d(do/dz_c)
-//   pass 2  bf16 mode: ONE combined tangent row xt = sum_c seed_c dPE_c;  G7 ht = (xt W1^T)*m1;  G8 ct = ht W2^T;  G9 gt = (ct Wa^T)*m3;
-//                      Z-side rows  zp = dov PE + xt, zh = dov h1 + ht, zc = dov c + ct, gz = dov g + gt, zd = dov PE6
-//           split modes: the same rows as the FORWARD pass of the combined row zp with frozen masks and dov-scaled biases (G7', G8');
-//                      gz is never formed - its column sum comes out of the dWa contraction
-//   wgrad   dW1 = qm^T zp, dW2 = y^T zh, dWa = (u*m3)^T zc, dWd = y^T zd  : K = points contractions, MN-major operands
+//   pass 2  the Z-side rows  zp = dov PE + sum_c seed_c dPE_c, zd = dov PE6, zh = dov h1 + ht, zc = dov c + ct  as the FORWARD pass of the
+//           combined row zp with frozen masks and dov-scaled biases (G7', G8'); gz = dov g + gt is never formed - its column sum
+//           comes out of the dWa contraction
+//   wgrad   dW1 = qm^T zp, dW2 = y^T zh, dWa = diag(u) (m3^T zc), dWd = y^T zd  : K = points contractions, MN-major operands
 //   colsum  bias gradients and the two vectors the folded output layer needs (vc, vg)
 //
 // Every [128 x Kd] 16-bit operand tile ("blob") is stored in the layout (*) of dpn_umma.cuh in shared memory (and, 32 points at a
@@ -46,68 +46,42 @@ constexpr int BLOB_H = TP * H * 2;            // 65536  [128 x 256] bf16
 constexpr int BLOB_C = TP * C * 2;            // 49152  [128 x 192] bf16
 constexpr int CORE_STRIDE = TP * 16;          // 2048   bytes between k-cores of a 128-row blob
 constexpr int STAGE_BYTES = 8192;             // one K=16 chunk (= one MMA) of a [256 x K] weight image
-// CTA pair (cta_group::2, build with -DDPN_PAIR=1): the two CTAs of a cluster run ONE M = 256 MMA; each CTA stages only ITS half
-// of every weight chunk (N/2 rows), which halves the shared-memory ingress per SM and doubles the ring depth.  Parity-green in all
-// modes and the pair MMA itself runs at 128 cycles per TWO tiles (tools/umma2_probe.cu; 128.6 per tile for cta_group::1, tools/umma_sw_probe.cu), but the
-// leader has to wait for the slower of two epilogues every round: measured f16x3 25.0 vs 24.3 ms, bf16 11.4 vs 10.9 ms per call.
-// Default 0 = cta_group::1, full chunks multicast to both CTAs.  The pair path pays off only with two tiles in flight per CTA.
-#ifndef DPN_PAIR
-#define DPN_PAIR 0
-#endif
-constexpr bool PAIR = DPN_PAIR != 0;
 #ifndef DPN_REUSE_A
 #define DPN_REUSE_A 1
 #endif
-constexpr bool REUSE_A = DPN_REUSE_A != 0;               // split modes: consecutive MMAs on the same A tile share one shared-memory fetch
-#ifndef DPN_NSTAGE
-#define DPN_NSTAGE (DPN_PAIR ? 10 : 5)
-#endif
-constexpr int NSTAGE = DPN_NSTAGE;                       // ring depth (>= 4: the producer streams four chunks ahead of an activation tile)
+constexpr bool REUSE_A = DPN_REUSE_A != 0;               // consecutive MMAs on the same shared-memory A tile share one fetch (A collector)
 #ifndef DPN_CLUSTER
 #define DPN_CLUSTER 2
 #endif
 constexpr int CLUSTER = DPN_CLUSTER;                     // CTAs (tiles of the same sample) sharing every weight chunk through one multicast L2 read
-constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] bf16 seed tile: col 0/1 = hi/lo halves of dov
+constexpr int AUX_BYTES = TP * 16 * 2;        // 4096   [128 x 16] 16-bit seed tile: col 0/1/2 = the three 16-bit terms of dov
 constexpr int IMG_HC = H * C * 2;             // 98304
 constexpr int IMG_HH = H * H * 2;             // 131072
-constexpr int GEN_IMG = 2 * IMG_HC + 4 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T, P, PT  (P = Wa W2, see FOLD below)
-constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, WaT
-// Workspace tile of one (net, point tile).  bf16 mode: H1 CC GG UM YT QM ZH ZC | ZP ZD | AUX.  Split modes: YT QM ZH ZC | ZP ZD | AUX |
-// MASK - pass 2 runs as the forward pass of the combined row and needs only the two ReLU masks of pass 1
-// (2 x 256 bits per point) instead of the h1 / c / g tiles (3 x 1 KB per point), and the weight-gradient kernel rebuilds its
-// J operand um = u [a3 > 0] from the same mask bits instead of reading a stored tile.
-constexpr int NBLOB_H = 8, NBLOB_C = 2;
-enum { B_H1 = 0, B_CC, B_GG, B_UM, B_YT, B_QM, B_ZH, B_ZC };
+constexpr int GEN_IMG = 2 * IMG_HC + 2 * IMG_HH;   // per (sample, net): W1, W1T, W2, W2T
+constexpr int STA_IMG = IMG_HC + 2 * IMG_HH;       // per net: Wd, Wa, (diag(u) Wa)^T
+// Workspace tile of one (net, point tile):  YT QM ZH ZC | ZP ZD | AUX | MASK.  Pass 2 runs as the forward pass of the combined row
+//  and needs only the ReLU mask m1 of pass 1 (256 bits per point) instead of the h1 / c / g tiles (3 x 1 KB per
+// point), and the weight-gradient kernel builds its J operand [a3 > 0] from the m3 mask bits instead of reading a stored tile.
+constexpr int NBLOB_H = 4, NBLOB_C = 2;
+enum { B_YT = 0, B_QM, B_ZH, B_ZC };
 constexpr int MASK_BYTES = 2 * TP * 32;       // [m1 | m3][128 rows][8 words]
 
-// Sizes that depend on the number of operand planes PL (1: bf16, 2: bf16 hi + lo).  Planes of one tile are contiguous,
-// in shared memory and in the workspace alike, so a tile still moves with one bulk copy.
+// Sizes that depend on the number of operand planes PL (1: bf16; 2: hi + lo, bf16 or scaled fp16).  Planes of one tile are
+// contiguous, in shared memory and in the workspace alike.
 template <int PL>
 struct Geo {
-  static constexpr int STAGE = STAGE_BYTES * PL / (PAIR ? 2 : 1);   // ring stage: [hi chunk | lo chunk] (PAIR: this CTA's half of the rows)
-  static constexpr int ACT = BLOB_H * PL;                        // activation buffer: plane p at p * BLOB_H
-  static constexpr int BH = BLOB_H * PL, BC = BLOB_C * PL;       // workspace blobs: plane p at p * BLOB_H (p * BLOB_C)
+  static constexpr int BH = BLOB_H * PL, BC = BLOB_C * PL;       // workspace tiles: plane p at p * BLOB_H (p * BLOB_C)
   static constexpr int GEN = GEN_IMG * PL, STA = STA_IMG * PL;
-  static constexpr int NBH = PL == 2 ? 4 : NBLOB_H;              // [128 x 256] tiles kept per (net, tile)
-  static constexpr size_t NET_TILE = (size_t)NBH * BH + (size_t)NBLOB_C * BC + AUX_BYTES + (PL == 2 ? MASK_BYTES : 0);
-  static constexpr int CTAS_PER_SM = PL == 1 ? 2 : 1;
-  // FOLD (one CTA per SM, all 512 TMEM columns): two GEMMs that share their A operand run back to back into TWO accumulators and
-  // share ONE epilogue round.  Pass 1: y = um Wa (G4) and q = um (Wa W2) + 2wo W2 (G5 with the pre-multiplied P = Wa W2) both read
-  // the um tile; pass 2: ct = ht W2^T (G8) and gt = ht P^T (G9) both read the ht tile.  Same result, one MMA -> epilogue -> MMA
-  // serialisation less per net in each pass.
-  static constexpr bool FOLD = false;    // (round 1 used it for the shared-memory variants of the split modes; they are gone: TMEM is full in the TS form)
-  static constexpr int TMEM_COLS = FOLD ? 512 : 256;
-  // Epilogue warps: warps w, w+4, w+8, ... share the TMEM lanes 32 (w % 4) .. +31 and split the 256 columns into NQ groups.
-  // 8 warps everywhere: 16 warps (column quarters) were measured for the one-CTA-per-SM split modes and LOSE 11 % - the 96-register
-  // budget of 576 threads spills in the pass-2 epilogues (f16x3 call 24.3 -> 27.0 ms); the code below stays generic in EW.
+  static constexpr size_t NET_TILE = (size_t)NBLOB_H * BH + (size_t)NBLOB_C * BC + AUX_BYTES + MASK_BYTES;
+  // Epilogue warps: warps w and w + 4 share the TMEM lanes 32 (w % 4) .. +31 and split the 256 columns.  8 warps: 16 (column
+  // quarters, 113 registers) and 12 (blocks split 3 / 3 / 2, pass 2) were measured and lose.
   static constexpr int EW = 8;
   static constexpr int ET = EW * 32;                             // epilogue threads
-  static constexpr int NQ = EW / 4;                              // column groups
-  static constexpr int NB = 8 / NQ;                              // 32-column blocks per thread
+  static constexpr int NB = 4;                                   // 32-column blocks per thread
   static constexpr int W_PROD = EW, W_MMA = EW + 1;              // producer / MMA-issuer warps
   static constexpr int THREADS = ET + 64;
 };
-enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, V_C2, NVEC };   // epilogue vectors staged in shared memory per net
+enum { V_B1 = 0, V_BSUM, V_BA, V_U, V_WO2, V_C2, NVEC };   // epilogue vectors staged in shared memory per net (pass 1)
 
 struct NetScales;
 
@@ -130,7 +104,6 @@ struct Work {
   // epilogue vectors (fp32)
   const float *b1, *bsum;  // [B][Kn][H]
   const float *ba, *uvec, *wo2, *cst;   // [Kn][H], cst [Kn]
-  const float* c2;         // [B][Kn][H]  2wo W2 (FOLD)
   // per-point
   const float* coord_data; // [B*N][6]
   const float* ref;        // [B*N][Kn] residual skip, or nullptr -> coord_data[:, k]
@@ -139,10 +112,10 @@ struct Work {
   float* pet;              // [B*T][C][TP] fp32 transposed coordinate features
   uint8_t* blobs;          // [B][Kn][T][NET_TILE_BYTES]
   float *o, *od, *dov, *dod;   // [B*T*TP][Kn], [..][Kn][3]
-  float *vc, *vg, *sm3, *sdo;  // [Kn][H] column sums (zc, gz, dov*m3) and [Kn] sum of dov
+  float *vc, *vg, *sdo;        // [Kn][H] column sums of zc / of the never-formed gz, and [Kn] sum of dov
   const NetScales* sc;         // [B][Kn] scaling plan (fp16 variant only)
   long long* phase_dbg;        // optional [kernel(2)][8] cycle counters (debug builds with DPN_PHASE_DEBUG=1), summed over CTAs
-  int xfirst;                  // split modes: cross-first accumulation of G1 - G3 (DPN_MODE_F16X3A)
+  int xfirst;                  // cross-first accumulation of G1 - G3 (DPN_MODE_F16X3A)
   int dbg_flags;               // DEBUG BUILDS ONLY (tools/build_debug.sh, DPN_DEBUG_FLAGS): 1 = no MMAs, 2 = empty epilogues, 4 = no tile stores
   float band[NF];
 };
@@ -151,8 +124,8 @@ template <int PL>
 __device__ __forceinline__ uint8_t* net_tile(const Work& w, int b, int k, int tl) {
   return w.blobs + (((size_t)b * w.Kn + k) * w.T + tl) * Geo<PL>::NET_TILE;
 }
-template <int PL> __host__ __device__ constexpr size_t off_h(int which) { return (size_t)(which - (PL == 2 ? (int)B_YT : 0)) * Geo<PL>::BH; }
-template <int PL> __host__ __device__ constexpr size_t off_zp() { return (size_t)Geo<PL>::NBH * Geo<PL>::BH; }
+template <int PL> __host__ __device__ constexpr size_t off_h(int which) { return (size_t)which * Geo<PL>::BH; }
+template <int PL> __host__ __device__ constexpr size_t off_zp() { return (size_t)NBLOB_H * Geo<PL>::BH; }
 template <int PL> __host__ __device__ constexpr size_t off_zd() { return off_zp<PL>() + Geo<PL>::BC; }
 template <int PL> __host__ __device__ constexpr size_t off_aux() { return off_zp<PL>() + 2 * Geo<PL>::BC; }
 template <int PL> __host__ __device__ constexpr size_t off_mask() { return off_aux<PL>() + AUX_BYTES; }
@@ -243,8 +216,8 @@ __device__ __forceinline__ void stg8(uint8_t* tile, uint32_t plane, uint32_t off
 // overflow whatever the weights are; the 30 binades of fp16 below the bound absorb the looseness of the bounds.
 // ------------------------------------------------------------------------------------------------
 struct NetScales {                       // one per (sample, net)
-  float sW1, sW2, sWd, sWa, sP;          // weight images (a matrix and its transpose share the factor); P = Wa W2
-  float sWaU;                            // split modes: the image of diag(u) Wa (B operand of G4, whose A operand is the bare m3 mask)
+  float sW1, sW2, sWd, sWa;              // weight images (a matrix and its transpose share the factor)
+  float sWaU;                            // the image of diag(u) Wa (B operand of G4, whose A operand is the bare m3 mask)
   float sH1, sC, sG, sUM, sY, sQ;        // tiles written by pass 1: h1, c, g, u*m3, y, q*m1
   float M1, Mc, l1W1, l1W12;             // bounds of |h1|, |c|; L1(W1), L1(W1) L1(W2)
   float rowB;                            // max(1, L1(W1), L1(W1) L1(W2)): growth of the pass-2 tangent row over its chain
@@ -272,123 +245,12 @@ __device__ __forceinline__ uint32_t piece_off(int r, int kc) { return (uint32_t)
 __device__ __forceinline__ uint32_t gp_off(const int KC, const int r, const int kc) {
   return (uint32_t)(r >> 5) * (uint32_t)(KC * 512) + (uint32_t)kc * 512u + (uint32_t)(r & 31) * 16u;
 }
-template <int PL>
-__device__ __forceinline__ uint32_t blob_off(const int KC, const int r, const int kc) { return PL == 2 ? gp_off(KC, r, kc) : piece_off(r, kc); }
-
-struct Pipe {            // shared-memory barriers of the fused kernels
-  uint64_t full[NSTAGE], empty[NSTAGE];
-  uint64_t a_bulk, a_epi, acc_ready, act_free;
-  uint64_t peer_full[NSTAGE], peer_epi, peer_bulk;   // leader only: mirrors of the peer CTA's full / a_epi / a_bulk (remote arrives)
-  uint64_t st_done;        // the bulk store that drains the activation tile has finished reading it
-  uint32_t tmem_base;
-};
 
 __device__ __forceinline__ void mbar_wait_t(uint64_t* bar, uint32_t parity, long long& acc) {
   const long long t0 = clock64();
   mbar_wait(bar, parity);
   acc += clock64() - t0;
 }
-
-// Producer side of the weight ring.  The WHOLE warp runs the loop (uniform control flow, see dpn_umma.cuh:elect_one); one elected
-// lane issues the copies.
-template <int PL>
-struct Producer {
-  Pipe* pp; uint8_t* ring; uint32_t rank; uint32_t s = 0, ph = 0;
-  uint64_t pol = l2_policy_evict_last();       // weight images: re-read by every tile of the sample, keep them in L2
-  __device__ __forceinline__ void put(const uint8_t* src, uint32_t bytes) {
-    mbar_wait(&pp->empty[s], ph ^ 1);                // every consumer (PAIR: the pair MMA; else every CTA of the cluster) is done with the previous occupant
-    if (elect_one()) {
-      if (PAIR) {                                      // my half of the rows of this chunk (the image stores the halves back to back)
-        mbar_arrive_expect_tx(&pp->full[s], bytes / 2);
-        bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src + rank * (bytes / 2), bytes / 2, &pp->full[s], pol);
-      } else {
-        mbar_arrive_expect_tx(&pp->full[s], bytes);    // my copy of the chunk: my slice + the slices my peers multicast to me
-        if (CLUSTER == 1) {
-          bulk_g2s_hint(ring + s * Geo<PL>::STAGE, src, bytes, &pp->full[s], pol);
-        } else {
-          const uint32_t slice = bytes / CLUSTER;
-          bulk_g2s_mc_hint(ring + s * Geo<PL>::STAGE + rank * slice, src + rank * slice, slice, &pp->full[s], (uint16_t)((1u << CLUSTER) - 1), pol);
-        }
-      }
-    }
-    if (++s == NSTAGE) { s = 0; ph ^= 1; }
-  }
-  // chunks [first, last) of a weight image whose K = 16 chunks are `bytes` per plane
-  __device__ __forceinline__ void stream(const uint8_t* img, int first, int last, uint32_t bytes) {
-    for (int i = first; i < last; ++i) put(img + (size_t)i * bytes * PL, bytes * PL);
-  }
-};
-
-// MMA side: the whole warp runs the loop, one elected lane issues.  A = the activation buffer (K-major, 128 rows), B = ring stages
-// (K-major).  Descriptors are built once per GEMM; a chunk only adds its byte offset (>> 4) to the 14-bit address field.
-// PAIR: the leader CTA issues M = 256 MMAs for both tiles once BOTH CTAs' operands are in place; the peer CTA runs the same
-// sequence but, instead of issuing, forwards each of its local completions (weight stage landed, epilogue done, A tile landed)
-// to the leader's mirror barrier with a remote arrive.  Completions come back to both CTAs through multicast commits.
-template <int PL, bool F16 = false>
-struct Issuer {
-  Pipe* pp; uint32_t act_addr, ring_addr, tmem; uint32_t rank; bool timed;
-  uint32_t s = 0, ph = 0; long long t_full = 0;
-  __device__ __forceinline__ bool leader() const { return !PAIR || rank == 0; }
-  __device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity, long long& t) {
-    if (timed) mbar_wait_t(bar, parity, t); else mbar_wait(bar, parity);
-  }
-  __device__ __forceinline__ void sync_local(uint64_t* local, uint64_t* mirror, uint32_t parity, long long& t) {
-    wait(local, parity, t);
-    if (PAIR) {
-      if (rank == 0) { const long long t0 = clock64(); mbar_wait_cluster(mirror, parity); t += clock64() - t0; }
-      else if (elect_one()) mbar_arrive_remote(mirror, 0);
-    }
-    tc_fence_after();
-  }
-  __device__ __forceinline__ void wait_epi(uint32_t& ae, long long& t) {      // PAIR: both CTAs' epilogue warps arrive on the leader's barrier
-    if (leader()) { wait(&pp->a_epi, ae & 1, t); tc_fence_after(); }
-    ++ae;
-  }
-  __device__ __forceinline__ void wait_bulk(uint32_t& ab, long long& t) { sync_local(&pp->a_bulk, &pp->peer_bulk, ab & 1, t); ++ab; }
-  __device__ __forceinline__ void commit(uint64_t* bar) {
-    if (!leader()) return;
-    if (elect_one()) { if (PAIR) mma_commit_pair(bar); else mma_commit(bar); }
-  }
-  __device__ __forceinline__ void gemm(int nchunks, int Nn, bool accumulate, uint32_t col = 0) {   // accumulator = TMEM columns [col, col + Nn)
-    const uint32_t tmem = this->tmem + col;
-    const int Nb = PAIR ? Nn / 2 : Nn;                                  // rows of B staged in this CTA
-    const uint32_t idesc = idesc_16(F16, Nn, 0, 0, PAIR ? 256 : 128);
-    const uint64_t a_base = smem_desc(act_addr, CORE_STRIDE, 128);
-    const uint64_t b_base = smem_desc(ring_addr, Nb * 16, 128);
-    const uint32_t b_lo = (uint32_t)(Nb * 32) >> 4;                     // lo plane of a stage / of the activation tile, in descriptor units
-    constexpr uint32_t a_lo = BLOB_H >> 4, a_step = (2 * CORE_STRIDE) >> 4, b_step = Geo<PL>::STAGE >> 4;
-    for (int c = 0; c < nchunks; ++c) {
-      sync_local(&pp->full[s], &pp->peer_full[s], ph, t_full);
-      if (leader()) {
-        const uint64_t ad = a_base + (uint32_t)c * a_step, bd = b_base + s * b_step;
-        const uint32_t first = (accumulate || c > 0) ? 1u : 0u;
-        if (elect_one()) {
-          if (PAIR) {
-            if (PL == 2) {                                 // small terms first: lo*hi + hi*lo + hi*hi into one accumulator
-              mma_pair(tmem, ad + a_lo, bd, idesc, first);
-              mma_pair(tmem, ad, bd + b_lo, idesc, 1u);
-              mma_pair(tmem, ad, bd, idesc, 1u);
-            } else {
-              mma_pair(tmem, ad, bd, idesc, first);
-            }
-            mma_commit_pair(&pp->empty[s]);
-          } else {
-            if (PL == 2) {                                 // A_hi is fetched once for its two MMAs (collector buffer)
-              mma_bf16(tmem, ad + a_lo, bd, idesc, first);
-              mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bd + b_lo, idesc, 1u);
-              mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem, ad, bd, idesc, 1u);
-            } else {
-              mma_bf16(tmem, ad, bd, idesc, first);
-            }
-            if (CLUSTER == 1) mma_commit(&pp->empty[s]); else mma_commit_mc(&pp->empty[s], (uint16_t)((1u << CLUSTER) - 1));
-          }
-        }
-      }
-      if (++s == NSTAGE) { s = 0; ph ^= 1; }
-    }
-  }
-};
-
 
 // Column sums over the 32 rows a warp owns: after the exchange lane l holds sum_rows v[row][l].  31 shuffles.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -405,433 +267,11 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-template <int PL>
-__device__ __forceinline__ void pipe_init(Pipe* pp, int warp, int tid) {
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) { mbar_init(&pp->full[s], 1); mbar_init(&pp->empty[s], PAIR ? 1 : CLUSTER); mbar_init(&pp->peer_full[s], 1); }
-    mbar_init(&pp->peer_epi, 1); mbar_init(&pp->peer_bulk, 1);
-    mbar_init(&pp->a_bulk, 1);
-    mbar_init(&pp->a_epi, PAIR ? 2 * Geo<PL>::EW : Geo<PL>::ET);   // every epilogue thread - PAIR: every epilogue warp of both CTAs - arrives
-    mbar_init(&pp->acc_ready, 1);
-    mbar_init(&pp->act_free, 1);
-    mbar_init(&pp->st_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == Geo<PL>::W_MMA) {                                  // the MMA warp of the fused kernels owns the allocation
-    if (PAIR) tmem_alloc_pair(&pp->tmem_base, Geo<PL>::TMEM_COLS); else tmem_alloc(&pp->tmem_base, Geo<PL>::TMEM_COLS);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (CLUSTER > 1) cluster_sync_all();              // peers' barriers exist before anything is multicast to them
-  // the leader passes ITS accumulator address to the pair MMA: both CTAs must have been given the same columns
-  if (PAIR && tid == 0 && cluster_ctarank() == 1 && ld_remote_u32(&pp->tmem_base, 0) != pp->tmem_base) __trap();
-}
-
-__device__ __forceinline__ void epi_done(Pipe* pp) {     // epilogue thread: my smem writes / TMEM reads are finished
-  tc_fence_before();
-  fence_proxy_async();
-  if (PAIR) {            // one arrival per warp, straight onto the LEADER's barrier (no relay hop for the peer CTA's tile)
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-      if (cluster_ctarank() == 0) mbar_arrive(&pp->a_epi); else mbar_arrive_remote(&pp->a_epi, 0);
-    }
-  } else {
-    mbar_arrive(&pp->a_epi);
-  }
-}
-
 // sign / partner of d(PE_j)/dz: PE[6f+c] = sin, PE[6f+3+c] = cos  ->  dPE[6f+c] = +band cos, dPE[6f+3+c] = -band sin
 #define DPE_PARTNER(J) (((J) % 6) < 3 ? (J) + 3 : (J)-3)
 #define DPE_SIGN(J) (((J) % 6) < 3 ? 1.0f : -1.0f)
 
-// ------------------------------------------------------------------------------------------------
-// Pass 1: values + reverse sweep.  One CTA per tile of 128 points, loops over the nets; 2 CTAs per SM.
-// warps 0-3: epilogue (thread = point = TMEM lane), warp 4: bulk-copy producer, warp 5: MMA issuer.
-// Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | 5 epilogue vectors (b1, b2+bd+e, ba, u, 2wo) 5 KB.
-// ------------------------------------------------------------------------------------------------
-template <int PL> constexpr int smem_fused() { return Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE + NVEC * H * 4 + TP * 4 * 4; }   // + per-row partial sums (o, dz[3])
-
 template <int PL> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(Geo<PL>::ET) : "memory"); }   // the epilogue warps only
-
-// NB consecutive 32-column blocks of this thread's TMEM lane: f(block, float (&v)[32])
-template <int NB, class F>
-__device__ __forceinline__ void tmem_blocks(uint32_t taddr, F&& f) {
-  // (software-pipelined TMEM loads - dpn_umma.cuh:tmem_for_each_block - were measured again with 168 registers per thread in the
-  //  one-CTA-per-SM modes: f16x3 call 24.4 -> 26.9 ms; the plain load / wait / process sequence stays)
-#pragma unroll 1
-  for (int cb = 0; cb < NB; ++cb) {
-    float v[32];
-    tmem_ld32(taddr + cb * 32, v);
-    f(cb, v);
-  }
-}
-
-__device__ __forceinline__ void load_vectors(float* svec, const Work& w, int b, int k, int t) {
-  const size_t vb = ((size_t)b * w.Kn + k) * H, vk = (size_t)k * H;
-  const float* src[NVEC] = {w.b1 + vb, w.bsum + vb, w.ba + vk, w.uvec + vk, w.wo2 + vk, w.c2 + vb};
-#pragma unroll
-  for (int i = 0; i < NVEC; ++i) svec[i * H + t] = __ldg(src[i] + t);       // t = 0..255
-}
-
-template <int PL, bool F16>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREADS, Geo<PL>::CTAS_PER_SM) pass1_kernel(const Work w, const int sweep) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ Pipe pipe;
-  uint8_t* act = smem;
-  uint8_t* ring = smem + Geo<PL>::ACT;
-  float* svec = reinterpret_cast<float*>(smem + Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE);
-  float* rowsum = svec + NVEC * H;                                // [TP][4]: o partial, dz[3]
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform by construction: the role branches below stay uniform
-  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
-  const size_t g = blockIdx.x;                       // global tile index
-  pipe_init<PL>(&pipe, warp, tid);
-  const uint32_t tmem = pipe.tmem_base;
-
-  if (warp == Geo<PL>::W_PROD) {
-    // ---------------- producer (whole warp, one elected lane issues) ----------------
-    Producer<PL> pr{&pipe, ring, cluster_ctarank()};
-    uint32_t af = 0, sd = 0;
-    const uint8_t* pe_src = w.pe_blob + g * Geo<PL>::BC;
-    const uint8_t* pe6_src = w.pe6_blob + g * Geo<PL>::BC;
-    auto load_a_tile = [&](const uint8_t* src) {                  // [128 x 192] tile, plane p -> act + p * BLOB_H
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&pipe.a_bulk, PL * BLOB_C);
-#pragma unroll
-        for (int p = 0; p < PL; ++p) bulk_g2s_hint(act + p * BLOB_H, src + p * BLOB_C, BLOB_C, &pipe.a_bulk, pr.pol);
-      }
-    };
-    for (int k = 0; k < w.Kn; ++k) {
-      const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
-      const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
-      const uint8_t *iW1 = gen, *iW1T = gen + PL * IMG_HC, *iW2 = gen + PL * 2 * IMG_HC, *iW2T = gen + PL * (2 * IMG_HC + IMG_HH);
-      const uint8_t* iPT = gen + PL * (2 * IMG_HC + 3 * IMG_HH);
-      const uint8_t *iWd = sta, *iWa = sta + PL * IMG_HC, *iWaT = sta + PL * (IMG_HC + IMG_HH);
-      pr.stream(iW1, 0, 4, STAGE_BYTES);              // these do not depend on the activation buffer
-      if (k > 0) {
-        mbar_wait(&pipe.act_free, af & 1); ++af;
-        if (sweep) { mbar_wait(&pipe.st_done, sd & 1); ++sd; }      // last tile of the previous net has been drained
-      }
-      load_a_tile(pe_src);
-      pr.stream(iW1, 4, 12, STAGE_BYTES);
-      pr.stream(iW2, 0, 16, STAGE_BYTES);
-      pr.stream(iWd, 0, 4, STAGE_BYTES);
-      mbar_wait(&pipe.act_free, af & 1); ++af;        // G2a has consumed h1
-      if (sweep) { mbar_wait(&pipe.st_done, sd & 1); ++sd; }        // ... and the bulk store has drained it to the workspace
-      load_a_tile(pe6_src);
-      pr.stream(iWd, 4, 12, STAGE_BYTES);
-      pr.stream(iWa, 0, 16, STAGE_BYTES);
-      if (sweep) {
-        pr.stream(iWaT, 0, 16, STAGE_BYTES);
-        pr.stream(Geo<PL>::FOLD ? iPT : iW2T, 0, 16, STAGE_BYTES);    // FOLD: q = um (Wa W2) + 2wo W2 straight from the um tile
-        if (sweep > 1) pr.stream(iW1T, 0, 16, 6144);
-      }
-    }
-  } else if (warp == Geo<PL>::W_MMA) {
-    // ---------------- MMA issuer (whole warp, one elected lane issues) ----------------
-    Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank(), w.phase_dbg != nullptr};
-    uint32_t ab = 0, ae = 0;
-    long long t_epi = 0, t_bulk = 0;
-    const long long t_begin = clock64();
-    for (int k = 0; k < w.Kn; ++k) {
-      if (k > 0) is.wait_epi(ae, t_epi);                             // last epilogue of the previous net has drained TMEM
-      is.wait_bulk(ab, t_bulk);
-      is.gemm(12, H, false); is.commit(&pipe.acc_ready);           // G1
-      is.wait_epi(ae, t_epi);
-      is.gemm(16, H, false); is.commit(&pipe.act_free);            // G2a
-      is.wait_bulk(ab, t_bulk);
-      is.gemm(12, H, true); is.commit(&pipe.acc_ready);            // G2b
-      is.wait_epi(ae, t_epi);
-      is.gemm(16, H, false); is.commit(&pipe.acc_ready);           // G3
-      if (sweep) {
-        is.wait_epi(ae, t_epi);
-        if (Geo<PL>::FOLD) {
-          is.gemm(16, H, false);                                     // G4 -> columns [0, 256)
-          is.gemm(16, H, false, 256); is.commit(&pipe.acc_ready);    // G5 (folded) -> columns [256, 512): one epilogue round for both
-        } else {
-          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G4
-          is.wait_epi(ae, t_epi);
-          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G5
-        }
-        if (sweep > 1) {
-          is.wait_epi(ae, t_epi);
-          is.gemm(16, C, false); is.commit(&pipe.acc_ready);       // G6
-        }
-      }
-      is.commit(&pipe.act_free);                                   // the activation buffer may take the next PE tile
-    }
-    if (w.phase_dbg && lane == 0) {
-      atomicAdd((unsigned long long*)w.phase_dbg + 0, (unsigned long long)(clock64() - t_begin));
-      atomicAdd((unsigned long long*)w.phase_dbg + 1, (unsigned long long)is.t_full);
-      atomicAdd((unsigned long long*)w.phase_dbg + 2, (unsigned long long)t_epi);
-      atomicAdd((unsigned long long*)w.phase_dbg + 3, (unsigned long long)t_bulk);
-    }
-  } else if (warp < Geo<PL>::EW) {
-    // ---------------- epilogue: thread = (point r, column group) ----------------
-    constexpr int NB = Geo<PL>::NB;                                 // 32-column blocks per thread (4: column halves, 2: quarters)
-    const int half = warp >> 2;                                     // column group: columns [32 NB half, 32 NB (half + 1))
-    const int r = (warp & 3) * 32 + lane;                           // row in tile = TMEM lane
-    const int c0 = half * NB;                                       // first 32-column block of this thread
-    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * (NB * 32);
-    const int p_local = tl * TP + r;
-    const bool valid = p_local < w.P;
-    const size_t q = (size_t)b * w.N + w.p0 + p_local;              // index into the caller's per-point arrays
-    const size_t row = g * TP + r;                                  // index into the pass-local per-point arrays
-    const float* pet = w.pet + g * (size_t)(C * TP) + r;
-    uint32_t ar = 0;
-    long long t_acc = 0, t_comp = 0, t_mark = 0;
-    const long long t_begin = clock64();
-    // Drain of a finished activation tile to the workspace: one bulk store by the TMA engine instead of 32 st.global
-    // per thread.  Call after epi_done(); `to_producer` when the next writer of the buffer is the bulk-load producer.
-    const uint64_t pol_stream = l2_policy_evict_first();              // activation tiles are written once, read much later
-    const uint64_t pol_keep = l2_policy_evict_last();                 // the tile's coordinate features are re-read for every net
-    auto drain = [&](uint8_t* blob, const bool to_producer) {
-      epi_bar<PL>();                                                    // every thread has written and fenced its part
-      if (tid == 0) {
-        bulk_s2g_hint(blob, act, Geo<PL>::ACT, pol_stream);        // all planes: they are contiguous on both sides
-        bulk_commit();
-        bulk_wait_read_all();
-        if (to_producer) mbar_arrive(&pipe.st_done);
-      }
-    };
-    if (half == 0) { rowsum[r * 4 + 0] = 0.f; rowsum[r * 4 + 1] = 0.f; rowsum[r * 4 + 2] = 0.f; rowsum[r * 4 + 3] = 0.f; }
-    for (int k = 0; k < w.Kn; ++k) {
-      uint8_t* nt = net_tile<PL>(w, b, k, tl);
-      epi_bar<PL>();                                                    // every warp is done with the previous net's vectors
-      if (tid < H) load_vectors(svec, w, b, k, tid);
-      epi_bar<PL>();
-      // fp16 variant: accumulators carry (scale of A tile) x (scale of weight image); i* undo that, s* scale the next tile
-      float i1 = 1.f, i2 = 1.f, i3 = 1.f, i4 = 1.f, i5 = 1.f, i6 = 1.f, sH1 = 1.f, sC = 1.f, sG = 1.f, sUM = 1.f, sY = 1.f, sQ = 1.f;
-      if (F16) {
-        const NetScales t = w.sc[b * w.Kn + k];
-        i1 = 1.f / (S_PE * t.sW1); i2 = 1.f / (t.sH1 * t.sW2); i3 = 1.f / (t.sC * t.sWa); i4 = 1.f / (t.sUM * t.sWa);
-        i5 = Geo<PL>::FOLD ? 1.f / (t.sUM * t.sP) : t.sQ / (t.sY * t.sW2); i6 = 1.f / (t.sQ * t.sW1);
-        sQ = t.sQ;
-        sH1 = t.sH1; sC = t.sC; sG = t.sG; sUM = t.sUM; sY = t.sY;
-      }
-      uint32_t m1w[NB];                                              // ReLU mask of a1 for this thread's columns
-#pragma unroll
-      for (int i = 0; i < NB; ++i) m1w[i] = 0u;
-      // ---- epilogue 1: h1 = relu(a1 + b1) ----
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-        const int cg = c0 + cb;
-        uint32_t bits = 0;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = *reinterpret_cast<const float4*>(svec + V_B1 * H + cg * 32 + j4 * 4);
-          const float bb[4] = {bv.x, bv.y, bv.z, bv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = F16 ? fmaf(v[j4 * 4 + e], i1, bb[e]) : v[j4 * 4 + e] + bb[e];
-            bits |= (a > 0.f ? 1u : 0u) << (j4 * 4 + e);
-            v[j4 * 4 + e] = F16 ? fmaxf(a, 0.f) * sH1 : fmaxf(a, 0.f);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < NB; ++i) m1w[i] = (cb == i) ? bits : m1w[i];
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
-        }
-      });
-      epi_done(&pipe); t_comp += clock64() - t_mark;
-      if (sweep) drain(blob_h<PL>(nt, B_H1), true);
-      // ---- epilogue 2: c = acc + (b2 + bd + e);  oc = 2wo.c ----
-      if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
-      float os0 = 0.f, os1 = 0.f;
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-        const int cg = c0 + cb;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 bv = *reinterpret_cast<const float4*>(svec + V_BSUM * H + cg * 32 + j4 * 4);
-          const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
-          const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float cc = F16 ? fmaf(v[j4 * 4 + e], i2, bb[e]) : v[j4 * 4 + e] + bb[e];
-            if (e & 1) os1 = fmaf(ww[e], cc, os1); else os0 = fmaf(ww[e], cc, os0);
-            v[j4 * 4 + e] = F16 ? cc * sC : cc;
-          }
-        }
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
-        }
-      });
-      epi_done(&pipe); t_comp += clock64() - t_mark;
-      if (sweep) drain(blob_h<PL>(nt, B_CC), false);
-      // ---- epilogue 3: g = relu(a3 + ba);  o = oc + u.g + cst + ref;  um = u*[a3>0] ----
-      if (sweep) epi_bar<PL>();
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-        const int cg = c0 + cb;
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          float um[8];
-#pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const float4 bv = *reinterpret_cast<const float4*>(svec + V_BA * H + cg * 32 + qd * 8 + h2 * 4);
-            const float4 uv = *reinterpret_cast<const float4*>(svec + V_U * H + cg * 32 + qd * 8 + h2 * 4);
-            const float bb[4] = {bv.x, bv.y, bv.z, bv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a = F16 ? fmaf(v[qd * 8 + h2 * 4 + e], i3, bb[e]) : v[qd * 8 + h2 * 4 + e] + bb[e];
-              const float gg = fmaxf(a, 0.f);
-              if (e & 1) os1 = fmaf(uu[e], gg, os1); else os0 = fmaf(uu[e], gg, os0);
-              v[qd * 8 + h2 * 4 + e] = F16 ? gg * sG : gg;
-              um[h2 * 4 + e] = a > 0.f ? (F16 ? uu[e] * sUM : uu[e]) : 0.f;
-            }
-          }
-          const uint32_t off = piece_off(r, cg * 4 + qd);
-          if (sweep) {                                                // values-only calls keep nothing for a backward pass,
-            stg8<PL, F16>(blob_h<PL>(nt, B_GG), BLOB_H, off, v + qd * 8);
-            sts8<PL, F16>(act, BLOB_H, off, um);                           // and their buffer already belongs to the next PE tile
-          }
-        }
-      });
-      atomicAdd(rowsum + r * 4, os0 + os1);                          // the two column halves of a row meet in shared memory
-      epi_done(&pipe); t_comp += clock64() - t_mark;
-      if (sweep) drain(blob_h<PL>(nt, B_UM), Geo<PL>::FOLD && sweep < 2); else epi_bar<PL>();
-      if (half == 0) {
-        if (valid) w.o[row * w.Kn + k] = rowsum[r * 4] + __ldg(w.cst + k) + (w.ref ? __ldg(w.ref + q * w.Kn + k) : __ldg(w.coord_data + q * 6 + k));
-        rowsum[r * 4] = 0.f;
-      }
-      if (!sweep) continue;
-      if (Geo<PL>::FOLD) {
-        // ---- epilogues 4 + 5 in one round: y = acc0 + 2wo -> workspace ;  qm = (acc1 + 2wo W2) * m1 -> next A tile ----
-        epi_bar<PL>();                                              // the drain of the um tile has released the buffer
-        mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-#pragma unroll 1
-        for (int cb = 0; cb < NB; ++cb) {
-          const int cg = c0 + cb;
-          float v[32];
-          tmem_ld32(tl_addr + cb * 32, v);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
-            const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[j4 * 4 + e] = F16 ? fmaf(v[j4 * 4 + e], i4, ww[e]) * sY : v[j4 * 4 + e] + ww[e];
-          }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) stg8<PL, F16>(blob_h<PL>(nt, B_YT), BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
-          tmem_ld32(tl_addr + 256 + cb * 32, v);
-          uint32_t bits = 0u;
-#pragma unroll
-          for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cv = *reinterpret_cast<const float4*>(svec + V_C2 * H + cg * 32 + j4 * 4);
-            const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = j4 * 4 + e;
-              const float qv = F16 ? fmaf(v[j], i5, cc[e]) * sQ : v[j] + cc[e];
-              v[j] = ((bits >> j) & 1u) ? qv : 0.f;
-            }
-          }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const uint32_t off = piece_off(r, cg * 4 + qd);
-            if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
-            else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);
-          }
-        }
-        epi_done(&pipe); t_comp += clock64() - t_mark;
-      } else {
-      // ---- epilogue 4: y = acc + 2wo ----
-        if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
-        mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-        tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-          const int cg = c0 + cb;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 wv = *reinterpret_cast<const float4*>(svec + V_WO2 * H + cg * 32 + j4 * 4);
-            if (F16) {
-              v[j4 * 4 + 0] = fmaf(v[j4 * 4 + 0], i4, wv.x) * sY; v[j4 * 4 + 1] = fmaf(v[j4 * 4 + 1], i4, wv.y) * sY;
-              v[j4 * 4 + 2] = fmaf(v[j4 * 4 + 2], i4, wv.z) * sY; v[j4 * 4 + 3] = fmaf(v[j4 * 4 + 3], i4, wv.w) * sY;
-            } else {
-              v[j4 * 4 + 0] += wv.x; v[j4 * 4 + 1] += wv.y; v[j4 * 4 + 2] += wv.z; v[j4 * 4 + 3] += wv.w;
-            }
-          }
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            sts8<PL, F16>(act, BLOB_H, piece_off(r, cg * 4 + qd), v + qd * 8);
-          }
-        });
-        epi_done(&pipe); t_comp += clock64() - t_mark;
-        drain(blob_h<PL>(nt, B_YT), sweep < 2);
-        // ---- epilogue 5: qm = acc * m1 ----
-        if (sweep) epi_bar<PL>();                                         // the drain of the previous tile has released the buffer
-        mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-        tmem_blocks<NB>(tl_addr, [&](const int cb, float (&v)[32]) {
-          const int cg = c0 + cb;
-          uint32_t bits = 0u;
-#pragma unroll
-          for (int i = 0; i < NB; ++i) bits = (cb == i) ? m1w[i] : bits;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? (F16 ? v[j] * i5 : v[j]) : 0.f;
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const uint32_t off = piece_off(r, cg * 4 + qd);
-            if (sweep > 1) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);
-            else stg8<PL, F16>(blob_h<PL>(nt, B_QM), BLOB_H, off, v + qd * 8);         // decoder-only backward: no G6, the tile goes straight out
-          }
-        });
-        epi_done(&pipe); t_comp += clock64() - t_mark;
-      }
-      if (sweep < 2) continue;
-      drain(blob_h<PL>(nt, B_QM), true);
-      // ---- epilogue 6: do/dz_c = sum_j jin_j dPE_j  (j % 3 == c); N = 192: each half takes one 96-column group ----
-      mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); t_mark = clock64();
-      float dz[3] = {0.f, 0.f, 0.f};
-      if (half < 2) {                                                // two 96-column groups; with 16 warps groups 2, 3 only wait
-        const uint32_t a6 = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * 96;
-        const float bsel = half ? 1.f : 0.f;
-#pragma unroll
-        for (int ib = 0; ib < 3; ++ib) {                             // 96 % 6 == 0 keeps the sin/cos pattern static per block
-          float pp[32], v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) pp[j] = ldg_f32_hint(pet + (size_t)(half * 96 + DPE_PARTNER(ib * 32 + j)) * TP, pol_keep);
-          tmem_ld32(a6 + ib * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int Jl = ib * 32 + j;
-            const float bnd = bsel * w.band[16 + Jl / 6] + (1.f - bsel) * w.band[Jl / 6];
-            dz[Jl % 3] = fmaf(DPE_SIGN(Jl) * bnd * v[j], pp[j], dz[Jl % 3]);
-          }
-        }
-      }
-      if (half < 2) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) atomicAdd(rowsum + r * 4 + 1 + c, F16 ? dz[c] * i6 : dz[c]);
-      }
-      epi_done(&pipe); t_comp += clock64() - t_mark;
-      epi_bar<PL>();
-      if (half == 0) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (valid) w.od[(row * w.Kn + k) * 3 + c] = rowsum[r * 4 + 1 + c];
-          rowsum[r * 4 + 1 + c] = 0.f;
-        }
-      }
-    }
-    if (tid == 0) bulk_wait_all();
-    if (w.phase_dbg && tid == 0) {
-      atomicAdd((unsigned long long*)w.phase_dbg + 4, (unsigned long long)(clock64() - t_begin));
-      atomicAdd((unsigned long long*)w.phase_dbg + 5, (unsigned long long)t_acc);
-      atomicAdd((unsigned long long*)w.phase_dbg + 7, (unsigned long long)t_comp);
-      atomicAdd((unsigned long long*)w.phase_dbg + 6, 1ull);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, Geo<PL>::TMEM_COLS); else tmem_dealloc(tmem, Geo<PL>::TMEM_COLS); }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Pass 1 of the split modes: A operands in TENSOR MEMORY.
@@ -849,40 +289,44 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 // accumulator of GEMM j + 1.
 // ------------------------------------------------------------------------------------------------
 namespace ts {
-constexpr int NS = 9;
-constexpr int W_BYTES = 2 * STAGE_BYTES;        // weight chunk [256 x 16] : hi 8 KB | lo 8 KB   ([192 x 16]: 6 KB | 6 KB)
 constexpr int A_PLANE = 2 * CORE_STRIDE;        // A slice [128 x 16] of one plane: 4 KB
-constexpr int STAGE = W_BYTES + 2 * A_PLANE;    // 24 KB
 constexpr uint32_t REGION = 256;               // TMEM columns of one ping-pong region
-constexpr int SMEM = NS * STAGE + NVEC * H * 4 + TP * 4 * 4;
+constexpr int NS_MAX = 16;
+template <int PL>
+struct Cfg {                                    // ring geometry for PL operand planes
+  static constexpr int NS = PL == 2 ? 9 : 16;
+  static constexpr int W_BYTES = PL * STAGE_BYTES;         // weight chunk [256 x 16]: 8 KB per plane, hi | lo  ([192 x 16]: 6 KB per plane)
+  static constexpr int STAGE = W_BYTES + PL * A_PLANE;     // 24 KB / 12 KB
+  static constexpr int SMEM = NS * STAGE + NVEC * H * 4 + TP * 4 * 4;
+};
 struct PipeTS {
-  uint64_t full[NS], empty[NS];
+  uint64_t full[NS_MAX], empty[NS_MAX];
   uint64_t blk[4];          // block cb of BOTH column halves of the next A operand is in tensor memory (one arrival per epilogue warp)
   uint64_t acc_ready[2];    // the GEMM accumulating into region 0 / 1 has completed
   uint64_t drained;         // the last epilogue of a net (which hands no operand on) has read its accumulator
   uint32_t tmem_base;
 };
-static_assert(SMEM + (int)sizeof(PipeTS) + 1024 <= 227 * 1024, "pass1_ts_kernel: ring + vectors + row sums + barriers must fit one SM's 227 KB");
+static_assert(Cfg<2>::SMEM + (int)sizeof(PipeTS) + 1024 <= 227 * 1024 && Cfg<1>::SMEM <= Cfg<2>::SMEM, "pass1_ts_kernel: ring + vectors + row sums + barriers must fit one SM's 227 KB");
 static_assert(2 * REGION == 512 && REGION == H, "TMEM map: two [128 x 256] fp32 accumulators, each converted in place into 2 x 16-bit planes");
 // K-chunk order of a TS-form GEMM: the two epilogue warp groups finish block cb of their column halves together, i.e. chunks
 // 2cb, 2cb+1 (half 0) and 8+2cb, 9+2cb (half 1)
 __host__ __device__ constexpr int block_order(int i) { return ((i >> 2) << 1) + (i & 1) + ((i >> 1) & 1) * 8; }
 }  // namespace ts
 
-template <bool F16, bool XF>                     // XF: cross-first accumulation of G1 - G3 (DPN_MODE_F16X3A)
+template <int PL, bool F16, bool XF>             // PL operand planes; XF: cross-first accumulation of G1 - G3 (DPN_MODE_F16X3A)
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREADS, 1) pass1_ts_kernel(const Work w, const int sweep) {
-  constexpr int PL = 2;
+  using TS = ts::Cfg<PL>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ ts::PipeTS pipe;
   uint8_t* ring = smem;
-  float* svec = reinterpret_cast<float*>(smem + ts::NS * ts::STAGE);
+  float* svec = reinterpret_cast<float*>(smem + TS::NS * TS::STAGE);
   float* rowsum = svec + NVEC * H;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < ts::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
+    for (int s = 0; s < TS::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(&pipe.blk[i], Geo<PL>::EW);
     mbar_init(&pipe.acc_ready[0], 1); mbar_init(&pipe.acc_ready[1], 1);
     mbar_init(&pipe.drained, Geo<PL>::EW);
@@ -915,7 +359,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const int a_planes = hi_only ? 1 : PL;
       mbar_wait(&pipe.empty[s], ph ^ 1);
       if (elect_one()) {
-        uint8_t* stg = ring + s * ts::STAGE;
+        uint8_t* stg = ring + s * TS::STAGE;
         mbar_arrive_expect_tx(&pipe.full[s], wbytes + (asrc ? a_planes * ts::A_PLANE : 0));
         if (CLUSTER == 1) {
           bulk_g2s_hint(stg, wsrc, wbytes, &pipe.full[s], pol);
@@ -924,10 +368,10 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           bulk_g2s_mc_hint(stg + rank * slice, wsrc + rank * slice, slice, &pipe.full[s], MC_MASK, pol);
         }
         if (asrc) {
-          for (int p = 0; p < a_planes; ++p) bulk_g2s_hint(stg + ts::W_BYTES + p * ts::A_PLANE, asrc + p * BLOB_C, ts::A_PLANE, &pipe.full[s], pol);
+          for (int p = 0; p < a_planes; ++p) bulk_g2s_hint(stg + TS::W_BYTES + p * ts::A_PLANE, asrc + p * BLOB_C, ts::A_PLANE, &pipe.full[s], pol);
         }
       }
-      if (++s == ts::NS) { s = 0; ph ^= 1; }
+      if (++s == TS::NS) { s = 0; ph ^= 1; }
     };
     const uint8_t* pe_src = w.pe_blob + g * Geo<PL>::BC;
     const uint8_t* pe6_src = w.pe6_blob + g * Geo<PL>::BC;
@@ -939,19 +383,19 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       // the MMA warp's order: G1 | G2b (PE6 slices: no dependence on an epilogue, issued first) | TS-form GEMMs in block order.
       // Cross-first GEMMs (G1 - G3 when masks matter, see the MMA warp) read every chunk twice: whole chunks for the cross terms,
       // then the hi planes again for the main terms.
-      for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe_src + (size_t)c * ts::A_PLANE);
-      if (xfirst) for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe_src + (size_t)c * ts::A_PLANE, true);
-      for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE);
-      for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
+      for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * TS::W_BYTES, TS::W_BYTES, pe_src + (size_t)c * ts::A_PLANE);
+      if (xfirst) for (int c = 0; c < 12; ++c) put(iW1 + (size_t)c * TS::W_BYTES, TS::W_BYTES, pe_src + (size_t)c * ts::A_PLANE, true);
+      for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * TS::W_BYTES, TS::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE);
+      for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * TS::W_BYTES, TS::W_BYTES, nullptr);
       if (xfirst) {
-        for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * ts::W_BYTES, ts::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE, true);
-        for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr, true);
+        for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * TS::W_BYTES, TS::W_BYTES, pe6_src + (size_t)c * ts::A_PLANE, true);
+        for (int c = 0; c < 16; ++c) put(iW2 + (size_t)c * TS::W_BYTES, TS::W_BYTES, nullptr, true);
       }
-      for (int i = 0; i < 16; ++i) put(iWa + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
-      if (xfirst) for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * ts::W_BYTES, ts::W_BYTES, nullptr, true);
+      for (int i = 0; i < 16; ++i) put(iWa + (size_t)ts::block_order(i) * TS::W_BYTES, TS::W_BYTES, nullptr);
+      if (xfirst) for (int c = 0; c < 16; ++c) put(iWa + (size_t)c * TS::W_BYTES, TS::W_BYTES, nullptr, true);
       if (sweep) {
-        for (int i = 0; i < 16; ++i) put(iWaT + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
-        for (int i = 0; i < 16; ++i) put(iW2T + (size_t)ts::block_order(i) * ts::W_BYTES, ts::W_BYTES, nullptr);
+        for (int i = 0; i < 16; ++i) put(iWaT + (size_t)ts::block_order(i) * TS::W_BYTES, TS::W_BYTES, nullptr);
+        for (int i = 0; i < 16; ++i) put(iW2T + (size_t)ts::block_order(i) * TS::W_BYTES, TS::W_BYTES, nullptr);
         if (sweep > 1)
           for (int i = 0; i < 16; ++i) put(iW1T + (size_t)ts::block_order(i) * (PL * 6144), PL * 6144, nullptr);
       }
@@ -963,7 +407,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     const bool timed = w.phase_dbg != nullptr;
     const long long t_begin = clock64();
     const uint32_t ring_addr = smem_u32(ring);
-    const uint64_t a_base = smem_desc(ring_addr + ts::W_BYTES, CORE_STRIDE, 128);
+    const uint64_t a_base = smem_desc(ring_addr + TS::W_BYTES, CORE_STRIDE, 128);
     // one K = 16 chunk: lo*hi + hi*lo + hi*hi into the accumulator at column d; A planes from tensor memory (a_hi) or from the stage
     // which of the products of a split contraction a chunk issues: all three | exact A operand (B_lo, B_hi) | the two cross terms | the main term
     enum { P_ALL = 0, P_EXACT = 1, P_CROSS = 2, P_MAIN = 3 };
@@ -973,16 +417,20 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       const uint32_t b_lo = (uint32_t)(Nn * 32) >> 4;
       if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
       tc_fence_after();
-      const uint64_t bd = b_base + s * (uint32_t)(ts::STAGE >> 4), bl = bd + b_lo;
+      const uint64_t bd = b_base + s * (uint32_t)(TS::STAGE >> 4), bl = bd + b_lo;
       if (elect_one()) {
         if (DPN_DBG(w, 1)) {                             // (debug builds: no MMAs, barrier protocol intact)
         } else if (a_in_tmem) {
-          if (part == P_ALL || part == P_CROSS) mma_ts(d, a_hi + 16, bd, idesc, first);   // (an exact 16-bit A operand - the 0 / 1 mask of G4 - has no lo plane)
-          if (part != P_MAIN) mma_ts(d, a_hi, bl, idesc, part == P_EXACT ? first : 1u);
-          if (part != P_CROSS) mma_ts(d, a_hi, bd, idesc, part == P_MAIN ? first : 1u);
+          if (PL == 1) {                                   // one plane: one product
+            mma_ts(d, a_hi, bd, idesc, first);
+          } else {
+            if (part == P_ALL || part == P_CROSS) mma_ts(d, a_hi + 16, bd, idesc, first);   // (an exact 16-bit A operand - the 0 / 1 mask of G4 - has no lo plane)
+            if (part != P_MAIN) mma_ts(d, a_hi, bl, idesc, part == P_EXACT ? first : 1u);
+            if (part != P_CROSS) mma_ts(d, a_hi, bd, idesc, part == P_MAIN ? first : 1u);
+          }
         } else {                                         // the A slice of this chunk sits behind the weights in the same stage
-          const uint64_t ad = a_base + s * (uint32_t)(ts::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
-          if (part == P_MAIN) {
+          const uint64_t ad = a_base + s * (uint32_t)(TS::STAGE >> 4), al = ad + (ts::A_PLANE >> 4);
+          if (PL == 1 || part == P_MAIN) {
             mma_bf16(d, ad, bd, idesc, first);
           } else {
             mma_bf16(d, al, bd, idesc, first);
@@ -996,7 +444,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         }
         if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
       }
-      if (++s == ts::NS) { s = 0; ph ^= 1; }
+      if (++s == TS::NS) { s = 0; ph ^= 1; }
     };
     // G over the PE / PE6 slices of the ring into region `cur`
     auto gemm_ss = [&](const int nchunks, const int part = P_ALL, const bool accumulate = false) {
@@ -1070,14 +518,14 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         if (blob && !DPN_DBG(w, 4)) {
           const uint32_t off = gp_off(32, r, cg * 4 + qd);
           __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
-          __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
+          if (PL == 2) __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[PL - 1]);
         }
         hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
-        lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
+        lo[qd * 4 + 0] = pq[PL - 1].x; lo[qd * 4 + 1] = pq[PL - 1].y; lo[qd * 4 + 2] = pq[PL - 1].z; lo[qd * 4 + 3] = pq[PL - 1].w;
       }
       if (to_a) {
         tmem_st16(blk_addr, hi);
-        tmem_st16(blk_addr + 16, lo);
+        if (PL == 2) tmem_st16(blk_addr + 16, lo);
       }
     };
     // this warp's part of block cb is in tensor memory / this warp has read the last accumulator of the net: one arrival per warp
@@ -1300,12 +748,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
   if (warp == Geo<PL>::W_MMA) tmem_dealloc(tmem, 512);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Pass 2: the combined tangent row, the Z-side operands of the weight gradients and three column sums.
-// Shared memory: activation tile 64 KB | weight ring 5 x 8 KB | column-sum accumulators 3 x 256 floats.
-// ------------------------------------------------------------------------------------------------
-template <int PL> constexpr int smem_pass2() { return Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE + 3 * H * 4 + 16; }
-
 // 8 consecutive values of a stored tile: sum of its planes
 template <int PL, bool F16 = false>
 __device__ __forceinline__ void unpack_planes(const uint4 (&q)[PL], float* v) {
@@ -1316,252 +758,6 @@ __device__ __forceinline__ void unpack_planes(const uint4 (&q)[PL], float* v) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] += l[e];
   }
-}
-
-template <int PL, bool F16>
-__global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREADS, Geo<PL>::CTAS_PER_SM) pass2_kernel(const Work w, const int tangent) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ Pipe pipe;
-  uint8_t* act = smem;
-  uint8_t* ring = smem + Geo<PL>::ACT;
-  float* csum = reinterpret_cast<float*>(smem + Geo<PL>::ACT + NSTAGE * Geo<PL>::STAGE);   // [3][H] + sdo
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform by construction: the role branches below stay uniform
-  const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
-  const size_t g = blockIdx.x;
-  pipe_init<PL>(&pipe, warp, tid);
-  const uint32_t tmem = pipe.tmem_base;
-
-  if (warp == Geo<PL>::W_PROD) {
-    if (tangent) {
-      Producer<PL> pr{&pipe, ring, cluster_ctarank()};
-      // (measured and dropped: cp.async.bulk.prefetch.L2 of this tile's h1 / c / g one net ahead makes pass 2 13 % SLOWER -
-      //  the epilogue loads are not latency-bound, the extra L2 traffic only competes with the streaming stores)
-      for (int k = 0; k < w.Kn; ++k) {
-        const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
-        const uint8_t* sta = w.img_sta + (size_t)k * Geo<PL>::STA;
-        pr.stream(gen, 0, 12, STAGE_BYTES);                      // W1
-        pr.stream(gen + PL * 2 * IMG_HC, 0, 16, STAGE_BYTES);    // W2
-        if (Geo<PL>::FOLD) pr.stream(gen + PL * (2 * IMG_HC + 2 * IMG_HH), 0, 16, STAGE_BYTES);   // P = Wa W2: gt = ht P^T from the ht tile
-        else pr.stream(sta + PL * IMG_HC, 0, 16, STAGE_BYTES);   // Wa
-      }
-    }
-  } else if (warp == Geo<PL>::W_MMA) {
-    if (tangent) {
-      Issuer<PL, F16> is{&pipe, smem_u32(act), smem_u32(ring), tmem, cluster_ctarank(), w.phase_dbg != nullptr};
-      uint32_t ae = 0;
-      long long t_epi = 0;
-      const long long t_begin = clock64();
-      for (int k = 0; k < w.Kn; ++k) {
-        is.wait_epi(ae, t_epi);
-        is.gemm(12, H, false); is.commit(&pipe.acc_ready);         // G7
-        is.wait_epi(ae, t_epi);
-        if (Geo<PL>::FOLD) {
-          is.gemm(16, H, false);                                     // G8 -> columns [0, 256)
-          is.gemm(16, H, false, 256); is.commit(&pipe.acc_ready);    // G9 (folded) -> columns [256, 512): both read the ht tile
-        } else {
-          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G8
-          is.wait_epi(ae, t_epi);
-          is.gemm(16, H, false); is.commit(&pipe.acc_ready);         // G9
-        }
-      }
-      if (w.phase_dbg && lane == 0) {
-        atomicAdd((unsigned long long*)w.phase_dbg + 8, (unsigned long long)(clock64() - t_begin));
-        atomicAdd((unsigned long long*)w.phase_dbg + 9, (unsigned long long)is.t_full);
-        atomicAdd((unsigned long long*)w.phase_dbg + 10, (unsigned long long)t_epi);
-      }
-    }
-  } else if (warp < Geo<PL>::EW) {
-    constexpr int NB = Geo<PL>::NB;
-    const int half = warp >> 2;                                     // column group (see pass 1)
-    const int r = (warp & 3) * 32 + lane;
-    const int c0 = half * NB;
-    const uint32_t tl_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + half * (NB * 32);
-    const size_t row = g * TP + r;
-    const float* pet = w.pet + g * (size_t)(C * TP) + r;
-    const uint8_t* pe6 = w.pe6_blob + g * Geo<PL>::BC;
-    uint32_t ar = 0;
-    long long t_acc = 0, t_comp = 0, t_mark = 0;
-    const long long t_begin = clock64();
-    const uint64_t pol_keep = l2_policy_evict_last();                 // the tile's coordinate features are re-read for every net
-    for (int i = tid; i < 3 * H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
-    epi_bar<PL>();
-    for (int k = 0; k < w.Kn; ++k) {
-      uint8_t* nt = net_tile<PL>(w, b, k, tl);
-      const float dv = w.dov[row * w.Kn + k];
-      float dd[3] = {0.f, 0.f, 0.f};
-      if (tangent) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) dd[c] = w.dod[(row * w.Kn + k) * 3 + c];
-      }
-      // fp16 variant: sp = power-of-two scale of this point's tangent row (its seeds set the magnitude of xt, ht, ct);
-      // the Z-side tiles share one scale per (sample, net) because the weight-gradient contraction runs over points
-      float sp = 1.f, isp = 1.f, sZP = 1.f, sZH = 1.f, sZC = 1.f, sZD = 1.f, iH1 = 1.f, iC = 1.f, iG = 1.f, iW1 = 1.f, iW2 = 1.f, iWa = 1.f;
-      float sDV = 1.f;
-      if (F16) {
-        const NetScales t = w.sc[b * w.Kn + k];
-        const float Rp = 16.f * fmaxf(fabsf(dd[0]), fmaxf(fabsf(dd[1]), fabsf(dd[2])));
-        sp = Rp > 0.f ? scale_for(Rp * t.rowB) : 1.f;
-        isp = 1.f / sp;
-        sZP = t.sZP; sZH = t.sZH; sZC = t.sZC; sZD = t.sZD; sDV = t.sDV;
-        iH1 = 1.f / t.sH1; iC = 1.f / t.sC; iG = 1.f / t.sG; iW1 = 1.f / t.sW1; iW2 = 1.f / t.sW2;
-        iWa = 1.f / (Geo<PL>::FOLD ? t.sP : t.sWa);                  // FOLD: G9 contracts ht with P = Wa W2
-      }
-      // seed tile for the bias-gradient MMAs of the wgrad kernel: col 0/1/2 = dov split into three 16-bit terms, rest 0
-      if (half == 0) {
-        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (F16) {
-          const float x = dv * sDV;
-          a8[0] = __half2float(__float2half_rn(x));
-          a8[1] = __half2float(__float2half_rn(x - a8[0]));
-          a8[2] = (x - a8[0]) - a8[1];
-        } else {
-          a8[0] = __uint_as_float(__float_as_uint(dv) & 0xFFFF0000u);
-          a8[1] = __uint_as_float(__float_as_uint(dv - a8[0]) & 0xFFFF0000u);
-          a8[2] = (dv - a8[0]) - a8[1];
-        }
-        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + blob_off<PL>(2, r, 0)), pack8f<F16>(a8));
-        __stcs(reinterpret_cast<uint4*>(blob_aux<PL>(nt) + blob_off<PL>(2, r, 1)), make_uint4(0u, 0u, 0u, 0u));
-      }
-      // ---- prologue: xt -> activation buffer; zp, zd -> workspace (each half takes 4 of the 8 column groups) ----
-      t_mark = clock64();
-#pragma unroll 1
-      for (int it = half * NB; it < half * NB + NB; ++it) {          // 24 columns = 4 frequencies = 3 pieces per iteration
-        float pe[24], xt[24], zp[24];
-        uint4 p6[3][PL];
-#pragma unroll
-        for (int j = 0; j < 24; ++j) pe[j] = ldg_f32_hint(pet + (size_t)(it * 24 + j) * TP, pol_keep);
-#pragma unroll
-        for (int qd = 0; qd < 3; ++qd)
-#pragma unroll
-          for (int p = 0; p < PL; ++p) p6[qd][p] = ldg_v4_hint(pe6 + p * BLOB_C + piece_off(r, it * 3 + qd), pol_keep);
-#pragma unroll
-        for (int j = 0; j < 24; ++j) {
-          const int J = it * 24 + j;                                  // it*24 is a multiple of 6: partner stays inside the block
-          const int jp = DPE_PARTNER(j);
-          xt[j] = dd[j % 3] * (DPE_SIGN(j) * w.band[J / 6]) * pe[jp];
-          zp[j] = fmaf(dv, pe[j], xt[j]);
-          if (F16) { xt[j] *= sp; zp[j] *= sZP; }
-        }
-#pragma unroll
-        for (int qd = 0; qd < 3; ++qd) {
-          const uint32_t off = piece_off(r, it * 3 + qd), goff = blob_off<PL>(24, r, it * 3 + qd);
-          if (tangent) sts8<PL, F16>(act, BLOB_H, off, xt + qd * 8);
-          stg8<PL, F16>(blob_zp<PL>(nt), BLOB_C, goff, zp + qd * 8);
-          float d6[8];
-          unpack_planes<PL, F16>(p6[qd], d6);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d6[e] *= F16 ? dv * (sZD / S_PE) : dv;
-          stg8<PL, F16>(blob_zd<PL>(nt), BLOB_C, goff, d6);
-        }
-      }
-      if (tangent) { epi_done(&pipe); t_comp += clock64() - t_mark; }
-      // ---- epilogue 7: ht = acc*m1, zh = dv*h1 + ht ;  8: ct = acc, zc = dv*c + ct ;  9: gz = dv*g + acc*m3 ----
-#pragma unroll 1
-      for (int st = 0; st < 3; ++st) {
-        const uint8_t* src = blob_h<PL>(nt, st == 0 ? B_H1 : (st == 1 ? B_CC : B_GG));
-        uint8_t* dst = blob_h<PL>(nt, st == 0 ? B_ZH : B_ZC);
-        uint4 nxt[4][PL];
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd)
-#pragma unroll
-          for (int p = 0; p < PL; ++p) nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + blob_off<PL>(32, r, c0 * 4 + qd)));
-        // FOLD: G8 and G9 were issued together; the st = 2 phase finds its accumulator (columns 256..511) already complete
-        if (tangent && !(Geo<PL>::FOLD && st == 2)) { mbar_wait_t(&pipe.acc_ready, ar & 1, t_acc); ++ar; tc_fence_after(); }
-        t_mark = clock64();
-        auto process = [&](const int cb, float (&v)[32]) {
-          const int cg = c0 + cb;
-          uint4 cur[4][PL];
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd)
-#pragma unroll
-            for (int p = 0; p < PL; ++p) cur[qd][p] = nxt[qd][p];
-          if (cb < NB - 1) {
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd)
-#pragma unroll
-              for (int p = 0; p < PL; ++p)
-                nxt[qd][p] = __ldcs(reinterpret_cast<const uint4*>(src + p * BLOB_H + blob_off<PL>(32, r, (cg + 1) * 4 + qd)));
-          }
-          float z[32];
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            float s[8];
-            unpack_planes<PL, F16>(cur[qd], s);
-            const float is = st == 0 ? iH1 : (st == 1 ? iC : iG);       // stored tile -> true values
-            const float iw = st == 0 ? iW1 : (st == 1 ? iW2 : iWa);     // accumulator -> (tangent row x sp)
-            const float sz = st == 0 ? sZH : sZC;
-            float zs[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float t = F16 ? v[qd * 8 + e] * iw : v[qd * 8 + e];
-              if (st != 1) t = s[e] > 0.f ? t : 0.f;                  // relu masks m1 (h1 > 0) / m3 (g > 0)
-              v[qd * 8 + e] = t;                                      // next A operand, still carrying sp
-              z[qd * 8 + e] = F16 ? fmaf(dv, s[e] * is, t * isp) : fmaf(dv, s[e], t);
-              zs[e] = F16 ? z[qd * 8 + e] * sz : z[qd * 8 + e];
-            }
-            const uint32_t off = piece_off(r, cg * 4 + qd);
-            if (st < 2) stg8<PL, F16>(dst, BLOB_H, blob_off<PL>(32, r, cg * 4 + qd), zs);
-            if (tangent && (st == 0 || (st == 1 && !Geo<PL>::FOLD))) sts8<PL, F16>(act, BLOB_H, off, v + qd * 8);   // FOLD: ct is no A operand
-          }
-          if (st >= 1) {                                              // column sums: zc -> vc, gz -> vg, dov*m3 -> sm3
-            const float cs = warp_colsum32(z, lane);
-            atomicAdd(csum + (st - 1) * H + cg * 32 + lane, cs);
-            if (st == 2 && PL == 1) {                                 // split modes: dba comes from the seed-tile MMA of wgrad2_kernel
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                float s[8];
-                unpack8f<F16>(cur[qd][0], s);                          // sign of the hi plane = sign of the value
-#pragma unroll
-                for (int e = 0; e < 8; ++e) z[qd * 8 + e] = s[e] > 0.f ? dv : 0.f;
-              }
-              const float c3 = warp_colsum32(z, lane);
-              atomicAdd(csum + 2 * H + cg * 32 + lane, c3);
-            }
-          }
-        };
-        if (tangent) {
-          tmem_blocks<NB>(tl_addr + ((Geo<PL>::FOLD && st == 2) ? 256u : 0u), process);
-        } else {
-#pragma unroll 1
-          for (int cb = 0; cb < NB; ++cb) {
-            float v0[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v0[j] = 0.f;
-            process(cb, v0);
-          }
-        }
-        if (tangent && (st == 0 || (st == 1 && !Geo<PL>::FOLD))) epi_done(&pipe);
-        t_comp += clock64() - t_mark;
-      }
-      // ---- flush this net's column sums ----
-      if (half == 0) {
-        float sd = dv;
-#pragma unroll
-        for (int m = 16; m; m >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, m);
-        if (lane == 0) atomicAdd(csum + 3 * H, sd);
-      }
-      epi_bar<PL>();
-      for (int i = tid; i < (PL == 1 ? 3 : 2) * H; i += Geo<PL>::ET) {
-        const int qn = i / H, j = i % H;
-        float* dstv = qn == 0 ? w.vc : (qn == 1 ? w.vg : w.sm3);
-        atomicAdd(dstv + (size_t)k * H + j, csum[i]);
-        csum[i] = 0.f;
-      }
-      if (tid == 0) { atomicAdd(w.sdo + k, csum[3 * H]); csum[3 * H] = 0.f; }
-      epi_bar<PL>();
-    }
-    if (w.phase_dbg && tid == 0) {
-      atomicAdd((unsigned long long*)w.phase_dbg + 12, (unsigned long long)(clock64() - t_begin));
-      atomicAdd((unsigned long long*)w.phase_dbg + 13, (unsigned long long)t_acc);
-      atomicAdd((unsigned long long*)w.phase_dbg + 15, (unsigned long long)t_comp);
-      atomicAdd((unsigned long long*)w.phase_dbg + 14, 1ull);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (CLUSTER > 1) cluster_sync_all();              // nobody leaves while a peer may still multicast into its smem / barriers
-  if (warp == Geo<PL>::W_MMA) { if (PAIR) tmem_dealloc_pair(tmem, Geo<PL>::TMEM_COLS); else tmem_dealloc(tmem, Geo<PL>::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1586,14 +782,18 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<PL>::THREA
 // the next net's prologue follows in the same threads.  7 x 16 KB weight ring.
 // ------------------------------------------------------------------------------------------------
 namespace p2z {
-constexpr int NS = 7;
-constexpr int W_BYTES = 2 * STAGE_BYTES;         // one K = 16 chunk of a [256 x K] image: hi 8 KB | lo 8 KB
-constexpr int ZD_BYTES = 2 * BLOB_C;             // zd staging: plane hi | plane lo, [128 x 192] each, layout (*)
 enum { V2_B1 = 0, V2_BSUM, NV2 };
-constexpr int SMEM = NS * W_BYTES + ZD_BYTES + NV2 * H * 4 + H * 4 + 16;          // + column sums of zc + sum of dov
+constexpr int NS_MAX = 14;
+template <int PL>
+struct Cfg {
+  static constexpr int NS = PL == 2 ? 7 : 14;
+  static constexpr int W_BYTES = PL * STAGE_BYTES;       // one K = 16 chunk of a [256 x K] image: 8 KB per plane, hi | lo
+  static constexpr int ZD_BYTES = PL * BLOB_C;           // zd staging: one [128 x 192] tile per plane, layout (*)
+  static constexpr int SMEM = NS * W_BYTES + ZD_BYTES + NV2 * H * 4 + H * 4 + 16;        // + column sums of zc + sum of dov
+};
 constexpr uint32_t REGION = 256, ZP_LO = 96;   // TMEM: regions R0 | R1; zp planes inside R1: hi [0,96) | lo [96,192)
 struct PipeZ {
-  uint64_t full[NS], empty[NS];
+  uint64_t full[NS_MAX], empty[NS_MAX];
   uint64_t blk[4];          // block i of both column halves of the next A operand is in tensor memory (one arrival per epilogue warp)
   uint64_t acc_ready[2];    // the GEMM accumulating into region 0 / 1 has completed
   uint32_t tmem_base;
@@ -1601,24 +801,24 @@ struct PipeZ {
 // K-chunks of zp (K = 192) complete after prologue iteration i of both halves: a half writes 24 columns = 1.5 chunks per iteration
 __host__ __device__ constexpr int zp_first(int i) { return i == 0 ? 0 : i == 1 ? 1 : i == 2 ? 3 : 4; }
 __host__ __device__ constexpr int zp_count(int i) { return (i & 1) ? 2 : 1; }
-static_assert(SMEM + (int)sizeof(PipeZ) + 1024 <= 227 * 1024, "pass2z_kernel: ring + zd tile + vectors must fit one SM's 227 KB");
+static_assert(Cfg<2>::SMEM + (int)sizeof(PipeZ) + 1024 <= 227 * 1024 && Cfg<1>::SMEM <= Cfg<2>::SMEM, "pass2z_kernel: ring + zd tile + vectors must fit one SM's 227 KB");
 }  // namespace p2z
 
-template <bool F16>
+template <int PL, bool F16>
 __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREADS, 1) pass2z_kernel(const Work w) {
-  constexpr int PL = 2;
+  using PZ = p2z::Cfg<PL>;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ p2z::PipeZ pipe;
   uint8_t* ring = smem;
-  uint8_t* zdt = smem + p2z::NS * p2z::W_BYTES;
-  float* svec = reinterpret_cast<float*>(zdt + p2z::ZD_BYTES);
+  uint8_t* zdt = smem + PZ::NS * PZ::W_BYTES;
+  float* svec = reinterpret_cast<float*>(zdt + PZ::ZD_BYTES);
   float* csum = svec + p2z::NV2 * H;                               // [H] + sdo
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int b = blockIdx.x / w.T, tl = blockIdx.x % w.T;
   const size_t g = blockIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < p2z::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
+    for (int s = 0; s < PZ::NS; ++s) { mbar_init(&pipe.full[s], 1); mbar_init(&pipe.empty[s], CLUSTER); }
     for (int i = 0; i < 4; ++i) mbar_init(&pipe.blk[i], Geo<PL>::EW);
     mbar_init(&pipe.acc_ready[0], 1); mbar_init(&pipe.acc_ready[1], 1);
     fence_barrier_init();
@@ -1639,16 +839,16 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     auto put = [&](const uint8_t* wsrc) {
       mbar_wait(&pipe.empty[s], ph ^ 1);
       if (elect_one()) {
-        uint8_t* stg = ring + s * p2z::W_BYTES;
-        mbar_arrive_expect_tx(&pipe.full[s], p2z::W_BYTES);
+        uint8_t* stg = ring + s * PZ::W_BYTES;
+        mbar_arrive_expect_tx(&pipe.full[s], PZ::W_BYTES);
         if (CLUSTER == 1) {
-          bulk_g2s_hint(stg, wsrc, p2z::W_BYTES, &pipe.full[s], pol);
+          bulk_g2s_hint(stg, wsrc, PZ::W_BYTES, &pipe.full[s], pol);
         } else {
-          constexpr uint32_t slice = p2z::W_BYTES / CLUSTER;
+          constexpr uint32_t slice = PZ::W_BYTES / CLUSTER;
           bulk_g2s_mc_hint(stg + rank * slice, wsrc + rank * slice, slice, &pipe.full[s], MC_MASK, pol);
         }
       }
-      if (++s == p2z::NS) { s = 0; ph ^= 1; }
+      if (++s == PZ::NS) { s = 0; ph ^= 1; }
     };
     for (int k = 0; k < w.Kn; ++k) {
       const uint8_t* gen = w.img_gen + ((size_t)b * w.Kn + k) * Geo<PL>::GEN;
@@ -1657,9 +857,9 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
       // the MMA warp's order: G7' in prologue-block order | zd Wd^T (no dependence on an epilogue) | G8' in block order
       for (int i = 0; i < 4; ++i)
         for (int h = 0; h < 2; ++h)
-          for (int j = 0; j < p2z::zp_count(i); ++j) put(iW1 + (size_t)(6 * h + p2z::zp_first(i) + j) * p2z::W_BYTES);
-      for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * p2z::W_BYTES);
-      for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * p2z::W_BYTES);
+          for (int j = 0; j < p2z::zp_count(i); ++j) put(iW1 + (size_t)(6 * h + p2z::zp_first(i) + j) * PZ::W_BYTES);
+      for (int c = 0; c < 12; ++c) put(iWd + (size_t)c * PZ::W_BYTES);
+      for (int i = 0; i < 16; ++i) put(iW2 + (size_t)ts::block_order(i) * PZ::W_BYTES);
     }
   } else if (warp == Geo<PL>::W_MMA) {
     // ---------------- MMA issuer ----------------
@@ -1677,21 +877,24 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
     auto chunk = [&](const uint32_t d, const bool a_in_tmem, const uint32_t a_hi, const uint32_t a_lo, const int zc, const uint32_t first) {
       if (timed) mbar_wait_t(&pipe.full[s], ph, t_full); else mbar_wait(&pipe.full[s], ph);
       tc_fence_after();
-      const uint64_t bd = b_base + s * (uint32_t)(p2z::W_BYTES >> 4), bl = bd + b_lo;
+      const uint64_t bd = b_base + s * (uint32_t)(PZ::W_BYTES >> 4), bl = bd + b_lo;
       if (elect_one()) {
         if (a_in_tmem) {
-          mma_ts(d, a_lo, bd, idesc, first);
-          mma_ts(d, a_hi, bl, idesc, 1u);
-          mma_ts(d, a_hi, bd, idesc, 1u);
+          if (PL == 2) { mma_ts(d, a_lo, bd, idesc, first); mma_ts(d, a_hi, bl, idesc, 1u); }
+          mma_ts(d, a_hi, bd, idesc, PL == 2 ? 1u : first);
         } else {
           const uint64_t ad = zd_base + (uint32_t)zc * zd_step, al = ad + zd_lo;
-          mma_bf16(d, al, bd, idesc, first);
-          mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
-          mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
+          if (PL == 2) {
+            mma_bf16(d, al, bd, idesc, first);
+            mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(d, ad, bl, idesc, 1u);
+            mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(d, ad, bd, idesc, 1u);
+          } else {
+            mma_bf16(d, ad, bd, idesc, first);
+          }
         }
         if (CLUSTER == 1) mma_commit(&pipe.empty[s]); else mma_commit_mc(&pipe.empty[s], MC_MASK);
       }
-      if (++s == p2z::NS) { s = 0; ph ^= 1; }
+      if (++s == PZ::NS) { s = 0; ph ^= 1; }
     };
     auto wait_blk = [&](const int i) { if (timed) mbar_wait_t(&pipe.blk[i], bp, t_epi); else mbar_wait(&pipe.blk[i], bp); tc_fence_after(); };
     // K = 256 GEMM whose A operand is region a, converted in place by the running epilogue
@@ -1759,13 +962,13 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
         if (blob) {
           const uint32_t off = gp_off(32, r, cg * 4 + qd);
           __stcs(reinterpret_cast<uint4*>(blob + off), pq[0]);
-          __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[1]);
+          if (PL == 2) __stcs(reinterpret_cast<uint4*>(blob + BLOB_H + off), pq[PL - 1]);
         }
         hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
-        lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
+        lo[qd * 4 + 0] = pq[PL - 1].x; lo[qd * 4 + 1] = pq[PL - 1].y; lo[qd * 4 + 2] = pq[PL - 1].z; lo[qd * 4 + 3] = pq[PL - 1].w;
       }
       tmem_st16(blk_addr, hi);                                         // in place: the planes replace the accumulator block they came from
-      tmem_st16(blk_addr + 16, lo);
+      if (PL == 2) tmem_st16(blk_addr + 16, lo);
     };
     for (int i = tid; i < H + 4; i += Geo<PL>::ET) csum[i] = 0.f;
     for (int k = 0; k < w.Kn; ++k) {
@@ -1854,23 +1057,23 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           split8<PL, F16>(zp + qd * 8, pq);
           const uint32_t goff = gp_off(24, r, it * 3 + qd);
           __stcs(reinterpret_cast<uint4*>(blob_zp<PL>(nt) + goff), pq[0]);
-          __stcs(reinterpret_cast<uint4*>(blob_zp<PL>(nt) + BLOB_C + goff), pq[1]);
+          if (PL == 2) __stcs(reinterpret_cast<uint4*>(blob_zp<PL>(nt) + BLOB_C + goff), pq[PL - 1]);
           hi[qd * 4 + 0] = pq[0].x; hi[qd * 4 + 1] = pq[0].y; hi[qd * 4 + 2] = pq[0].z; hi[qd * 4 + 3] = pq[0].w;
-          lo[qd * 4 + 0] = pq[1].x; lo[qd * 4 + 1] = pq[1].y; lo[qd * 4 + 2] = pq[1].z; lo[qd * 4 + 3] = pq[1].w;
+          lo[qd * 4 + 0] = pq[PL - 1].x; lo[qd * 4 + 1] = pq[PL - 1].y; lo[qd * 4 + 2] = pq[PL - 1].z; lo[qd * 4 + 3] = pq[PL - 1].w;
           float d6[8], da[8];
           unpack_planes<PL, F16>(p6[qd], d6);
 #pragma unroll
           for (int e = 0; e < 8; ++e) { da[e] = F16 ? d6[e] * (dv * (sZDa / S_PE)) : d6[e] * dv; d6[e] *= F16 ? dv * (sZD / S_PE) : dv; }
           split8<PL, F16>(d6, pq);
           __stcs(reinterpret_cast<uint4*>(blob_zd<PL>(nt) + goff), pq[0]);
-          __stcs(reinterpret_cast<uint4*>(blob_zd<PL>(nt) + BLOB_C + goff), pq[1]);
-          if (F16) split8<PL, F16>(da, pq);                           // (bf16x3: no scales, the same planes serve both)
+          if (PL == 2) __stcs(reinterpret_cast<uint4*>(blob_zd<PL>(nt) + BLOB_C + goff), pq[PL - 1]);
+          if (F16) split8<PL, F16>(da, pq);                           // (bf16 / bf16x3: no scales, the same planes serve both)
           const uint32_t soff = piece_off(r, it * 3 + qd);
           *reinterpret_cast<uint4*>(zdt + soff) = pq[0];
-          *reinterpret_cast<uint4*>(zdt + BLOB_C + soff) = pq[1];
+          if (PL == 2) *reinterpret_cast<uint4*>(zdt + BLOB_C + soff) = pq[PL - 1];
         }
         tmem_st8(R1 + it * 12, hi); tmem_st4(R1 + it * 12 + 8, hi + 8);
-        tmem_st8(R1 + p2z::ZP_LO + it * 12, lo); tmem_st4(R1 + p2z::ZP_LO + it * 12 + 8, lo + 8);
+        if (PL == 2) { tmem_st8(R1 + p2z::ZP_LO + it * 12, lo); tmem_st4(R1 + p2z::ZP_LO + it * 12 + 8, lo + 8); }
         blk_done(it - half * NB);
       }
       if (timed) t_pro += clock64() - t_p0;
@@ -1921,7 +1124,7 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
           split8<PL, F16>(v + qd * 8, pq);
           const uint32_t off = gp_off(32, r, cg * 4 + qd);
           __stcs(reinterpret_cast<uint4*>(blob_h<PL>(nt, B_ZC) + off), pq[0]);
-          __stcs(reinterpret_cast<uint4*>(blob_h<PL>(nt, B_ZC) + BLOB_H + off), pq[1]);
+          if (PL == 2) __stcs(reinterpret_cast<uint4*>(blob_h<PL>(nt, B_ZC) + BLOB_H + off), pq[PL - 1]);
         }
         const float cs = warp_colsum32(z, lane);
         atomicAdd(csum + cg * 32 + lane, cs * inv_sZC);
@@ -1957,12 +1160,6 @@ __global__ void __cluster_dims__(CLUSTER, 1, 1) __launch_bounds__(Geo<2>::THREAD
 }
 
 // ------------------------------------------------------------------------------------------------
-// Weight gradients: D[out-half (128 lanes) x in (N cols)] += sum over points  J[p,out] Z[p,in]
-// Both operands are MN-major views of the stored [128 points x width] blobs.  One CTA per
-// (sample, net, layer, out-half, split); single smem stage, 2 CTAs per SM interleave load and MMA.
-// The two N = 192 layers have 64 spare TMEM columns: an extra N = 16 MMA against the seed tile (hi/lo of dov)
-// yields the dov-weighted column sums of their J operand = the bias gradients db1 (J = qm) and db2 (J = y).
-// ------------------------------------------------------------------------------------------------
 struct WgradWork {
   int B, Kn, T, splits;
   const uint8_t* blobs;
@@ -1973,138 +1170,6 @@ struct WgradWork {
   float *gW1, *gW2, *gWa, *gWd;
   float *gb1, *gb2, *ge, *gbd, *gba;
 };
-
-template <int PL> constexpr int smem_wgrad() { return PL * (BLOB_H / 2 + BLOB_H) + AUX_BYTES; }   // 102400 / 200704
-
-template <int PL, bool F16>
-__global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const WgradWork w) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full, empty, acc_ready;
-  __shared__ uint32_t tmem_s;
-  uint8_t* sJ = smem;                          // PL x 32 KB: 128 points x 128 out (half), plane p at p * 32 KB
-  uint8_t* sZ = smem + PL * (BLOB_H / 2);      // PL x up to 64 KB, plane p at p * zbytes
-  uint8_t* sX = smem + PL * (BLOB_H / 2 + BLOB_H);   // 4 KB seed tile
-  const int tid = threadIdx.x;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);            // warp-uniform: the loader / issuer warps run with all lanes, one elected lane issues
-  int item = blockIdx.x;
-  const int split = item % w.splits; item /= w.splits;
-  const int mh = item & 1; item >>= 1;
-  const int layer = item & 3; item >>= 2;
-  const int k = item % w.Kn, b = item / w.Kn;
-  const int Nn = (layer == 0 || layer == 3) ? C : H;
-  const bool aux = Nn == C;
-  const uint32_t zbytes = (uint32_t)TP * Nn * 2;
-  const int jsel = layer == 0 ? B_QM : (layer == 2 ? B_UM : B_YT);
-  const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
-  if (tid == 0) {
-    mbar_init(&full, 1); mbar_init(&empty, 1); mbar_init(&acc_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 5) tmem_alloc(&tmem_s, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_s;
-  if (t1 > t0) {
-    if (warp == 4) {
-      for (int t = t0; t < t1; ++t) {
-        const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
-        const uint8_t* zsrc = layer == 0 ? nt + (size_t)NBLOB_H * Geo<PL>::BH
-                            : layer == 3 ? nt + (size_t)NBLOB_H * Geo<PL>::BH + Geo<PL>::BC
-                            : nt + (size_t)(layer == 1 ? B_ZH : B_ZC) * Geo<PL>::BH;
-        const uint32_t i = t - t0;
-        mbar_wait(&empty, (i & 1) ^ 1);
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&full, PL * (BLOB_H / 2 + zbytes) + (aux ? AUX_BYTES : 0));
-#pragma unroll
-          for (int p = 0; p < PL; ++p)
-            bulk_g2s(sJ + p * (BLOB_H / 2), nt + (size_t)jsel * Geo<PL>::BH + (size_t)p * BLOB_H + (size_t)mh * (BLOB_H / 2), BLOB_H / 2, &full);
-          bulk_g2s(sZ, zsrc, PL * zbytes, &full);                        // the planes of a tile are contiguous
-          if (aux) bulk_g2s(sX, nt + (size_t)NBLOB_H * Geo<PL>::BH + 2 * Geo<PL>::BC, AUX_BYTES, &full);
-        }
-      }
-    } else if (warp == 5) {
-      const uint32_t idesc = idesc_16(F16, Nn, 1, 1), idesc_x = idesc_16(F16, 16, 1, 1);
-      // descriptors once; a K = 16-point step adds 256 bytes (>> 4) to the address field
-      const uint64_t a_hi = smem_desc(smem_u32(sJ), 128, CORE_STRIDE), b_hi = smem_desc(smem_u32(sZ), 128, CORE_STRIDE);
-      const uint64_t x_d = smem_desc(smem_u32(sX), 128, CORE_STRIDE);
-      const uint32_t a_lo = (BLOB_H / 2) >> 4, b_lo = zbytes >> 4;
-      for (int t = t0; t < t1; ++t) {
-        const uint32_t i = t - t0;
-        mbar_wait(&full, i & 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {                              // 16 points per MMA
-            const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
-            const uint64_t ad = a_hi + ks * 16, bd = b_hi + ks * 16;
-            const uint64_t xd = x_d + ks * 16;
-            if (PL == 2 && REUSE_A) {                      // every J plane is fetched once per step for all MMAs that read it
-              if (aux) {
-                mma_f16_c<A_FILL>(tmem, ad + a_lo, bd, idesc, first);
-                mma_f16_c<A_LAST>(tmem + C, ad + a_lo, xd, idesc_x, first);
-                mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
-                mma_f16_c<A_USE>(tmem, ad, bd, idesc, 1u);
-                mma_f16_c<A_LAST>(tmem + C, ad, xd, idesc_x, 1u);
-              } else {
-                mma_bf16(tmem, ad + a_lo, bd, idesc, first);
-                mma_f16_c<A_FILL>(tmem, ad, bd + b_lo, idesc, 1u);
-                mma_f16_c<A_LAST>(tmem, ad, bd, idesc, 1u);
-              }
-            } else if (PL == 2) {
-              mma_bf16(tmem, ad + a_lo, bd, idesc, first);
-              mma_bf16(tmem, ad, bd + b_lo, idesc, 1u);
-              mma_bf16(tmem, ad, bd, idesc, 1u);
-              if (aux) { mma_bf16(tmem + C, ad, xd, idesc_x, first); mma_bf16(tmem + C, ad + a_lo, xd, idesc_x, 1u); }
-            } else {
-              if (aux) { mma_f16_c<REUSE_A ? A_FILL : A_DISCARD>(tmem, ad, bd, idesc, first); mma_f16_c<REUSE_A ? A_LAST : A_DISCARD>(tmem + C, ad, xd, idesc_x, first); }
-              else mma_bf16(tmem, ad, bd, idesc, first);
-            }
-          }
-          mma_commit(&empty);
-        }
-      }
-      if (elect_one()) mma_commit(&acc_ready);
-    } else if (warp < 4) {
-      mbar_wait(&acc_ready, 0);
-      tc_fence_after();
-      const size_t gk = ((size_t)b * w.Kn + k);
-      float* dst = layer == 0 ? w.gW1 + gk * H * C
-                 : layer == 1 ? w.gW2 + gk * H * H
-                 : layer == 2 ? w.gWa + (size_t)k * H * H
-                 : w.gWd + (size_t)k * H * C;
-      dst += (size_t)(mh * TP + tid) * Nn;
-      float un = 1.f, un_x = 1.f;                                      // fp16 variant: undo (J tile scale) x (Z tile / seed scale)
-      if (F16) {
-        const NetScales t = w.sc[gk];
-        const float sj = layer == 0 ? t.sQ : (layer == 2 ? t.sUM : t.sY);
-        const float sz = layer == 0 ? t.sZP : (layer == 1 ? t.sZH : (layer == 2 ? t.sZC : t.sZD));
-        un = (1.f / sj) * (1.f / sz); un_x = (1.f / sj) * (1.f / t.sDV);      // separately: sj * sz may leave the fp32 range
-      }
-      float v[32];
-      for (int cb = 0; cb < Nn / 32; ++cb) {
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + cb * 32 + j, F16 ? v[j] * un : v[j]);
-      }
-      if (aux) {
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + C, v);
-        const float bsum = (v[0] + v[1] + v[2]) * un_x;                // the three 16-bit terms of the seed
-        const int out = mh * TP + tid;
-        if (layer == 0) {
-          atomicAdd(w.gb1 + gk * H + out, bsum);
-        } else {
-          atomicAdd(w.gb2 + gk * H + out, bsum);
-          atomicAdd(w.ge + gk * H + out, bsum);
-          atomicAdd(w.gbd + (size_t)k * H + out, bsum);
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
-}
 
 // ------------------------------------------------------------------------------------------------
 // Weight gradients of the split modes: same contraction, restructured around what limited wgrad_kernel<2> (one 200 KB stage per SM:
@@ -2127,25 +1192,29 @@ __global__ void __launch_bounds__(192, Geo<PL>::CTAS_PER_SM) wgrad_kernel(const 
 // ------------------------------------------------------------------------------------------------
 namespace wg2 {
 constexpr int PT = 32;                              // points per stage
-constexpr int NSTG = 3;
 constexpr int J_PLANE = PT * 128 * 2;               // 8192: [16 k-cores of this out-half][32][16 B]
 constexpr int ZH_PLANE = PT * H * 2;                // 16384
 constexpr int ZC_PLANE = PT * C * 2;                // 12288
 constexpr int X_BYTES = PT * 16 * 2;                // 1024 seed tile
-constexpr int OFF_Z1 = 2 * J_PLANE, OFF_Z2 = OFF_Z1 + 2 * ZH_PLANE, OFF_X = OFF_Z2 + 2 * ZC_PLANE;
-constexpr int STAGE = OFF_X + X_BYTES;              // 74752
-constexpr int SMEM = NSTG * STAGE;                  // 224256
 constexpr int ROW_PAD = 16;                         // bytes between staged output rows: 1040-byte pitch -> conflict-free 16-byte stores
 constexpr int ITEMS = 3;                            // work-item kinds per (sample, net)
-static_assert(128 * (H * 4 + ROW_PAD) <= SMEM, "the staged [128 x 256] fp32 output must fit the (idle) stages");
-static_assert(SMEM + 1024 <= 227 * 1024, "three stages must fit one SM's 227 KB");
+constexpr int NSTG_MAX = 5;
+template <int PL>
+struct Cfg {                                        // stage = J planes | Z1 planes (zp / zh / zc) | Z2 planes (zd) | seed tile
+  static constexpr int NSTG = PL == 2 ? 3 : 5;
+  static constexpr int OFF_Z1 = PL * J_PLANE, OFF_Z2 = OFF_Z1 + PL * ZH_PLANE, OFF_X = OFF_Z2 + PL * ZC_PLANE;
+  static constexpr int STAGE = OFF_X + X_BYTES;     // 74752 / 37888
+  static constexpr int SMEM = NSTG * STAGE;         // 224256 / 189440
+  static_assert(128 * (H * 4 + ROW_PAD) <= SMEM, "the staged [128 x 256] fp32 output must fit the (idle) stages");
+  static_assert(SMEM + 1024 <= 227 * 1024, "the stages must fit one SM's 227 KB");
+};
 }  // namespace wg2
 
-template <bool F16>
+template <int PL, bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kernel(const WgradWork w) {
-  constexpr int PL = 2;
+  using WG = wg2::Cfg<PL>;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t full[wg2::NSTG], empty[wg2::NSTG], acc_ready;
+  __shared__ uint64_t full[wg2::NSTG_MAX], empty[wg2::NSTG_MAX], acc_ready;
   __shared__ uint32_t tmem_s;
   const int tid = threadIdx.x;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -2162,7 +1231,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
   const int t0 = (int)((long long)w.T * split / w.splits), t1 = (int)((long long)w.T * (split + 1) / w.splits);
   const int nst = 4 * (t1 - t0);                                      // quarter-tiles
   if (tid == 0) {
-    for (int s = 0; s < wg2::NSTG; ++s) { mbar_init(&full[s], build_j ? 129 : 1); mbar_init(&empty[s], 2); }
+    for (int s = 0; s < WG::NSTG; ++s) { mbar_init(&full[s], build_j ? 129 : 1); mbar_init(&empty[s], 2); }
     mbar_init(&acc_ready, 1);
     fence_barrier_init();
   }
@@ -2183,19 +1252,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
         const uint32_t z1stride = kind == 0 ? BLOB_C : BLOB_H;          // plane stride of the Z1 tile in the workspace
         const uint8_t* z2src = nt + off_zd<PL>() + (size_t)pq * wg2::ZC_PLANE;
         const uint8_t* xsrc = nt + off_aux<PL>() + (size_t)pq * wg2::X_BYTES;
-        const int s = i % wg2::NSTG;
-        uint8_t* st = smem + s * wg2::STAGE;
-        mbar_wait(&empty[s], ((i / wg2::NSTG) & 1) ^ 1);              // BOTH CTAs are done with the previous occupant (multicast commits)
+        const int s = i % WG::NSTG;
+        uint8_t* st = smem + s * WG::STAGE;
+        mbar_wait(&empty[s], ((i / WG::NSTG) & 1) ^ 1);              // BOTH CTAs are done with the previous occupant (multicast commits)
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], (build_j ? 0 : 2 * wg2::J_PLANE) + 2 * z1plane + (two ? 2 * wg2::ZC_PLANE : 0) + wg2::X_BYTES);
+          mbar_arrive_expect_tx(&full[s], (build_j ? 0 : PL * wg2::J_PLANE) + PL * z1plane + (two ? PL * wg2::ZC_PLANE : 0) + wg2::X_BYTES);
           const uint32_t zh = z1plane / 2, z2h = wg2::ZC_PLANE / 2, xh = wg2::X_BYTES / 2;
 #pragma unroll
           for (int p = 0; p < PL; ++p) {
             if (!build_j) bulk_g2s(st + p * wg2::J_PLANE, jsrc + (size_t)p * BLOB_H, wg2::J_PLANE, &full[s]);
-            bulk_g2s_mc(st + wg2::OFF_Z1 + p * wg2::ZH_PLANE + mh * zh, z1src + (size_t)p * z1stride + mh * zh, zh, &full[s], (uint16_t)3);
-            if (two) bulk_g2s_mc(st + wg2::OFF_Z2 + p * wg2::ZC_PLANE + mh * z2h, z2src + (size_t)p * BLOB_C + mh * z2h, z2h, &full[s], (uint16_t)3);
+            bulk_g2s_mc(st + WG::OFF_Z1 + p * wg2::ZH_PLANE + mh * zh, z1src + (size_t)p * z1stride + mh * zh, zh, &full[s], (uint16_t)3);
+            if (two) bulk_g2s_mc(st + WG::OFF_Z2 + p * wg2::ZC_PLANE + mh * z2h, z2src + (size_t)p * BLOB_C + mh * z2h, z2h, &full[s], (uint16_t)3);
           }
-          bulk_g2s_mc(st + wg2::OFF_X + mh * xh, xsrc + mh * xh, xh, &full[s], (uint16_t)3);
+          bulk_g2s_mc(st + WG::OFF_X + mh * xh, xsrc + mh * xh, xh, &full[s], (uint16_t)3);
         }
       }
     } else if (warp == 5) {
@@ -2205,11 +1274,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
       constexpr uint32_t SBO = wg2::PT * 16;
       constexpr uint32_t a_lo = wg2::J_PLANE >> 4, b1_lo = wg2::ZH_PLANE >> 4, b2_lo = wg2::ZC_PLANE >> 4;
       for (int i = 0; i < nst; ++i) {
-        const int s = i % wg2::NSTG;
-        const uint32_t base = smem_u32(smem + s * wg2::STAGE);
-        const uint64_t a_hi = smem_desc(base, 128, SBO), b1_hi = smem_desc(base + wg2::OFF_Z1, 128, SBO), b2_hi = smem_desc(base + wg2::OFF_Z2, 128, SBO);
-        const uint64_t x_d = smem_desc(base + wg2::OFF_X, 128, SBO);
-        mbar_wait(&full[s], (i / wg2::NSTG) & 1);
+        const int s = i % WG::NSTG;
+        const uint32_t base = smem_u32(smem + s * WG::STAGE);
+        const uint64_t a_hi = smem_desc(base, 128, SBO), b1_hi = smem_desc(base + WG::OFF_Z1, 128, SBO), b2_hi = smem_desc(base + WG::OFF_Z2, 128, SBO);
+        const uint64_t x_d = smem_desc(base + WG::OFF_X, 128, SBO);
+        mbar_wait(&full[s], (i / WG::NSTG) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
@@ -2217,7 +1286,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
             const uint32_t first = (i > 0 || ks > 0) ? 1u : 0u;
             const uint64_t ad = a_hi + ks * 16, b1 = b1_hi + ks * 16, b2 = b2_hi + ks * 16, xd = x_d + ks * 16;
             // every J plane is fetched from shared memory once per step for all MMAs that read it (A collector)
-            if (build_j) {                                   // exact one-plane J (the mask): J Z_lo + J Z_hi + J seeds
+            if (PL == 1) {                                   // one plane per operand: J Z1 (+ J Z2) + J seeds
+              mma_f16_c<A_FILL>(tmem, ad, b1, idesc1, first);
+              if (two) mma_f16_c<A_USE>(tmem + COL_D2, ad, b2, idesc2, first);
+              mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, first);
+            } else if (build_j) {                            // exact one-plane J (the mask): J Z_lo + J Z_hi + J seeds
               mma_f16_c<A_FILL>(tmem, ad, b1 + b1_lo, idesc1, first);
               mma_f16_c<A_USE>(tmem, ad, b1, idesc1, 1u);
               mma_f16_c<A_LAST>(tmem + COL_X, ad, xd, idesc_x, first);
@@ -2247,11 +1320,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
         // J quarter-tile = [16 k-cores][32 points][8 features], one plane: thread = (point, 32-feature group gq): 4 pieces from one mask word
         const int pt = tid & 31, gq = tid >> 5;
         for (int i = 0; i < nst; ++i) {
-          const int t = t0 + (i >> 2), pq = i & 3, s = i % wg2::NSTG;
+          const int t = t0 + (i >> 2), pq = i & 3, s = i % WG::NSTG;
           const uint8_t* nt = w.blobs + (((size_t)b * w.Kn + k) * w.T + t) * Geo<PL>::NET_TILE;
           const uint32_t mw = __ldg(reinterpret_cast<const uint32_t*>(nt + off_mask<PL>() + MASK_BYTES / 2) + (size_t)(pq * wg2::PT + pt) * 8 + mh * 4 + gq);
-          uint8_t* st = smem + s * wg2::STAGE;
-          mbar_wait(&empty[s], ((i / wg2::NSTG) & 1) ^ 1);            // both CTAs' MMAs are done with the previous occupant of the stage
+          uint8_t* st = smem + s * WG::STAGE;
+          mbar_wait(&empty[s], ((i / WG::NSTG) & 1) ^ 1);            // both CTAs' MMAs are done with the previous occupant of the stage
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t bits = (mw >> (j * 8)) & 0xFFu;
@@ -2349,43 +1422,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1) wgrad2_kerne
 // ------------------------------------------------------------------------------------------------
 // SIMT helpers of the tensor-core mode
 // ------------------------------------------------------------------------------------------------
-// ---- FOLD: P = Wa W2 and c2 = 2wo W2 per (sample, net), fp32 on the CUDA cores (0.8 GMAC per call) ---------------------------
-// y = um Wa + 2wo and q = y W2 are consecutive linear maps of the same tile, so q = um P + c2: G4 and G5 can share one round.
-__global__ void __launch_bounds__(256) pfold_kernel(int Kn, const float* __restrict__ Wa, const float* __restrict__ W2,
-                                                    float* __restrict__ P) {
-  __shared__ float sA[32][33], sB[32][33];
-  const int bk = blockIdx.z, k = bk % Kn;
-  const float* A = Wa + (size_t)k * H * H;                     // [j][i]
-  const float* Bm = W2 + (size_t)bk * H * H;                   // [i][l]
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads, 4 rows each
-  const int j0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int i0 = 0; i0 < H; i0 += 32) {
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      sA[ty * 4 + rr][tx] = A[(size_t)(j0 + ty * 4 + rr) * H + i0 + tx];
-      sB[ty * 4 + rr][tx] = Bm[(size_t)(i0 + ty * 4 + rr) * H + l0 + tx];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const float bv = sB[i][tx];
-#pragma unroll
-      for (int rr = 0; rr < 4; ++rr) acc[rr] = fmaf(sA[ty * 4 + rr][i], bv, acc[rr]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int rr = 0; rr < 4; ++rr) P[((size_t)bk * H + j0 + ty * 4 + rr) * H + l0 + tx] = acc[rr];
-}
-__global__ void __launch_bounds__(256) c2_kernel(int Kn, const float* __restrict__ wo2, const float* __restrict__ W2, float* __restrict__ c2) {
-  const int bk = blockIdx.x, k = bk % Kn, l = threadIdx.x;
-  const float* Bm = W2 + (size_t)bk * H * H;
-  float s = 0.f;
-  for (int i = 0; i < H; ++i) s = fmaf(wo2[(size_t)k * H + i], Bm[(size_t)i * H + l], s);
-  c2[(size_t)bk * H + l] = s;
-}
-
 // ---- scaling plan of the fp16 variant -------------------------------------------------------------
 __device__ __forceinline__ float block_max256(float v, float* red) {      // 256 threads; every thread gets the result
 #pragma unroll
@@ -2404,8 +1440,7 @@ __global__ void __launch_bounds__(1024) bounds_kernel(int Kn, const float* __res
                                                      const float* __restrict__ W2, const float* __restrict__ Wd,
                                                      const float* __restrict__ Wa, const float* __restrict__ ba,
                                                      const float* __restrict__ bsum, const float* __restrict__ uvec,
-                                                     const float* __restrict__ wo2, const float* __restrict__ P,
-                                                     NetScales* __restrict__ tab) {
+                                                     const float* __restrict__ wo2, NetScales* __restrict__ tab) {
   __shared__ float red[8];
   __shared__ float srow[8][H];                                       // per matrix row: L1 norm / maximum of W1, Wd, W2, Wa
   // 1024 threads: the block reads ~1.4 MB and one SM's memory-level parallelism is what bounds it (48 blocks on 148 SMs)
@@ -2439,7 +1474,7 @@ __global__ void __launch_bounds__(1024) bounds_kernel(int Kn, const float* __res
     }
   }
   // column-wise L1 norms: thread (part, j) walks down a quarter of column j (coalesced across the block)
-  float c2 = 0.f, ca = 0.f, mp = 0.f;
+  float c2 = 0.f, ca = 0.f;
   for (int i0 = part * 64; i0 < part * 64 + 64; i0 += 16) {          // 32 independent loads in flight per thread
     float t2[16], ta[16];
 #pragma unroll
@@ -2454,13 +1489,10 @@ __global__ void __launch_bounds__(1024) bounds_kernel(int Kn, const float* __res
   ca = (scol[1][0][j] + scol[1][1][j]) + (scol[1][2][j] + scol[1][3][j]);
   const float r1 = srow[0][j], m1 = srow[1][j], rd = srow[2][j], md = srow[3][j];
   const float r2 = srow[4][j], m2 = srow[5][j], ra = srow[6][j], ma = srow[7][j];
-  if (P)
-    for (int i = 0; i < H; ++i) mp = fmaxf(mp, fabsf(P[((size_t)bk * H + j) * H + i]));
   const float l1W1 = block_max256(r1, red), M1 = block_max256(r1 + fabsf(b1[(size_t)bk * H + j]), red);
   const float l1W2 = block_max256(r2, red), l1Wd = block_max256(rd, red), l1Wa = block_max256(ra, red);
   const float cW2 = block_max256(c2, red), cWa = block_max256(ca, red);
   const float mW1 = block_max256(m1, red), mW2 = block_max256(m2, red), mWd = block_max256(md, red), mWa = block_max256(ma, red);
-  const float mP = block_max256(mp, red);
   const float mBs = block_max256(fabsf(bsum[(size_t)bk * H + j]), red), mBa = block_max256(fabsf(ba[(size_t)k * H + j]), red);
   const float Mu = block_max256(fabsf(uvec[(size_t)k * H + j]), red), mWo2 = block_max256(fabsf(wo2[(size_t)k * H + j]), red);
   const float mWaU = block_max256(fabsf(uvec[(size_t)k * H + j]) * ma, red);       // max |u_j Wa_ji|
@@ -2470,7 +1502,6 @@ __global__ void __launch_bounds__(1024) bounds_kernel(int Kn, const float* __res
     const float My = Mu * cWa + mWo2, Mq = My * cW2;
     t.sW1 = scale_for(mW1 * 32.f);                   // weights: maximum -> 2^10
     t.sWa = scale_for(mWa * 32.f);
-    t.sP = scale_for(mP * 32.f);
     t.sWaU = scale_for(mWaU * 32.f);
     t.sWd = scale_for(mWd * 32.f);                   // preliminary: plan_kernel couples sWd, sH1 and sW2
     t.sW2 = scale_for(mW2);                          // preliminary: the LARGEST admissible factor
@@ -2556,18 +1587,16 @@ __global__ void image_kernel(const float* __restrict__ src, size_t src_stride, u
   }
   if (F16) {                                                         // entry blockIdx.y: (sample, net) for generated weights, (0, net) for static ones
     const NetScales& t = tab[blockIdx.y];
-    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : (which == 3 ? t.sWa : (which == 5 ? t.sWaU : t.sP))));
+    const float sc = which == 0 ? t.sW1 : (which == 1 ? t.sW2 : (which == 2 ? t.sWd : (which == 3 ? t.sWa : t.sWaU)));
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] *= sc;
   }
   uint4 pq[PL];
   split8<PL, F16>(v, pq);
-  // chunk = [rows of CTA 0 | rows of CTA 1] (PAIR: each CTA of a pair stages its half of the rows), each part [hi plane | lo plane],
-  // each plane two k-cores of (part rows) x 16 bytes
-  const int prows = PAIR ? rows / 2 : rows, part = r / prows, rr = r % prows;
-  const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)part * PL * prows * 32 + (size_t)(kc & 1) * prows * 16 + (size_t)rr * 16;
+  // chunk = [hi plane | lo plane], each plane two k-cores of rows x 16 bytes
+  const size_t base = (size_t)(kc >> 1) * PL * rows * 32 + (size_t)(kc & 1) * rows * 16 + (size_t)r * 16;
 #pragma unroll
-  for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * prows * 32) = pq[p];
+  for (int p = 0; p < PL; ++p) *reinterpret_cast<uint4*>(D + base + (size_t)p * rows * 32) = pq[p];
 }
 
 // coordinate / data features of one tile: bf16 blobs (GEMM operands) and the fp32 transposed copy (epilogues)
@@ -2637,12 +1666,6 @@ __global__ void __launch_bounds__(TP) encode_kernel(const DevConsts K, const Wor
   }
 }
 
-// gba = u * sum_p dov m3  (the column sum comes from pass 2)
-__global__ void finalize_ba_kernel(int n, const float* __restrict__ uvec, const float* __restrict__ sm3, float* __restrict__ gba) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) gba[i] = uvec[i] * sm3[i];
-}
-
 __global__ void seed_copy_kernel(const Work w, const float* __restrict__ d_o, float scale) {
   // values-only backward: dov[row][k] = d_o[q][k] * scale for valid rows
   const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2669,7 +1692,7 @@ __global__ void gather_o_kernel(const Work w, float* __restrict__ o_out) {
 // ------------------------------------------------------------------------------------------------
 struct Carve {
   uint8_t *img_gen, *img_sta, *pe_blob, *pe6_blob, *blobs;
-  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sm3, *sdo, *P, *c2;
+  float *pet, *o, *od, *dov, *dod, *uvec, *wo2, *cst, *bsum, *vc, *vg, *sdo;
   long long* dbg;
   NetScales* sc;
   int* seedmax;
@@ -2699,10 +1722,7 @@ static Carve carve(uint8_t* base, int chunk, int Kn, int B, int pl) {
   c.bsum = reinterpret_cast<float*>(take((size_t)B * Kn * H * 4));
   c.vc = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.vg = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
-  c.sm3 = reinterpret_cast<float*>(take((size_t)Kn * H * 4));
   c.sdo = reinterpret_cast<float*>(take((size_t)Kn * 4));
-  c.P = reinterpret_cast<float*>(take((size_t)B * Kn * H * H * 4));
-  c.c2 = reinterpret_cast<float*>(take((size_t)B * Kn * H * 4));
   c.dbg = reinterpret_cast<long long*>(take(16 * 8));
   c.sc = reinterpret_cast<NetScales*>(take((size_t)B * Kn * sizeof(NetScales)));
   c.seedmax = reinterpret_cast<int*>(take((size_t)B * Kn * 2 * sizeof(int)));
@@ -2721,8 +1741,8 @@ size_t workspace_bytes(int chunk, int Kn, int B, int planes) { return carve(null
 template <int PL, bool F16>
 static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cudaStream_t st) {
   struct Spec { const float* src; size_t sstride; size_t doff; size_t dstride; int rows, kd, tr, batches; uint8_t* dst; int which; const float* kscale; };
-  // split modes: the transposed Wa image carries u (G4: y = m3 (diag(u) Wa) + 2wo with the bare mask as A operand)
-  const float* ku = PL == 2 ? c.uvec : nullptr;
+  // the transposed Wa image carries u (G4: y = m3 (diag(u) Wa) + 2wo with the bare mask as A operand)
+  const float* ku = c.uvec;
   const Spec specs[] = {
       {Wt.W1, (size_t)H * C, 0, GEN_IMG, H, C, 0, B * Kn, c.img_gen, 0, nullptr},              // W1  : rows = out, k = in
       {Wt.W1, (size_t)H * C, IMG_HC, GEN_IMG, C, H, 1, B * Kn, c.img_gen, 0, nullptr},         // W1T : rows = in,  k = out
@@ -2745,23 +1765,16 @@ static int make_images(const DpnWeights& Wt, const Carve& c, int B, int Kn, cuda
 template <int PL, bool F16>
 static int run_planes(const Job& J, cudaStream_t st) {
   const int B = J.shape.B, N = J.shape.N, Kn = J.shape.K, chunk = J.chunk;
-  const int smem_fused = tc::smem_fused<PL>(), smem_pass2 = tc::smem_pass2<PL>(), smem_wgrad = tc::smem_wgrad<PL>();
   {
     // function attributes are per device: set them once for every device this process drives (bit d of the mask)
     static std::atomic<unsigned long long> attr_done_mask{0ull};
     int dev = 0;
     DPN_CUDA_OK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !((attr_done_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
-      if constexpr (PL == 2) {
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::SMEM));
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass2z_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2z::SMEM));
-        DPN_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::SMEM));
-      } else {
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_pass2));
-        DPN_CUDA_OK(cudaFuncSetAttribute(pass1_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_fused));
-        DPN_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wgrad));
-      }
+      DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<PL, F16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::Cfg<PL>::SMEM));
+      if constexpr (PL == 2) DPN_CUDA_OK(cudaFuncSetAttribute(pass1_ts_kernel<PL, F16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::Cfg<PL>::SMEM));
+      DPN_CUDA_OK(cudaFuncSetAttribute(pass2z_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, p2z::Cfg<PL>::SMEM));
+      DPN_CUDA_OK(cudaFuncSetAttribute(wgrad2_kernel<PL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg2::Cfg<PL>::SMEM));
       if (dev >= 0 && dev < 64) attr_done_mask.fetch_or(1ull << dev, std::memory_order_release);
     }
   }
@@ -2780,14 +1793,8 @@ static int run_planes(const Job& J, cudaStream_t st) {
   constexpr bool phase_debug = false;
 #endif
   if ((rc = f32::launch_prep(B, Kn, Wt, c.uvec, c.wo2, c.cst, c.bsum, st))) return rc;
-  if (Geo<PL>::FOLD) {
-    pfold_kernel<<<dim3(H / 32, H / 32, B * Kn), 256, 0, st>>>(Kn, Wt.Wa, Wt.W2, c.P);
-    DPN_LAUNCH_OK();
-    c2_kernel<<<B * Kn, 256, 0, st>>>(Kn, c.wo2, Wt.W2, c.c2);
-    DPN_LAUNCH_OK();
-  }
   if (F16) {                                                          // scaling plan before anything is converted to fp16
-    bounds_kernel<<<B * Kn, 1024, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, Geo<PL>::FOLD ? c.P : nullptr, c.sc);
+    bounds_kernel<<<B * Kn, 1024, 0, st>>>(Kn, Wt.W1, Wt.b1, Wt.W2, Wt.Wd, Wt.Wa, Wt.ba, c.bsum, c.uvec, c.wo2, c.sc);
     DPN_LAUNCH_OK();
     plan_kernel<<<1, 32, 0, st>>>(B, Kn, c.sc);
     DPN_LAUNCH_OK();
@@ -2809,7 +1816,6 @@ static int run_planes(const Job& J, cudaStream_t st) {
     DPN_CUDA_OK(cudaMemsetAsync(G.ba, 0, (size_t)Kn * H * 4, st));
     DPN_CUDA_OK(cudaMemsetAsync(c.vc, 0, (size_t)Kn * H * 4, st));
     DPN_CUDA_OK(cudaMemsetAsync(c.vg, 0, (size_t)Kn * H * 4, st));
-    DPN_CUDA_OK(cudaMemsetAsync(c.sm3, 0, (size_t)Kn * H * 4, st));
     DPN_CUDA_OK(cudaMemsetAsync(c.sdo, 0, (size_t)Kn * 4, st));
   }
   for (int p0 = 0; p0 < N; p0 += chunk) {
@@ -2820,11 +1826,11 @@ static int run_planes(const Job& J, cudaStream_t st) {
     memset(&w, 0, sizeof(w));
     w.B = B; w.Kn = Kn; w.T = T; w.P = P; w.N = N; w.p0 = p0;
     w.img_gen = c.img_gen; w.img_sta = c.img_sta;
-    w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst; w.c2 = c.c2;
+    w.b1 = Wt.b1; w.bsum = c.bsum; w.ba = Wt.ba; w.uvec = c.uvec; w.wo2 = c.wo2; w.cst = c.cst;
     w.coord_data = J.pts->coord_data; w.ref = J.pts->ref;
     w.pe_blob = c.pe_blob; w.pe6_blob = c.pe6_blob; w.pet = c.pet; w.blobs = c.blobs;
     w.o = c.o; w.od = c.od; w.dov = c.dov; w.dod = c.dod;
-    w.vc = c.vc; w.vg = c.vg; w.sm3 = c.sm3; w.sdo = c.sdo;
+    w.vc = c.vc; w.vg = c.vg; w.sdo = c.sdo;
     w.sc = c.sc;
     w.xfirst = J.shape.mode == DPN_MODE_F16X3A ? 1 : 0;
     w.phase_dbg = phase_debug ? c.dbg : nullptr;
@@ -2835,11 +1841,11 @@ static int run_planes(const Job& J, cudaStream_t st) {
     const int tiles = B * T;
     encode_kernel<PL, F16><<<tiles, TP, 0, st>>>(J.dc, w, J.pts->x, J.pts->y, J.pts->t, J.pts->coord_pe);
     DPN_LAUNCH_OK();
-    if constexpr (PL == 2) {                      // split modes: the A operand lives in tensor memory
-      if (w.xfirst) pass1_ts_kernel<F16, true><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
-      else pass1_ts_kernel<F16, false><<<tiles, Geo<2>::THREADS, ts::SMEM, st>>>(w, sweep);
+    if constexpr (PL == 2) {
+      if (w.xfirst) pass1_ts_kernel<PL, F16, true><<<tiles, Geo<PL>::THREADS, ts::Cfg<PL>::SMEM, st>>>(w, sweep);
+      else pass1_ts_kernel<PL, F16, false><<<tiles, Geo<PL>::THREADS, ts::Cfg<PL>::SMEM, st>>>(w, sweep);
     } else {
-      pass1_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_fused, st>>>(w, sweep);
+      pass1_ts_kernel<PL, F16, false><<<tiles, Geo<PL>::THREADS, ts::Cfg<PL>::SMEM, st>>>(w, sweep);
     }
     DPN_LAUNCH_OK();
     if (J.kind == JOB_DEC_FWD) {
@@ -2873,20 +1879,19 @@ static int run_planes(const Job& J, cudaStream_t st) {
       zscale_kernel<<<(B * Kn + 63) / 64, 64, 0, st>>>(B * Kn, c.seedmax, c.sc);
       DPN_LAUNCH_OK();
     }
-    if constexpr (PL == 2) pass2z_kernel<F16><<<tiles, Geo<2>::THREADS, p2z::SMEM, st>>>(w);
-    else pass2_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, smem_pass2, st>>>(w, pde ? 1 : 0);
+    pass2z_kernel<PL, F16><<<tiles, Geo<PL>::THREADS, p2z::Cfg<PL>::SMEM, st>>>(w);
     DPN_LAUNCH_OK();
     WgradWork ww;
     ww.B = B; ww.Kn = Kn; ww.T = T; ww.blobs = c.blobs; ww.sc = c.sc; ww.uvec = c.uvec;
     ww.Wa = Wt.Wa; ww.ba = Wt.ba; ww.vg = c.vg;
     ww.gW1 = G.W1; ww.gW2 = G.W2; ww.gWa = G.Wa; ww.gWd = G.Wd;
     ww.gb1 = G.b1; ww.gb2 = G.b2; ww.ge = G.e; ww.gbd = G.bd; ww.gba = G.ba;
-    const int items = B * Kn * (PL == 2 ? 2 * wg2::ITEMS : 8);            // x 2 output halves
+    const int items = B * Kn * 2 * wg2::ITEMS;                            // x 2 output halves
     // point-splits per (sample, net, layer, out-half): fill whole waves of resident CTAs (148 SMs x CTAs per SM); every split
     // adds one fp32 red.add pass over the gradient tile, so prefer the smallest count within 2 % of the best wave efficiency
     int splits = 1;
     {
-      const double slots = 148.0 * Geo<PL>::CTAS_PER_SM;
+      const double slots = 148.0;
       double best = 0.0;
       for (int sp = 1; sp <= 8 && sp <= T; ++sp) {
         const double waves = items * sp / slots, eff = waves / ceil(waves);
@@ -2897,11 +1902,10 @@ static int run_planes(const Job& J, cudaStream_t st) {
       // against an fp64 oracle at 65 536 points: 1e-4 with 64 tiles per CTA, 7e-6 with 4).  The split modes therefore flush to the
       // fp32 red.add sums (round-to-nearest) every `wgrad_tiles` tiles (32: 1.7e-5 at no measurable cost; 16: 1.2e-5 for +2 % time).
       static const int wgrad_tiles = getenv("DPN_WGRAD_TILES") ? atoi(getenv("DPN_WGRAD_TILES")) : 32;
-      if (PL == 2 && wgrad_tiles > 0 && (T + splits - 1) / splits > wgrad_tiles) splits = (T + wgrad_tiles - 1) / wgrad_tiles;
+      if (wgrad_tiles > 0 && (T + splits - 1) / splits > wgrad_tiles) splits = (T + wgrad_tiles - 1) / wgrad_tiles;
     }
     ww.splits = splits;
-    if constexpr (PL == 2) wgrad2_kernel<F16><<<items * splits, 192, wg2::SMEM, st>>>(ww);
-    else wgrad_kernel<PL, F16><<<items * splits, 192, smem_wgrad, st>>>(ww);
+    wgrad2_kernel<PL, F16><<<items * splits, 192, wg2::Cfg<PL>::SMEM, st>>>(ww);
     DPN_LAUNCH_OK();
   }
 #ifdef DPN_DEBUG_BUILD
@@ -2918,10 +1922,6 @@ static int run_planes(const Job& J, cudaStream_t st) {
 #endif
   if (want_bwd) {
     if ((rc = f32::launch_finalize(Kn, Wt, c.vc, c.vg, c.sdo, *J.grads, st))) return rc;
-    if (PL == 1) {                                                    // split modes: dba is a seed-tile product of wgrad2_kernel
-      finalize_ba_kernel<<<(Kn * H + 255) / 256, 256, 0, st>>>(Kn * H, c.uvec, c.sm3, J.grads->ba);
-      DPN_LAUNCH_OK();
-    }
   }
   return 0;
 }

@@ -61,14 +61,14 @@ def test_mode_enum_matches_header():
     need = C.c_size_t(0)
     bad = N.DpnShape(B=1, N=128, K=6, mode=max(N.MODES.values()) + 1, n_norm=0, seed_scale=1.0, chunk=0)
     assert N.lib().dpn_workspace_bytes(C.byref(bad), C.byref(need)) != 0
-    # the headline shape runs as one pass in every tensor-core mode; the split modes keep two planes per stored tile but only the
-    # masks of h1 / g, the bf16 mode one plane and the h1 / c / g tiles: same workspace class (16 vs 23 GB)
+    # the headline shape runs as one pass in every tensor-core mode; all of them keep the same tiles (YT QM ZH ZC | ZP ZD | seeds | masks),
+    # the split modes as two 16-bit planes, the bf16 mode as one: 18 vs 9.4 GB
     sizes = {}
     for name, mode in N.MODES.items():
         shp = N.DpnShape(B=8, N=65536, K=6, mode=mode, n_norm=0, seed_scale=0.125, chunk=0)
         assert N.lib().dpn_workspace_bytes(C.byref(shp), C.byref(need)) == 0
         sizes[name] = need.value
-    assert 0.8 < sizes["f16x3"] / sizes["bf16"] < 1.6 and sizes["f16x3"] == sizes["bf16x3"], sizes
+    assert 1.7 < sizes["f16x3"] / sizes["bf16"] < 2.1 and sizes["f16x3"] == sizes["bf16x3"] == sizes["f16x3a"], sizes
     assert max(sizes.values()) < 40 * 2 ** 30, sizes
 
 
