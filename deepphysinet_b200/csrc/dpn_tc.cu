@@ -1172,8 +1172,8 @@ struct WgradWork {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Weight gradients of the split modes: same contraction, restructured around what limited wgrad_kernel<2> (one 200 KB stage per SM:
-// load and MMA strictly alternate, 3.8 TB/s where the same access pattern reaches 5.5 TB/s with two resident CTAs).  The kernel is
+// Weight gradients: K = points contractions of the tiles pass 1 / pass 2 stored (round 1 ran them with one 200 KB stage per SM - load
+// and MMA strictly alternating, 3.8 TB/s).  The kernel is
 // HBM-bound (it reads every operand tile pass 1 / pass 2 wrote), so the structure follows the bytes:
 //   * tiles are stored [point quarter][k-core][32 rows][16 B] (gp_off), so a 32-point quarter of every operand is contiguous; THREE
 //     stages of 73 KB: the bulk loads of quarter-tiles i+1, i+2 run under the MMAs of quarter-tile i;

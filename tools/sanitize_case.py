@@ -1,5 +1,5 @@
 """One small fused call per split-mode kernel set, for compute-sanitizer (tools/gpu_sanitize.sh): N = 300 query points, B = 2,
-f16x3 (pass1_ts_kernel, pass2z_kernel, wgrad2_kernel) and bf16 (pass1_kernel, pass2_kernel, wgrad_kernel); prints a checksum."""
+f16x3 and bf16 (the PL = 2 and PL = 1 instantiations of pass1_ts_kernel, pass2z_kernel, wgrad2_kernel); prints a checksum."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
