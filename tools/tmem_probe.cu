@@ -1,8 +1,9 @@
 // TMEM -> register bandwidth probe (tcgen05.ld.32x32b.x32): how many bytes per clock can the epilogue warps pull?
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc tools/tmem_probe.cu -o tools/bin/tmem_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc -I tools tools/tmem_probe.cu -o tools/bin/tmem_probe
 #include <cstdio>
 #include <cstdlib>
 #include "dpn_umma.cuh"
+#include "probe_extra.cuh"
 using namespace dpn::umma;
 
 __global__ void __launch_bounds__(512, 1) probe(long long* out, float* sink, int nwarps, int reps, int batch) {

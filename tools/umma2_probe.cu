@@ -2,7 +2,7 @@
 // each CTA holds its A tile [128 x K] and HALF of B ([N/2 x K], rows r*N/2 ...), the leader issues the MMAs, the commit is
 // multicast to both CTAs, each CTA reads its own D [128 x N] from its TMEM.  Also exercises a remote mbarrier arrive
 // (peer -> leader) before the leader may issue.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc tools/umma2_probe.cu -o tools/bin/umma2_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc -I tools tools/umma2_probe.cu -o tools/bin/umma2_probe
 //   ./umma2_probe <mode>     mode 0: both CTAs alloc/dealloc with cta_group::2 ; mode 1: N = 192 ; mode 2: fp16 operands ; mode 3: throughput
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "dpn_umma.cuh"
+#include "probe_extra.cuh"
 
 using namespace dpn::umma;
 

@@ -1,5 +1,5 @@
 // Hardware probe for the hand-rolled tcgen05 plumbing in deepphysinet_b200/csrc/dpn_umma.cuh.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc tools/umma_probe.cu -o gpurun_out/umma_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc -I tools tools/umma_probe.cu -o gpurun_out/umma_probe
 //   ./umma_probe <mode>
 // mode 0  K-major A,B   (LBO = k-core stride, SBO = 8-row-group stride)    <- what the kernels assume
 // mode 1  K-major A,B   with LBO/SBO swapped                                (must FAIL if 0 is right)
@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "dpn_umma.cuh"
+#include "probe_extra.cuh"
 
 using namespace dpn::umma;
 

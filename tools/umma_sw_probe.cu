@@ -3,7 +3,7 @@
 // M=128 N=256 K=16 MMA = the tensor-pipe floor when the issue loop is lean (the 152.4 of tools/umma_probe.cu mode 5 was that
 // probe's branchy single-lane loop).  The swizzled modes here compute correct results but their timings are issue-bound by the
 // runtime divisions in sw_desc() - do not read them as hardware rates.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc tools/umma_sw_probe.cu -o tools/bin/umma_sw_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc -I tools tools/umma_sw_probe.cu -o tools/bin/umma_sw_probe
 //   ./umma_sw_probe <swizzle bytes: 0 | 32 | 64 | 128> <reps>
 // Layout of a [rows x 64] 16-bit tile with swizzle width Wb: K is cut into slabs of Wb/2 elements; inside a slab row r starts at
 // r * Wb and the 16-byte chunk index is XORed with the address bits [7, 7 + log2(Wb/16)) (the Swizzle<B,4,3> pattern), slabs are
@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "dpn_umma.cuh"
+#include "probe_extra.cuh"
 
 using namespace dpn::umma;
 

@@ -1,7 +1,7 @@
 // Hardware probe for the TS form of tcgen05.mma: A operand in TENSOR MEMORY (written by the CTA's own threads with tcgen05.st),
 // B operand in shared memory (no-swizzle K-major tile as everywhere in dpn_tc.cu), D in TMEM.
 // A [128 x K] bf16 is laid out lane = row, 32-bit column j holds elements (2j, 2j+1) -> K/2 columns; D uses columns 256...
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc tools/umma_ts_probe.cu -o tools/bin/umma_ts_probe
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I deepphysinet_b200/csrc -I tools tools/umma_ts_probe.cu -o tools/bin/umma_ts_probe
 //   ./umma_ts_probe <mode>     mode 0: correctness (K = 64) ; mode 1: throughput (256 x K = 64, back to back)
 #include <cstdio>
 #include <cstdlib>
@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "dpn_umma.cuh"
+#include "probe_extra.cuh"
 
 using namespace dpn::umma;
 
@@ -30,7 +31,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void probe_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a_tmem),
                "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(160, 1) probe(Params p) {
     for (int rep = 0; rep < p.reps; ++rep)
       for (int ks = 0; ks < K / 16; ++ks) {
         const uint64_t bd = smem_desc(smem_u32(sB) + ks * 2 * N * 16, N * 16, 128);
-        mma_ts(tbase + 256, tbase + ks * 8, bd, idesc, (rep | ks) ? 1u : 0u);       // 16 bf16 = 8 columns per K step
+        probe_mma_ts(tbase + 256, tbase + ks * 8, bd, idesc, (rep | ks) ? 1u : 0u);       // 16 bf16 = 8 columns per K step
       }
     mma_commit(&bar_mma);
     mbar_wait(&bar_mma, 0);
